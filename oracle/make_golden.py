@@ -1,0 +1,192 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates `tests/golden/*.pt` by running the REFERENCE ITSELF
+(imported read-only from /root/reference through oracle/ref_import.py) on seeded synthetic
+inputs.  Run in the build container (the reference tree is absent on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+Fixtures are small (inputs are regenerated from seeds at test time; only reference OUTPUTS
+and a weight checksum are stored).  The parameterisations include the ones the reference's
+own print-style tests use (tests/modeling/stereo/cost_processors/utils/test_cat_fms.py:26-40,
+tests/modeling/stereo/disp_predictors/test_disp_predictors.py:42-77).
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_import  # noqa: E402
+import seeded  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+VOLUME_CASES = [
+    # name, B, C, H, W, max_disp, start_disp, dilation
+    ("ref_test", 1, 1, 3, 4, 5, -2, 2),        # the reference test's own parameterisation
+    ("plain", 2, 4, 5, 16, 6, 0, 1),
+    ("dilated", 1, 3, 4, 20, 9, 0, 2),
+    ("negstart", 1, 2, 3, 12, 7, -3, 1),
+    ("odd_lin", 1, 2, 2, 24, 10, 0, 3),        # (max_disp-1) % dilation != 0: truncated linspace
+    ("wide", 1, 2, 2, 6, 9, -4, 1),            # |d| reaches W-1 and beyond the image
+    ("cfg1ish", 1, 8, 6, 32, 12, 0, 1),
+]
+
+
+def volume_inputs(name, B, C, H, W):
+    if name == "ref_test":
+        left = torch.linspace(1, H * W, H * W).reshape(1, 1, H, W)
+        right = torch.linspace(H * W + 1, H * W * 2, H * W).reshape(1, 1, H, W)
+        return left, right
+    return seeded.feature_pair(B, C, H, W, seed=len(name) * 7 + C)
+
+
+def gen_volumes():
+    CAT, DIF = ref_import.ref_funcs()
+    out = {}
+    for name, B, C, H, W, md, sd, dil in VOLUME_CASES:
+        l, r = volume_inputs(name, B, C, H, W)
+        kw = dict(max_disp=md, start_disp=sd, dilation=dil)
+        rec = dict(params=(B, C, H, W, md, sd, dil))
+        rec["cat"] = CAT["default"](l, r, **kw)
+        rec["dif"] = DIF["default"](l, r, **kw)
+        if H > 1 and W > 1 and rec["cat"].shape[2] > 1:
+            rec["fast_cat"] = CAT["fast_mode"](l, r, **kw)
+            rec["fast_dif"] = DIF["fast_mode"](l, r, **kw)
+            rec["fast_dif_norm"] = DIF["fast_mode"](l, r, normalize=True, p=1.0, **kw)
+            g = torch.Generator().manual_seed(5)
+            D = rec["cat"].shape[2]
+            ds = torch.rand(B, D, H, W, generator=g) * md + sd
+            rec["disp_sample"] = ds
+            rec["fast_cat_sampled"] = CAT["fast_mode"](l, r, disp_sample=ds, **kw)
+        out[name] = rec
+    torch.save(out, os.path.join(OUT, "volumes.pt"))
+    print("volumes.pt", len(out))
+
+
+PRED_CASES = [
+    # name, B, D(max_disp), H, W, start, dilation, alpha, normalize
+    ("ref_test_ones", 1, 9, 2, 2, -4, 2, 1.0, True),
+    ("plain", 2, 12, 5, 7, 0, 1, 1.0, True),
+    ("alpha", 1, 16, 4, 6, 0, 1, 3.0, True),
+    ("nonorm", 1, 8, 3, 5, 2, 1, 1.0, False),
+    ("dil3", 1, 20, 3, 4, -5, 3, 0.5, True),
+    ("d192", 1, 192, 4, 8, 0, 1, 1.0, True),
+]
+
+
+def gen_predictors():
+    ref_import.install()
+    from dmb.modeling.stereo.disp_predictors.builder import PREDICTORS
+    out = {}
+    for name, B, md, H, W, sd, dil, alpha, norm in PRED_CASES:
+        D = (md + dil - 1) // dil
+        if name == "ref_test_ones":
+            cost = torch.ones(B, D, H, W)
+        else:
+            g = torch.Generator().manual_seed(D * 31 + H)
+            cost = torch.randn(B, D, H, W, generator=g) * 2.0
+        rec = dict(params=(B, md, H, W, sd, dil, alpha, norm), cost=cost)
+        kw = dict(max_disp=md, start_disp=sd, dilation=dil, alpha=alpha, normalize=norm)
+        rec["DEFAULT"] = PREDICTORS["DEFAULT"](**kw)(cost)
+        rec["FASTER"] = PREDICTORS["FASTER"](**kw)(cost).detach()
+        g = torch.Generator().manual_seed(3)
+        ds = torch.rand(B, D, H, W, generator=g) * md
+        rec["disp_sample"] = ds
+        rec["DEFAULT_sampled"] = PREDICTORS["DEFAULT"](**kw)(cost, disp_sample=ds)
+        for radius, rdil in ((1, 1), (2, 1), (2, 2)):
+            rec["LOCAL_r%d_d%d" % (radius, rdil)] = PREDICTORS["LOCAL"](
+                radius=radius, radius_dilation=rdil, **kw)(cost)
+        out[name] = rec
+    torch.save(out, os.path.join(OUT, "predictors.pt"))
+    print("predictors.pt", len(out))
+
+
+def build_ref_processor(agg_type, feat_disp, max_disp):
+    cfg = ref_import.load_config("configs/PSMNet/scene_flow.py")
+    cfg.model.max_disp = max_disp
+    cfg.model.cost_processor.cost_computation.max_disp = feat_disp
+    cfg.model.cost_processor.cost_aggregator.max_disp = max_disp
+    cfg.model.cost_processor.cost_aggregator.type = agg_type
+    cfg.model.disp_predictor.max_disp = max_disp
+    proc = ref_import.ref_cost_processor(cfg).eval()
+    pred = ref_import.ref_disp_predictor(cfg).eval()
+    return proc, pred
+
+
+def gen_aggregators():
+    """Config 1: features [1,32,16,32], cost_computation.max_disp=12,
+    aggregator/predictor max_disp=48.  Seeded weights (plain and sharpened), randomised BN."""
+    out = {}
+    for agg_type in ("PSMNet", "AcfNet"):
+        proc, pred = build_ref_processor(agg_type, 12, 48)
+        entries = seeded.aggregator_entries(agg_type, 64)
+        ref_sd = proc.aggregator.state_dict()
+        assert [k for k, _, _ in entries] == list(ref_sd.keys()), "state-dict key order differs from reference"
+        for k, shape, _ in entries:
+            assert tuple(ref_sd[k].shape) == tuple(shape), (k, ref_sd[k].shape, shape)
+        for variant, seed, sharpen, shift in (("plain", 0, 1.0, None), ("sharp", 1, 4.0, 5)):
+            sd = seeded.seeded_state_dict(entries, seed=seed, sharpen=sharpen)
+            proc.aggregator.load_state_dict(sd)
+            l, r = seeded.feature_pair(1, 32, 16, 32, seed=100 + seed, scale=0.5, shift=shift)
+            with torch.no_grad():
+                costs = proc(l, r)
+                disps = [pred(c) for c in costs]
+            rec = dict(seed=seed, sharpen=sharpen, shift=shift, weight_checksum=seeded.checksum(sd),
+                       disps=[d.clone() for d in disps],
+                       # strided sample of the full-resolution costs (keeps the fixture small)
+                       cost_samples=[c[:, ::3, ::4, ::4].clone() for c in costs],
+                       cost_absmax=[float(c.abs().max()) for c in costs])
+            out["%s_%s" % (agg_type, variant)] = rec
+            print(agg_type, variant, "disp mean/std", float(disps[0].mean()), float(disps[0].std()))
+    torch.save(out, os.path.join(OUT, "aggregators.pt"))
+    print("aggregators.pt", len(out))
+
+
+def gen_hourglass():
+    """A bare Hourglass (cost_processors/utils/hourglass.py) with presqu/postsqu given."""
+    ref_import.install()
+    from dmb.modeling.stereo.cost_processors.utils.hourglass import Hourglass
+    hg = Hourglass(in_planes=32, batch_norm=True).eval()
+    entries = []
+    seeded._hourglass(entries, "hg", 32, bias=False)
+    entries = [(k[3:], s, r) for k, s, r in entries]
+    sd = seeded.seeded_state_dict(entries, seed=7)
+    assert list(sd.keys()) == list(hg.state_dict().keys())
+    hg.load_state_dict(sd)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 32, 8, 8, 12, generator=g)
+    pre = torch.randn(1, 64, 4, 4, 6, generator=g)
+    post = torch.randn(1, 64, 4, 4, 6, generator=g)
+    with torch.no_grad():
+        o1 = hg(x, None, None)
+        o2 = hg(x, pre, post)
+    torch.save(dict(weight_checksum=seeded.checksum(sd), first=[t.clone() for t in o1],
+                    second=[t.clone() for t in o2]), os.path.join(OUT, "hourglass.pt"))
+    print("hourglass.pt")
+
+
+def gen_epe():
+    # the package __init__ chain pulls visualisation deps; load the single file instead
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_pixel_error", os.path.join(ref_import.REFERENCE_ROOT, "dmb/data/datasets/evaluation/stereo/pixel_error.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    calc_error = mod.calc_error
+    g = torch.Generator().manual_seed(2)
+    gt = torch.rand(1, 1, 16, 24, generator=g) * 220 - 10
+    est = gt + torch.randn(1, 1, 16, 24, generator=g)
+    e = calc_error(est, gt, 0, 192)
+    torch.save(dict(gt=gt, est=est, epe=float(e["epe"])), os.path.join(OUT, "epe.pt"))
+    print("epe.pt", float(e["epe"]))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    gen_volumes()
+    gen_predictors()
+    gen_hourglass()
+    gen_epe()
+    gen_aggregators()

@@ -1,0 +1,136 @@
+"""Pins the CPU oracle (oracle/dmb_oracle.py) against outputs of the reference itself
+(tests/golden/*.pt, produced by oracle/make_golden.py).  CPU only."""
+import os
+
+import pytest
+import torch
+
+import dmb_oracle as O
+import seeded
+from make_golden import VOLUME_CASES, PRED_CASES, volume_inputs
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+@pytest.mark.parametrize("case", [c[0] for c in VOLUME_CASES])
+def test_volumes_match_reference(golden_dir, case):
+    rec = _load(golden_dir, "volumes.pt")[case]
+    B, C, H, W, md, sd, dil = rec["params"]
+    l, r = volume_inputs(case, B, C, H, W)
+    kw = dict(max_disp=md, start_disp=sd, dilation=dil)
+    assert torch.equal(O.cat_volume(l, r, **kw), rec["cat"])          # pure copy: bit exact
+    assert torch.equal(O.dif_volume(l, r, **kw), rec["dif"])          # one fp32 subtract: bit exact
+    if "fast_cat" in rec:
+        torch.testing.assert_close(O.fast_cat_volume(l, r, **kw), rec["fast_cat"], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(O.fast_dif_volume(l, r, **kw), rec["fast_dif"], atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(O.fast_dif_volume(l, r, normalize=True, p=1.0, **kw), rec["fast_dif_norm"],
+                                   atol=1e-5, rtol=1e-5)
+        got = O.fast_cat_volume(l, r, disp_sample=rec["disp_sample"], **kw)
+        torch.testing.assert_close(got, rec["fast_cat_sampled"], atol=1e-5, rtol=1e-5)
+
+
+def test_reference_test_vector_by_hand(golden_dir):
+    """The reference's own parameterisation (test_cat_fms.py:26-40): disparities -2, 0, 2."""
+    assert O.disp_indices(5, -2, 2) == [-2, 0, 2]
+    rec = _load(golden_dir, "volumes.pt")["ref_test"]
+    cat = rec["cat"]
+    l, r = volume_inputs("ref_test", 1, 1, 3, 4)
+    # d=+2: columns 2..3 hold L[x], R[x-2]
+    assert torch.equal(cat[0, 0, 2, :, 2:], l[0, 0, :, 2:]) and torch.equal(cat[0, 1, 2, :, 2:], r[0, 0, :, :2])
+    assert float(cat[0, :, 2, :, :2].abs().sum()) == 0.0
+    # d=-2: columns 0..1 hold L[x], R[x+2]
+    assert torch.equal(cat[0, 1, 0, :, :2], r[0, 0, :, 2:])
+
+
+@pytest.mark.parametrize("case", [c[0] for c in PRED_CASES])
+def test_predictors_match_reference(golden_dir, case):
+    rec = _load(golden_dir, "predictors.pt")[case]
+    B, md, H, W, sd, dil, alpha, norm = rec["params"]
+    cost = rec["cost"]
+    kw = dict(max_disp=md, start_disp=sd, dilation=dil, alpha=alpha, normalize=norm)
+    got = O.soft_argmin(cost, **kw)
+    torch.testing.assert_close(got, rec["DEFAULT"], atol=2e-5, rtol=1e-5)
+    torch.testing.assert_close(got, rec["FASTER"], atol=2e-5, rtol=1e-5)
+    torch.testing.assert_close(O.soft_argmin(cost, disp_sample=rec["disp_sample"], **kw), rec["DEFAULT_sampled"],
+                               atol=2e-5, rtol=1e-5)
+    for radius, rdil in ((1, 1), (2, 1), (2, 2)):
+        got = O.local_soft_argmin(cost, md, radius, sd, dil, rdil, alpha)
+        torch.testing.assert_close(got, rec["LOCAL_r%d_d%d" % (radius, rdil)], atol=2e-5, rtol=1e-5)
+
+
+def test_uniform_cost_regresses_to_zero(golden_dir):
+    """Known answer implied by test_disp_predictors.py:42-77: all-ones cost, samples -4..4."""
+    rec = _load(golden_dir, "predictors.pt")["ref_test_ones"]
+    assert float(rec["DEFAULT"].abs().max()) < 1e-6
+    assert float(O.soft_argmin(rec["cost"], 9, -4, 2).abs().max()) < 1e-6
+
+
+def test_hourglass_matches_reference(golden_dir):
+    rec = _load(golden_dir, "hourglass.pt")
+    entries = []
+    seeded._hourglass(entries, "hg", 32, bias=False)
+    sd = seeded.seeded_state_dict([(k[3:], s, r) for k, s, r in entries], seed=7)
+    assert abs(seeded.checksum(sd) - rec["weight_checksum"]) < 1e-6 * rec["weight_checksum"]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 32, 8, 8, 12, generator=g)
+    pre = torch.randn(1, 64, 4, 4, 6, generator=g)
+    post = torch.randn(1, 64, 4, 4, 6, generator=g)
+    sd = {"hg." + k: v for k, v in sd.items()}
+    for got, want in zip(O.hourglass(sd, "hg", x), rec["first"]):
+        torch.testing.assert_close(got, want, atol=1e-4, rtol=1e-4)
+    for got, want in zip(O.hourglass(sd, "hg", x, pre, post), rec["second"]):
+        torch.testing.assert_close(got, want, atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("agg", ["PSMNet", "AcfNet"])
+@pytest.mark.parametrize("variant", ["plain", "sharp"])
+def test_aggregators_match_reference(golden_dir, agg, variant):
+    rec = _load(golden_dir, "aggregators.pt")["%s_%s" % (agg, variant)]
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries(agg, 64), seed=rec["seed"], sharpen=rec["sharpen"])
+    assert abs(seeded.checksum(sd) - rec["weight_checksum"]) < 1e-6 * rec["weight_checksum"]
+    l, r = seeded.feature_pair(1, 32, 16, 32, seed=100 + rec["seed"], scale=0.5, shift=rec["shift"])
+    raw = O.cat_volume(l, r, 12, 0, 1)
+    fn = O.psm_aggregator if agg == "PSMNet" else O.acf_aggregator
+    costs = fn(sd, raw, 48)
+    for c, want, amax in zip(costs, rec["cost_samples"], rec["cost_absmax"]):
+        torch.testing.assert_close(c[:, ::3, ::4, ::4], want, atol=1e-5 * max(1.0, amax), rtol=1e-4)
+    for c, want in zip(costs, rec["disps"]):
+        got = O.soft_argmin(c, 48)
+        assert float((got - want).abs().max()) < 1e-3   # the north-star tolerance, oracle vs reference
+
+
+def test_trilinear_restatement_equals_interpolate():
+    g = torch.Generator().manual_seed(4)
+    c = torch.randn(1, 1, 5, 6, 7, generator=g)
+    want = torch.nn.functional.interpolate(c, [20, 24, 28], mode="trilinear", align_corners=True)
+    torch.testing.assert_close(O.trilinear_up(c, (20, 24, 28)), want, atol=1e-5, rtol=1e-5)
+
+
+def test_epe_matches_reference(golden_dir):
+    rec = _load(golden_dir, "epe.pt")
+    assert abs(O.epe(rec["est"], rec["gt"], 0, 192) - rec["epe"]) < 1e-6
+
+
+def test_spn_scan_forward_backward_consistent():
+    """spn_scan (in-place restatement) vs its autograd twin, all four directions."""
+    g = torch.Generator().manual_seed(9)
+    X = torch.randn(2, 3, 5, 6, generator=g)
+    G = [torch.rand(2, 3, 5, 6, generator=g) * 0.3 for _ in range(3)]
+    for horizontal in (True, False):
+        for reverse in (False, True):
+            a = O.spn_scan(X, *G, horizontal, reverse)
+            b = O._spn_autograd(X, *G, horizontal, reverse)
+            torch.testing.assert_close(a, b, atol=1e-6, rtol=1e-6)
+
+
+def test_sga_lga_basic_properties():
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(1, 2, 6, 5, 7, generator=g)
+    # guidance with only the w0 tap non-zero => A_r = x for all r => output x
+    gd = torch.zeros(1, 4, 5, 2, 5, 7); gd[:, :, 0] = 3.0
+    torch.testing.assert_close(O.sga(x, gd.view(1, 40, 5, 7)), x)
+    c = torch.randn(1, 6, 5, 7, generator=g)
+    gl = torch.zeros(1, 3, 5, 5, 5, 7); gl[:, 0, 2, 2] = 2.0        # centre tap only
+    torch.testing.assert_close(O.lga(c, gl.view(1, 75, 5, 7)), c)
