@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- disparity maps/sec of the PSMNet forward (960x540 padded to 544x960, D=192).
+
+    python bench.py --gpus N --steps K --warmup W            # ours (CUDA, through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # CPU oracle port on the host cores
+
+One "step" = one full forward of one batch of synthetic stereo pairs per GPU: PSMNet backbone
+(torch/cuDNN, outside the hot-path scope) -> cat cost volume -> PSMAggregator -> 3x soft-argmin
+(the hot path: hand-written CUDA).  Multi-GPU: independent pairs per rank (weak scaling), no
+data-path collective -- the path shards on the batch axis.
+
+Prints ONE JSON line on rank 0 (see the keys at the bottom).  Timing: CUDA events on the launching
+stream, barrier + synchronize on both sides, max over ranks.  No reference-tree access at run time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+H_IMG, W_IMG, H_PAD, MAX_DISP = 540, 960, 544, 192
+H4, W4, D4 = H_PAD // 4, W_IMG // 4, MAX_DISP // 4
+
+
+# ----------------------------------------------------------------------------------------------
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], tflops_burst=p["bf16_tflops"],
+                    tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+def trunk_macs(B=1, d=D4, h=H4, w=W4):
+    """Multiply-accumulates of the PSMAggregator trunk."""
+    n4 = d * h * w
+    n8 = (d // 2) * (h // 2) * (w // 2)
+    n16 = (d // 4) * (h // 4) * (w // 4)
+    t = 27
+    macs = n4 * t * (64 * 32 + 32 * 32 * 3)                          # dres0, dres1
+    hg = n8 * t * 32 * 64 + n8 * t * 64 * 64 + n16 * t * 64 * 64 * 2  # conv1..conv4
+    hg += n16 * t * 64 * 64 + n8 * t * 64 * 32                        # conv5, conv6 (per INPUT voxel)
+    macs += 3 * hg
+    macs += 3 * (n4 * t * 32 * 32 + n4 * t * 32)                      # classif
+    return B * macs
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2]); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm), power_w_max=(max(power) if power else None))
+
+
+def synth_images(B, seed, device=None):
+    """960x540 synthetic pair, top-padded to 544 like the reference's eval transform
+    (dmb/data/transforms/stereo_trans.py:92-117): right = left shifted by a smooth disparity."""
+    g = torch.Generator().manual_seed(seed)
+    left = torch.rand(B, 3, H_IMG, W_IMG, generator=g)
+    shift = 24
+    right = torch.roll(left, -shift, dims=3) + 0.01 * torch.randn(B, 3, H_IMG, W_IMG, generator=g)
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(1, 3, 1, 1)
+    pad = (0, 0, H_PAD - H_IMG, 0)
+    left = torch.nn.functional.pad((left - mean) / std, pad)
+    right = torch.nn.functional.pad((right - mean) / std, pad)
+    return left.contiguous(), right.contiguous()
+
+
+def build_model(device, engine, precision):
+    import seeded
+    import densematchingbenchmark_b200 as P
+    from densematchingbenchmark_b200.modeling.stereo.backbones import PSMNetBackbone
+    cfg = P.ConfigDict(model=dict(
+        batch_norm=True,
+        cost_processor=dict(type="Concatenation",
+                            cost_computation=dict(type="default", max_disp=D4, start_disp=0, dilation=1),
+                            cost_aggregator=dict(type="PSMNet", max_disp=MAX_DISP, in_planes=64)),
+        disp_predictor=dict(type="FASTER", max_disp=MAX_DISP, start_disp=0, dilation=1, alpha=1.0, normalize=True)))
+    torch.manual_seed(0)
+    backbone = PSMNetBackbone(3, True)
+    for m in backbone.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.normal_(0, 0.05); m.running_var.uniform_(0.8, 1.2)
+    proc = P.build_cost_processor(cfg)
+    pred = P.build_disp_predictor(cfg)
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=0, sharpen=4.0)
+    proc.aggregator.load_state_dict(sd)
+    proc.aggregator.engine = engine
+    proc.aggregator.precision = precision
+    return backbone.to(device).eval(), proc.to(device).eval(), pred.to(device).eval(), sd
+
+
+CPU_BAND = 256   # image rows of the CPU sample (the SPP branch's 64x64 pooling needs >= 256)
+
+
+def cpu_forward_sample(sd, threads, band=CPU_BAND):
+    """The oracle port of the full forward (torch-CPU backbone + oracle hot path) on a band of
+    `band` image rows at full width and disparity range.  Returns seconds."""
+    import dmb_oracle as O
+    from densematchingbenchmark_b200.modeling.stereo.backbones import PSMNetBackbone
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    backbone = PSMNetBackbone(3, True).eval()
+    g = torch.Generator().manual_seed(5)
+    left = torch.randn(1, 3, band, W_IMG, generator=g)
+    right = torch.roll(left, -24, dims=3)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        lf, rf = backbone(left, right)
+        O.psm_hot_path(sd, lf, rf, MAX_DISP, prefix="")
+    return time.perf_counter() - t0
+
+
+# ----------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path, timed on the host cores.
+    The reference tree cannot travel to the GPU box (python, un-vendored deps), so this is the
+    oracle port (kind 'port'), pinned to the reference by tests/golden."""
+    if rank != 0:
+        return
+    import seeded
+    threads = os.cpu_count() or 1
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=0, sharpen=4.0)
+    frac = CPU_BAND / float(H_PAD)
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_forward_sample(sd, threads)
+    times = [cpu_forward_sample(sd, threads) for _ in range(args.steps)]
+    ms = 1e3 * sum(times) / len(times)
+    value = frac / (ms / 1e3)                   # pairs per second, extrapolated from the band by rows
+    line = {
+        "impl": "reference", "metric": "disparity maps/sec (PSMNet, 960x540, D=192)", "value": value,
+        "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "PSMNet full forward (backbone + cat volume + PSMAggregator + 3x soft-argmin), 544x960 "
+                               "D=192, CPU fp32, each step = a %d-of-%d image-row band, throughput extrapolated by rows"
+                               % (CPU_BAND, H_PAD)},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                         "sample": "%d of %d image rows, full width/disparity, backbone + hot path" % (CPU_BAND, H_PAD)},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from densematchingbenchmark_b200 import _cabi
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    backbone, proc, pred, sd = build_model(device, args.engine, args.precision)
+    B = args.batch
+    left_h, right_h = synth_images(B, seed=1234 + rank)
+    left_h, right_h = left_h.pin_memory(), right_h.pin_memory()
+    left, right = left_h.to(device), right_h.to(device)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def forward(l, r, marks=None):
+        with torch.no_grad():
+            if marks is not None: marks.append(ev()); marks[-1].record()
+            lf, rf = backbone(l, r)
+            lf, rf = lf.float().contiguous(), rf.float().contiguous()
+            if marks is not None: marks.append(ev()); marks[-1].record()
+            raw = proc.func(lf, rf, **proc.default_args)
+            if marks is not None: marks.append(ev()); marks[-1].record()
+            costs = proc.aggregator(raw)
+            if marks is not None: marks.append(ev()); marks[-1].record()
+            disps = [pred(c) for c in costs]
+            if marks is not None: marks.append(ev()); marks[-1].record()
+        return disps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(3, args.warmup)):
+        forward(left, right)
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier(); torch.cuda.synchronize()
+    n0 = _cabi.launch_count()
+    all_marks = []
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    for _ in range(args.steps):
+        marks = []
+        forward(left, right, marks)
+        all_marks.append(marks)
+    t_end.record()
+    torch.cuda.synchronize(); barrier()
+    launches = _cabi.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = t_start.elapsed_time(t_end) / args.steps
+    seg = [0.0] * 4
+    for marks in all_marks:
+        for i in range(4):
+            seg[i] += marks[i].elapsed_time(marks[i + 1])
+    seg = [s / args.steps for s in seg]                      # backbone, cat, aggregator, regress (ms)
+
+    # ---- end-to-end through the public API with host buffers -----------------------------------
+    barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out_h = None
+    for _ in range(args.steps):
+        l = left_h.to(device, non_blocking=True)
+        r = right_h.to(device, non_blocking=True)
+        disps = forward(l, r)
+        out_h = disps[0].cpu()                               # D2H of the step's result (forces completion)
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+
+    pk = peaks()
+    macs = trunk_macs(B)
+    agg_ms = seg[2]
+    passes = 3 if (args.precision == "bf16x3" and proc.aggregator._use_tc(torch.empty(B, 64, D4, H4, W4, device=device))) else 1
+    achieved_tflops = 2.0 * macs / (agg_ms * 1e-3) / 1e12
+    cat_bytes = B * (2 * 32 * H4 * W4 + 64 * D4 * H4 * W4) * 4
+    roofline = {"bound": "tensor", "kernel": "PSMAggregator trunk (25 conv launches + 3 upsample), timed as one span",
+                "achieved": achieved_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved_tflops / pk["tflops_sustained"], "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "algorithmic_flops_per_step": 2.0 * macs, "mma_passes": passes, "traffic": None}
+    roofline_cat = {"bound": "hbm", "kernel": "cat_volume (fp32 NCDHW)", "achieved": cat_bytes / (seg[1] * 1e-3) / 1e9,
+                    "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": cat_bytes / (seg[1] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                    "algorithmic_bytes_per_step": cat_bytes, "traffic": None}
+
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cpu_forward_sample(sd, threads)                      # warm-up
+        dt = min(cpu_forward_sample(sd, threads) for _ in range(2))
+        cpu_base = {"value": (CPU_BAND / float(H_PAD)) / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                    "sample": "backbone + hot path on %d of %d image rows (full width/disparity), best of 2, %.1f s each"
+                              % (CPU_BAND, H_PAD, dt)}
+
+    pairs = B * world
+    line = {
+        "metric": "disparity maps/sec (PSMNet, 960x540, D=192)", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": ("bf16x3 (split-bf16 tensor-core MMAs, fp32 accumulate)" if passes == 3 else
+                  ("bf16" if proc.aggregator._use_tc(torch.empty(B, 64, D4, H4, W4, device=device)) else "f32")),
+        "data": "synthetic",
+        "config": {"workload": "PSMNet full forward: backbone (torch/cuDNN, out of hot-path scope) + cat volume + "
+                               "PSMAggregator + 3x FasterSoftArgmin; 960x540 top-padded to 544x960, D=192",
+                   "pairs_per_gpu": B, "parallelism": "replicas x%d (batch sharding, no collective)" % world,
+                   "engine": args.engine, "precision": args.precision,
+                   "l2": "intermediates (401 MB cat volume, 200 MB activations) exceed the 126 MB L2; no explicit flush"},
+        "segments_ms": {"backbone": seg[0], "cat_volume": seg[1], "aggregator": seg[2], "regress": seg[3]},
+        "hot_path": {"ms": seg[1] + seg[2] + seg[3], "pairs_per_s": B / ((seg[1] + seg[2] + seg[3]) * 1e-3)},
+        "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(2 * left_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "roofline_cat_volume": roofline_cat, "clocks": clocks,
+    }
+    if cpu_base is not None:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step")
+    ap.add_argument("--engine", default="auto", choices=["auto", "tc", "direct"])
+    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

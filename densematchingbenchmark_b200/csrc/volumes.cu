@@ -1,0 +1,472 @@
+// Raw cost-volume builders: concatenation, difference, group-wise correlation, warped
+// ("fast_mode") variants, and the channels-last bf16 volume feeding the tensor-core trunk.
+//
+// Reference behaviour restated by oracle/dmb_oracle.py (cat_volume, dif_volume, gwc_volume,
+// warp_volume); reference sources: dmb/modeling/stereo/cost_processors/utils/cat_fms.py:7-82,
+// dif_fms.py:7-86, dmb/modeling/stereo/layers/inverse_warp_3d.py:4-52.
+//
+// All of these are HBM-write-bound: one feature row (<= a few KB) fans out into D rows of the
+// volume.  The row is staged ONCE per CTA in shared memory with a 1-D bulk async copy (TMA
+// engine, UBLKCP) and re-read from there for every disparity; the volume is written with
+// 16-byte streaming stores.
+#include "common.cuh"
+
+namespace dmb {
+
+constexpr int kMaxDisp = 256;
+struct DispList {
+    int d[kMaxDisp];
+};
+
+// valid output columns for integer disparity d (cat_fms.py:36-44)
+__device__ __forceinline__ bool col_valid(int x, int d, int W) { return d >= 0 ? (x >= d) : (x < W + d); }
+
+// ---------------------------------------------------------------------------------------
+// cat / dif volume, NCDHW fp32.
+// One CTA per source row (b, channel, y).  MODE 0: concat (channel index runs over 2C, the
+// CTA copies either the left or the right row); MODE 1: difference (both rows staged).
+// ---------------------------------------------------------------------------------------
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(256) volume_rows_kernel(const float* __restrict__ left,
+                                                          const float* __restrict__ right,
+                                                          float* __restrict__ out, int C, int H, int W, int D,
+                                                          int k0, int Dtotal, DispList dl) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* row_a = reinterpret_cast<float*>(smem_raw);            // left row (or the only row)
+    float* row_b = row_a + ((W + 3) & ~3);                        // right row (MODE 1)
+    __shared__ uint64_t bar;
+
+    const int y = blockIdx.x;
+    const int c = blockIdx.y;
+    const int b = blockIdx.z;
+    const int CO = (MODE == 0) ? 2 * C : C;
+    const bool is_right = (MODE == 0) && (c >= C);
+    const int cs = is_right ? c - C : c;
+    const float* src_a = ((MODE == 0 && is_right) ? right : left) + ((size_t)(b * C + cs) * H + y) * W;
+    const float* src_b = right + ((size_t)(b * C + cs) * H + y) * W;
+
+    if (VEC) {
+        const uint32_t bytes = W * 4;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, MODE == 1 ? 2 * bytes : bytes);
+            bulk_g2s(row_a, src_a, bytes, &bar);
+            if (MODE == 1) bulk_g2s(row_b, src_b, bytes, &bar);
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            row_a[x] = src_a[x];
+            if (MODE == 1) row_b[x] = src_b[x];
+        }
+        __syncthreads();
+    }
+
+    float* out_row0 = out + (((size_t)(b * CO + c) * Dtotal + k0) * H + y) * W;
+    const size_t kstride = (size_t)H * W;
+
+    if (VEC) {
+        const int W4 = W >> 2;
+        for (int i = threadIdx.x; i < D * W4; i += blockDim.x) {
+            const int k = i / W4;
+            const int x = (i - k * W4) << 2;
+            const int d = dl.d[k];
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xx = x + j;
+                float val = 0.f;
+                if (col_valid(xx, d, W)) {
+                    if (MODE == 0)
+                        val = is_right ? row_a[xx - d] : row_a[xx];
+                    else
+                        val = row_a[xx] - row_b[xx - d];
+                }
+                v[j] = val;
+            }
+            st_cs_f4(out_row0 + k * kstride + x, make_float4(v[0], v[1], v[2], v[3]));
+        }
+    } else {
+        for (int i = threadIdx.x; i < D * W; i += blockDim.x) {
+            const int k = i / W;
+            const int xx = i - k * W;
+            const int d = dl.d[k];
+            float val = 0.f;
+            if (col_valid(xx, d, W)) {
+                if (MODE == 0)
+                    val = is_right ? row_a[xx - d] : row_a[xx];
+                else
+                    val = row_a[xx] - row_b[xx - d];
+            }
+            out_row0[k * kstride + xx] = val;
+        }
+    }
+}
+
+template <int MODE>
+static int launch_volume_rows(const float* left, const float* right, float* out, int B, int C, int H, int W,
+                              const int* disp_idx_host, int D, void* stream) {
+    DMB_REQUIRE(left && right && out && disp_idx_host, "volume: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "volume: non-positive dimension");
+    DMB_REQUIRE(H <= 65535 && (MODE == 0 ? 2 * C : C) <= 65535 && B <= 65535, "volume: grid dimension too large");
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(left) | reinterpret_cast<uintptr_t>(right) |
+                                       reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+    const size_t smem = (size_t)((W + 3) & ~3) * 4 * (MODE == 1 ? 2 : 1);
+    DMB_REQUIRE(smem <= 200 * 1024, "volume: feature row too wide (W=%d)", W);
+    if (smem > 48 * 1024) {
+        DMB_CUDA(cudaFuncSetAttribute(volume_rows_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DMB_CUDA(cudaFuncSetAttribute(volume_rows_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 grid(H, MODE == 0 ? 2 * C : C, B);
+    for (int k0 = 0; k0 < D; k0 += kMaxDisp) {
+        DispList dl;
+        const int n = (D - k0 < kMaxDisp) ? D - k0 : kMaxDisp;
+        for (int i = 0; i < n; ++i) {
+            dl.d[i] = disp_idx_host[k0 + i];
+            // |d| >= W: nothing valid; clamp so that index arithmetic stays in range
+            if (dl.d[i] >= W) dl.d[i] = W;
+            if (dl.d[i] <= -W) dl.d[i] = -W;
+        }
+        if (vec)
+            volume_rows_kernel<MODE, true><<<grid, 256, smem, as_stream(stream)>>>(left, right, out, C, H, W, n, k0, D, dl);
+        else
+            volume_rows_kernel<MODE, false><<<grid, 256, smem, as_stream(stream)>>>(left, right, out, C, H, W, n, k0, D, dl);
+        int rc = check_launch("volume_rows_kernel");
+        if (rc) return rc;
+    }
+    return DMB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// group-wise correlation, NCDHW fp32.  One CTA per (b, group, y): the group's CPG left and
+// right rows are staged in shared memory, every thread produces 4 consecutive columns of one
+// disparity row.
+// ---------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) gwc_rows_kernel(const float* __restrict__ left, const float* __restrict__ right,
+                                                       float* __restrict__ out, int C, int G, int H, int W, int D,
+                                                       int k0, int Dtotal, DispList dl) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cpg = C / G;
+    const int Wp = (W + 3) & ~3;
+    float* sl = reinterpret_cast<float*>(smem_raw);   // [cpg][Wp]
+    float* sr = sl + cpg * Wp;                        // [cpg][Wp]
+    __shared__ uint64_t bar;
+
+    const int y = blockIdx.x, g = blockIdx.y, b = blockIdx.z;
+    const size_t plane = (size_t)H * W;
+    const float* l0 = left + ((size_t)(b * C + g * cpg) * H + y) * W;
+    const float* r0 = right + ((size_t)(b * C + g * cpg) * H + y) * W;
+
+    if (VEC) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, 2u * cpg * W * 4u);
+            for (int c = 0; c < cpg; ++c) {
+                bulk_g2s(sl + c * Wp, l0 + c * plane, W * 4, &bar);
+                bulk_g2s(sr + c * Wp, r0 + c * plane, W * 4, &bar);
+            }
+        }
+        mbar_wait(&bar, 0);
+    } else {
+        for (int i = threadIdx.x; i < cpg * W; i += blockDim.x) {
+            const int c = i / W, x = i - c * W;
+            sl[c * Wp + x] = l0[c * plane + x];
+            sr[c * Wp + x] = r0[c * plane + x];
+        }
+        __syncthreads();
+    }
+
+    float* out_row0 = out + (((size_t)(b * G + g) * Dtotal + k0) * H + y) * W;
+    const float inv = (float)cpg;
+    const int W4 = Wp >> 2;
+    for (int i = threadIdx.x; i < D * W4; i += blockDim.x) {
+        const int k = i / W4;
+        const int x = (i - k * W4) << 2;
+        const int d = dl.d[k];
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < cpg; ++c) {
+            const float* lr = sl + c * Wp + x;
+            const float* rr = sr + c * Wp + x - d;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int xx = x + j;
+                if (xx < W && col_valid(xx, d, W)) acc[j] = fmaf(lr[j], rr[j], acc[j]);
+            }
+        }
+        float* o = out_row0 + (size_t)k * plane + x;
+        if (VEC) {
+            st_cs_f4(o, make_float4(acc[0] / inv, acc[1] / inv, acc[2] / inv, acc[3] / inv));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (x + j < W) o[j] = acc[j] / inv;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// warped ("fast_mode") volumes.  One thread per (b, k, y, x); loops over channels.
+// grid_sample arithmetic restated in oracle/dmb_oracle.py:warp_volume.
+// ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) warp_volume_kernel(const float* __restrict__ left, const float* __restrict__ right,
+                                                          const float* __restrict__ disp, float* __restrict__ out,
+                                                          int B, int C, int H, int W, int D, float p) {
+    const size_t total = (size_t)B * D * H * W;
+    const size_t plane = (size_t)H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = i % W;
+        const int y = (i / W) % H;
+        const int k = (i / plane) % D;
+        const int b = i / (plane * D);
+        // same operation order as the reference (inverse_warp_3d.py:36-42, then grid_sample's
+        // un-normalisation ((g+1)*size-1)/2); __f*_rn keeps the compiler from contracting to FMA
+        const float gx = __fsub_rn((float)x, disp[i]);
+        const float nx = __fsub_rn(__fmul_rn(__fdiv_rn(gx, (float)(W - 1)), 2.f), 1.f);
+        const float ny = __fsub_rn(__fmul_rn(__fdiv_rn((float)y, (float)(H - 1)), 2.f), 1.f);
+        const float nz = __fsub_rn(__fmul_rn(__fdiv_rn((float)k, (float)(D - 1)), 2.f), 1.f);
+        const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(nx, 1.f), (float)W), 1.f), 2.f);
+        const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(ny, 1.f), (float)H), 1.f), 2.f);
+        const float iz = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(nz, 1.f), (float)D), 1.f), 2.f);
+        const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+        const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+        const float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+        float wz = 0.f;
+        if (z0 >= 0 && z0 <= D - 1) wz += 1.f - tz;
+        if (z0 + 1 >= 0 && z0 + 1 <= D - 1) wz += tz;
+        const bool vx0 = x0 >= 0 && x0 <= W - 1, vx1 = x0 + 1 >= 0 && x0 + 1 <= W - 1;
+        const bool vy0 = y0 >= 0 && y0 <= H - 1, vy1 = y0 + 1 >= 0 && y0 + 1 <= H - 1;
+        const float w00 = (vx0 && vy0) ? (1.f - tx) * (1.f - ty) * wz : 0.f;
+        const float w01 = (vx1 && vy0) ? tx * (1.f - ty) * wz : 0.f;
+        const float w10 = (vx0 && vy1) ? (1.f - tx) * ty * wz : 0.f;
+        const float w11 = (vx1 && vy1) ? tx * ty * wz : 0.f;
+        const int xa = min(max(x0, 0), W - 1), xb = min(max(x0 + 1, 0), W - 1);
+        const int ya = min(max(y0, 0), H - 1), yb = min(max(y0 + 1, 0), H - 1);
+        float norm_acc = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float* rp = right + (size_t)(b * C + c) * plane;
+            const float t = w00 * __ldg(rp + ya * W + xa) + w01 * __ldg(rp + ya * W + xb) +
+                            w10 * __ldg(rp + yb * W + xa) + w11 * __ldg(rp + yb * W + xb);
+            const float l = (t > 0.f) ? __ldg(left + (size_t)(b * C + c) * plane + y * W + x) : 0.f;
+            if (MODE == 0) {
+                out[(((size_t)(b * 2 * C + c) * D + k) * H + y) * W + x] = l;
+                out[(((size_t)(b * 2 * C + C + c) * D + k) * H + y) * W + x] = t;
+            } else if (MODE == 1) {
+                out[(((size_t)(b * C + c) * D + k) * H + y) * W + x] = l - t;
+            } else {
+                const float a = fabsf(l - t);
+                norm_acc += (p == 1.f) ? a : ((p == 2.f) ? a * a : powf(a, p));
+            }
+        }
+        if (MODE == 2) out[i] = (p == 1.f) ? norm_acc : ((p == 2.f) ? sqrtf(norm_acc) : powf(norm_acc, 1.f / p));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// channels-last bf16 (hi[,lo]) layout helpers and the channels-last cat volume
+// ---------------------------------------------------------------------------------------
+// x: [B,C,S] fp32 (S = D*H*W) -> y: [B,S,C] bf16 hi/lo.  32x32 smem transpose tiles.
+__global__ void __launch_bounds__(256) ncs_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                        __nv_bfloat16* __restrict__ lo, int C, size_t S) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const size_t s0 = (size_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const size_t s = s0 + tx;
+        tile[j][tx] = (c < C && s < S) ? x[((size_t)b * C + c) * S + s] : 0.f;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const size_t s = s0 + j;
+        const int c = c0 + tx;
+        if (s < S && c < C) {
+            __nv_bfloat16 h, l;
+            split_bf16(tile[tx][j], h, l);
+            const size_t o = ((size_t)b * S + s) * C + c;
+            hi[o] = h;
+            if (lo) lo[o] = l;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cl_to_ncs_kernel(const __nv_bfloat16* __restrict__ hi,
+                                                        const __nv_bfloat16* __restrict__ lo, float* __restrict__ y,
+                                                        int C, size_t S) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const size_t s0 = (size_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int j = ty; j < 32; j += 8) {
+        const size_t s = s0 + j;
+        const int c = c0 + tx;
+        float v = 0.f;
+        if (s < S && c < C) {
+            const size_t o = ((size_t)b * S + s) * C + c;
+            v = __bfloat162float(hi[o]);
+            if (lo) v += __bfloat162float(lo[o]);
+        }
+        tile[j][tx] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int c = c0 + j;
+        const size_t s = s0 + tx;
+        if (c < C && s < S) y[((size_t)b * C + c) * S + s] = tile[tx][j];
+    }
+}
+
+// feats: [B,H,W,C] bf16 (channels last); out: [B,D,H,W,2C] bf16.  One thread per 16 bytes
+// (8 channels) of one voxel and plane; every load and store is a 16-byte vector access.
+__global__ void __launch_bounds__(256) cat_volume_cl_kernel(const uint4* __restrict__ l_hi, const uint4* __restrict__ l_lo,
+                                                            const uint4* __restrict__ r_hi, const uint4* __restrict__ r_lo,
+                                                            uint4* __restrict__ o_hi, uint4* __restrict__ o_lo,
+                                                            int B, int C8, int H, int W, int D, DispList dl) {
+    const int V = 2 * C8;                       // 16-byte vectors per voxel
+    const size_t total = (size_t)B * D * H * W * V;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = i % V;
+        size_t r = i / V;
+        const int x = r % W; r /= W;
+        const int y = r % H; r /= H;
+        const int k = r % D;
+        const int b = r / D;
+        const int d = dl.d[k];
+        uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
+        if (col_valid(x, d, W)) {
+            if (v < C8) {
+                const size_t s = (((size_t)b * H + y) * W + x) * C8 + v;
+                h = __ldg(l_hi + s);
+                if (o_lo) l = __ldg(l_lo + s);
+            } else {
+                const size_t s = (((size_t)b * H + y) * W + (x - d)) * C8 + (v - C8);
+                h = __ldg(r_hi + s);
+                if (o_lo) l = __ldg(r_lo + s);
+            }
+        }
+        __stcs(o_hi + i, h);
+        if (o_lo) __stcs(o_lo + i, l);
+    }
+}
+
+}  // namespace dmb
+
+using namespace dmb;
+
+extern "C" int dmb_b200_cat_volume(const float* left, const float* right, float* out, int B, int C, int H, int W,
+                                   const int* disp_idx_host, int D, void* stream) {
+    return launch_volume_rows<0>(left, right, out, B, C, H, W, disp_idx_host, D, stream);
+}
+
+extern "C" int dmb_b200_dif_volume(const float* left, const float* right, float* out, int B, int C, int H, int W,
+                                   const int* disp_idx_host, int D, void* stream) {
+    return launch_volume_rows<1>(left, right, out, B, C, H, W, disp_idx_host, D, stream);
+}
+
+extern "C" int dmb_b200_gwc_volume(const float* left, const float* right, float* out, int B, int C, int H, int W, int G,
+                                   const int* disp_idx_host, int D, void* stream) {
+    DMB_REQUIRE(left && right && out && disp_idx_host, "gwc_volume: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0 && G > 0, "gwc_volume: non-positive dimension");
+    DMB_REQUIRE(C % G == 0, "gwc_volume: C=%d not divisible by groups=%d", C, G);
+    DMB_REQUIRE(H <= 65535 && G <= 65535 && B <= 65535, "gwc_volume: grid dimension too large");
+    const int cpg = C / G;
+    const int Wp = (W + 3) & ~3;
+    const bool vec = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(left) | reinterpret_cast<uintptr_t>(right) |
+                                       reinterpret_cast<uintptr_t>(out)) % 16 == 0);
+    const size_t smem = (size_t)2 * cpg * Wp * 4;
+    DMB_REQUIRE(smem <= 200 * 1024, "gwc_volume: group rows do not fit shared memory (cpg=%d, W=%d)", cpg, W);
+    if (smem > 48 * 1024) {
+        DMB_CUDA(cudaFuncSetAttribute(gwc_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DMB_CUDA(cudaFuncSetAttribute(gwc_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    dim3 grid(H, G, B);
+    for (int k0 = 0; k0 < D; k0 += kMaxDisp) {
+        DispList dl;
+        const int n = (D - k0 < kMaxDisp) ? D - k0 : kMaxDisp;
+        for (int i = 0; i < n; ++i) {
+            int d = disp_idx_host[k0 + i];
+            dl.d[i] = d >= W ? W : (d <= -W ? -W : d);
+        }
+        if (vec)
+            gwc_rows_kernel<true><<<grid, 256, smem, as_stream(stream)>>>(left, right, out, C, G, H, W, n, k0, D, dl);
+        else
+            gwc_rows_kernel<false><<<grid, 256, smem, as_stream(stream)>>>(left, right, out, C, G, H, W, n, k0, D, dl);
+        int rc = check_launch("gwc_rows_kernel");
+        if (rc) return rc;
+    }
+    return DMB_OK;
+}
+
+extern "C" int dmb_b200_warp_volume(const float* left, const float* right, const float* disp_sample, float* out, int B,
+                                    int C, int H, int W, int D, int mode, float p, void* stream) {
+    DMB_REQUIRE(left && right && disp_sample && out, "warp_volume: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "warp_volume: non-positive dimension");
+    DMB_REQUIRE(mode >= 0 && mode <= 2, "warp_volume: mode must be 0, 1 or 2");
+    DMB_REQUIRE(p > 0.f, "warp_volume: p must be positive");
+    const size_t total = (size_t)B * D * H * W;
+    const int blocks = (int)((total + 255) / 256 < (size_t)sm_count() * 32 ? (total + 255) / 256 : (size_t)sm_count() * 32);
+    if (mode == 0)
+        warp_volume_kernel<0><<<blocks, 256, 0, as_stream(stream)>>>(left, right, disp_sample, out, B, C, H, W, D, p);
+    else if (mode == 1)
+        warp_volume_kernel<1><<<blocks, 256, 0, as_stream(stream)>>>(left, right, disp_sample, out, B, C, H, W, D, p);
+    else
+        warp_volume_kernel<2><<<blocks, 256, 0, as_stream(stream)>>>(left, right, disp_sample, out, B, C, H, W, D, p);
+    return check_launch("warp_volume_kernel");
+}
+
+extern "C" int dmb_b200_ncdhw_to_cl(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W,
+                                    void* stream) {
+    DMB_REQUIRE(x && y_hi, "ncdhw_to_cl: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ncdhw_to_cl: non-positive dimension");
+    const size_t S = (size_t)D * H * W;
+    DMB_REQUIRE(B <= 65535 && cdiv(C, 32) <= 65535, "ncdhw_to_cl: grid dimension too large");
+    dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(C, 32), B);
+    ncs_to_cl_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, C, S);
+    return check_launch("ncs_to_cl_kernel");
+}
+
+extern "C" int dmb_b200_cl_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W,
+                                    void* stream) {
+    DMB_REQUIRE(x_hi && y, "cl_to_ncdhw: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "cl_to_ncdhw: non-positive dimension");
+    const size_t S = (size_t)D * H * W;
+    DMB_REQUIRE(B <= 65535 && cdiv(C, 32) <= 65535, "cl_to_ncdhw: grid dimension too large");
+    dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(C, 32), B);
+    cl_to_ncs_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, y, C, S);
+    return check_launch("cl_to_ncs_kernel");
+}
+
+extern "C" int dmb_b200_cat_volume_cl(const void* l_hi, const void* l_lo, const void* r_hi, const void* r_lo,
+                                      void* out_hi, void* out_lo, int B, int C, int H, int W,
+                                      const int* disp_idx_host, int D, void* stream) {
+    DMB_REQUIRE(l_hi && r_hi && out_hi && disp_idx_host, "cat_volume_cl: null pointer");
+    DMB_REQUIRE(!out_lo || (l_lo && r_lo), "cat_volume_cl: out_lo given without l_lo/r_lo");
+    DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "cat_volume_cl: non-positive dimension");
+    DMB_REQUIRE(C % 8 == 0, "cat_volume_cl: C=%d must be a multiple of 8", C);
+    DMB_REQUIRE(D <= kMaxDisp, "cat_volume_cl: D=%d exceeds %d", D, kMaxDisp);
+    DispList dl;
+    for (int i = 0; i < D; ++i) {
+        int d = disp_idx_host[i];
+        dl.d[i] = d >= W ? W : (d <= -W ? -W : d);
+    }
+    const size_t total = (size_t)B * D * H * W * (C / 4);
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    cat_volume_cl_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
+        (const uint4*)l_hi, (const uint4*)l_lo, (const uint4*)r_hi, (const uint4*)r_lo, (uint4*)out_hi, (uint4*)out_lo, B,
+        C / 8, H, W, D, dl);
+    return check_launch("cat_volume_cl_kernel");
+}

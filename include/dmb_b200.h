@@ -1,0 +1,184 @@
+/*
+ * dmb_b200.h -- C ABI of the B200-native cost-volume hot path for DenseMatchingBenchmark (dmb).
+ *
+ * The reference has no C boundary for this path: every function below replaces a piece of
+ * PyTorch/ATen code reached from `dmb.modeling.stereo.{cost_processors,disp_predictors}`
+ * or the pybind11 module of `dmb.ops.spn` (dmb/ops/spn/src/gaterecurrent2dnoind_cuda.cpp:86-89,
+ * whose entry points take torch::Tensor).  Here the boundary is plain C: raw DEVICE pointers,
+ * explicit sizes, a dtype code, and the CUDA stream to launch on.  No torch types.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative DMB_ERR_* code otherwise and never
+ *     aborts the process (contrast gaterecurrent2dnoind_kernel.cu:544-549, `exit(-1)`);
+ *     `dmb_b200_last_error()` returns a thread-local message for the last failure;
+ *   - kernels are launched on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream) -- contrast the reference op which always uses the legacy stream
+ *     (gaterecurrent2dnoind_kernel.cu:542);
+ *   - tensors are dense, contiguous, in the layout stated per function; "NCDHW" etc. are the
+ *     reference layouts, "NDHWC" (channels last) is the internal layout of the tensor-core trunk;
+ *   - all pointers are device pointers unless the name ends in `_host`;
+ *   - the library is re-entrant per (device, stream); it keeps no global mutable state besides
+ *     lazily-resolved driver entry points and per-device attribute caches.
+ */
+#ifndef DMB_B200_H_
+#define DMB_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMB_OK 0
+#define DMB_ERR_INVALID (-1)      /* bad argument (shape, dtype, alignment, null pointer) */
+#define DMB_ERR_CUDA (-2)         /* a CUDA runtime / driver call failed */
+#define DMB_ERR_UNSUPPORTED (-3)  /* valid request this build has no kernel for */
+
+#define DMB_F32 0
+#define DMB_BF16 1
+
+/* library / ABI version, bumped whenever a signature changes */
+int dmb_b200_abi_version(void);
+const char* dmb_b200_last_error(void);
+/* number of kernels this library has launched in the calling process (all threads) */
+int64_t dmb_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Raw cost-volume builders.  `disp_idx_host` holds the D integer disparities enumerated by the
+ * caller exactly like the reference (`int(linspace(start, start+max-1, D))`, cat_fms.py:27-35).
+ * Features are [B,C,H,W] float32 (NCHW).
+ * ---------------------------------------------------------------------------------------- */
+
+/* cat_fms (dmb/modeling/stereo/cost_processors/utils/cat_fms.py:7-48)
+ * out: [B,2C,D,H,W] float32, every element written (zeros where the reference leaves zeros). */
+int dmb_b200_cat_volume(const float* left, const float* right, float* out,
+                        int B, int C, int H, int W, const int* disp_idx_host, int D, void* stream);
+
+/* dif_fms (dmb/modeling/stereo/cost_processors/utils/dif_fms.py:7-46); out: [B,C,D,H,W] float32 */
+int dmb_b200_dif_volume(const float* left, const float* right, float* out,
+                        int B, int C, int H, int W, const int* disp_idx_host, int D, void* stream);
+
+/* group-wise correlation (GwcNet eq. 3; NO reference code, see oracle/dmb_oracle.py:gwc_volume)
+ * out: [B,G,D,H,W] float32; C % G == 0. */
+int dmb_b200_gwc_volume(const float* left, const float* right, float* out,
+                        int B, int C, int H, int W, int G, const int* disp_idx_host, int D, void* stream);
+
+/* fast_cat_fms / fast_dif_fms (cat_fms.py:51-82, dif_fms.py:49-86) with inverse_warp_3d
+ * (dmb/modeling/stereo/layers/inverse_warp_3d.py:4-52) folded in.
+ * disp_sample: [B,D,H,W] float32 (per-pixel disparity samples).
+ * mode 0: concat -> out [B,2C,D,H,W];  mode 1: difference -> out [B,C,D,H,W];
+ * mode 2: difference then p-norm over C (normalize=True) -> out [B,D,H,W]. */
+int dmb_b200_warp_volume(const float* left, const float* right, const float* disp_sample, float* out,
+                         int B, int C, int H, int W, int D, int mode, float p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 3-D convolution, generic direct kernel (any channel count / 3-D kernel size / stride /
+ * transposed), fp32 NCDHW.  Replaces the cuDNN calls behind conv3d_bn[_relu] / deconv3d_bn
+ * (dmb/modeling/stereo/layers/basic_layers.py:68-216) with BN folded by the caller:
+ *     y = act( conv(x, w) + bias + residual )
+ * w_packed: [KD*KH*KW][Cin][Cout] float32 (caller repacks; for a transposed conv the caller
+ * passes the ConvTranspose3d weight [Cin,Cout,k,k,k] permuted the same way, un-flipped).
+ * bias: [Cout] or NULL.  residual: same shape as y or NULL.  relu: 0/1 applied last.
+ * dims_in = {D,H,W} of x, dims_out = {D,H,W} of y.
+ * ---------------------------------------------------------------------------------------- */
+int dmb_b200_conv3d_direct(const float* x, const float* w_packed, const float* bias, const float* residual,
+                           float* y, int B, int Cin, int Cout, const int* dims_in, const int* dims_out,
+                           const int* ksize, int stride, int pad, int transposed, int relu, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cost upsampling + disparity regression.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Upsample a low-resolution 1-channel cost [B,Dl,Hl,Wl] (float32) to [B,D,H,W] and/or regress
+ * the disparity map [B,1,H,W] from the upsampled values without materialising them.
+ *   mode 0: trilinear, align_corners=True (F.interpolate in aggregators/PSMNet.py:75-88)
+ *   mode 1: ConvTranspose3d(1,1,8,stride 4,pad 2) with `up_weight` [8*8*8] (AcfNet.py:55-57,81-83);
+ *           requires D==4*Dl, H==4*Hl, W==4*Wl.
+ * cost_out (nullable): [B,D,H,W] float32.  disp_out (nullable): [B,1,H,W] float32 =
+ *   sum_d softmax_d(alpha*cost)[d] * (start_disp + d*disp_step)   (normalize=1)
+ *   sum_d alpha*cost[d] * (...)                                     (normalize=0)
+ * i.e. FasterSoftArgmin / SoftArgmin (faster_soft_argmin.py:51-75, soft_argmin.py:44-75) fused
+ * onto the last aggregation write.  disp_values (nullable, [D] float32 device) overrides the
+ * arithmetic ramp with explicit sample values (the frozen `disp_regression.weight`). */
+int dmb_b200_upsample_regress(const float* cost_low, const float* up_weight, float* cost_out, float* disp_out,
+                              int B, int Dl, int Hl, int Wl, int D, int H, int W, int mode,
+                              float alpha, int normalize, float start_disp, float disp_step,
+                              const float* disp_values, void* stream);
+
+/* SoftArgmin / FasterSoftArgmin on a materialised cost [B,D,H,W] float32 -> [B,1,H,W].
+ * Exactly one of disp_values ([D]) / disp_sample ([B,D,H,W]) may be non-NULL; if both are NULL
+ * the ramp start_disp + d*disp_step is used. */
+int dmb_b200_soft_argmin(const float* cost, float* disp_out, int B, int D, int H, int W,
+                         float alpha, int normalize, float start_disp, float disp_step,
+                         const float* disp_values, const float* disp_sample, void* stream);
+
+/* LocalSoftArgmin (disp_predictors/local_soft_argmin.py:47-105) */
+int dmb_b200_local_soft_argmin(const float* cost, float* disp_out, int B, int D, int H, int W,
+                               int radius, int radius_dilation, float alpha, float start_disp, float dilation,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * dmb.ops: SPN 3-neighbour gated scan (dmb/ops/spn/src/gaterecurrent2dnoind_kernel.cu).
+ * All tensors [N,C,H,W] float32.  One launch per call (the reference issues W or H launches).
+ * ---------------------------------------------------------------------------------------- */
+int dmb_b200_spn_forward(const float* X, const float* G1, const float* G2, const float* G3, float* Hout,
+                         int N, int C, int H, int W, int horizontal, int reverse, void* stream);
+/* grad_out is not modified (the reference accumulates into it in place); the four gradients
+ * are fully written. */
+int dmb_b200_spn_backward(const float* X, const float* G1, const float* G2, const float* G3,
+                          const float* Hout, const float* grad_out,
+                          float* gX, float* gG1, float* gG2, float* gG3,
+                          int N, int C, int H, int W, int horizontal, int reverse, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GANet aggregation layers (NO reference code; semantics fixed by oracle/dmb_oracle.py).
+ * ---------------------------------------------------------------------------------------- */
+/* SGA: x [B,C,D,H,W], guidance [B,4,5,C,H,W] (un-normalised; L1-normalised over the 5 taps
+ * inside), out [B,C,D,H,W] = max over the 4 scan directions. */
+int dmb_b200_sga(const float* x, const float* guidance, float* out,
+                 int B, int C, int D, int H, int W, void* stream);
+/* LGA: x [B,D,H,W], guidance [B,3,K,K,H,W] with K=2*radius+1 (L1-normalised over all 3*K*K
+ * weights inside), out [B,D,H,W]. */
+int dmb_b200_lga(const float* x, const float* guidance, float* out,
+                 int B, int D, int H, int W, int radius, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05) trunk: channels-last bf16 activations, optionally as a (hi, lo) split
+ * pair that carries ~16 mantissa bits through bf16 MMAs with fp32 accumulation.
+ * ---------------------------------------------------------------------------------------- */
+
+/* cat volume straight into the trunk's layout.  l_hi.. r_lo: channels-last features [B,H,W,C] bf16
+ * (made by dmb_b200_ncdhw_to_cl with D=1); out_hi/out_lo: [B,D,H,W,2C] bf16.  *_lo == NULL =>
+ * plain bf16 (no split).  C % 8 == 0. */
+int dmb_b200_cat_volume_cl(const void* l_hi, const void* l_lo, const void* r_hi, const void* r_lo,
+                           void* out_hi, void* out_lo,
+                           int B, int C, int H, int W, const int* disp_idx_host, int D, void* stream);
+
+/* 3x3x3 convolution / stride-2 convolution / stride-2 transposed convolution on tcgen05.
+ * x_hi/x_lo: [B,Di,Hi,Wi,Cin] bf16; w_hi/w_lo: packed by dmb_b200_conv3d_tc_pack_weights;
+ * bias [Cout] f32 or NULL; res_hi/res_lo residual (same shape as y) or NULL; relu 0/1;
+ * y_hi/y_lo: [B,Do,Ho,Wo,Cout] bf16.  *_lo == NULL selects plain bf16 for that tensor.
+ * y_f32 (nullable): also/only write y as [B,Cout,Do,Ho,Wo] float32 (NCDHW; used for Cout==1).
+ * kind: 0 = stride-1 conv, 1 = stride-2 conv, 2 = stride-2 transposed conv (k3,p1,op1). */
+int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                       const float* bias, const void* res_hi, const void* res_lo,
+                       void* y_hi, void* y_lo, float* y_f32,
+                       int B, int Cin, int Cout, const int* dims_in, const int* dims_out,
+                       int kind, int relu, void* stream);
+/* w: [27][Cin][Cout] float32 (same packing as conv3d_direct) -> w_hi/w_lo bf16 in the layout the
+ * kernel's TMA descriptor expects ([27][Cout_pad][Cin], K-major). Cout_pad = max(Cout,16). */
+int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_hi, void* w_lo,
+                                    int Cin, int Cout, void* stream);
+/* bytes of one packed weight plane */
+int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout);
+/* 1 if this device/build can run the tcgen05 path */
+int dmb_b200_conv3d_tc_available(void);
+
+/* layout helpers for the trunk boundary */
+int dmb_b200_ncdhw_to_cl(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, void* stream);
+int dmb_b200_cl_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMB_B200_H_ */

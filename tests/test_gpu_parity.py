@@ -1,0 +1,372 @@
+"""GPU parity tests: every CUDA kernel (through the C ABI / the dmb-mirror modules) against the
+CPU oracle and the golden fixtures produced by the reference itself.  Run on the B200 box:
+    python -m pytest tests -m gpu -x -q
+Tolerances: bit-exact for pure data movement (cat / dif volumes); fp32 rounding-order level for
+floating-point kernels; the north-star bound |d_disp| < 1e-3 px for end-to-end disparity."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dmb_oracle as O
+import seeded
+from make_golden import VOLUME_CASES, PRED_CASES, volume_inputs
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def P():
+    import densematchingbenchmark_b200 as pkg
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return pkg
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def _cfg(P, agg="PSMNet", feat_disp=12, max_disp=48, proc="Concatenation", comp_type="default", pred="FASTER", **comp):
+    cc = dict(type=comp_type, max_disp=feat_disp, start_disp=0, dilation=1)
+    cc.update(comp)
+    return P.ConfigDict(model=dict(
+        batch_norm=True,
+        cost_processor=dict(type=proc, cost_computation=cc,
+                            cost_aggregator=dict(type=agg, max_disp=max_disp, in_planes=64)),
+        disp_predictor=dict(type=pred, max_disp=max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=True)))
+
+
+# ------------------------------------------------------------------------------- volumes
+@pytest.mark.parametrize("case", [c[0] for c in VOLUME_CASES])
+def test_volumes_vs_reference_golden(P, golden_dir, case):
+    rec = _load(golden_dir, "volumes.pt")[case]
+    B, C, H, W, md, sd, dil = rec["params"]
+    l, r = volume_inputs(case, B, C, H, W)
+    kw = dict(max_disp=md, start_disp=sd, dilation=dil)
+    lg, rg = l.to(DEV), r.to(DEV)
+    assert torch.equal(P.CAT_FUNCS["default"](lg, rg, **kw).cpu(), rec["cat"])       # bit exact
+    assert torch.equal(P.DIF_FUNCS["default"](lg, rg, **kw).cpu(), rec["dif"])       # bit exact
+    if "fast_cat" in rec:
+        tol = dict(atol=2e-5, rtol=1e-5)
+        torch.testing.assert_close(P.CAT_FUNCS["fast_mode"](lg, rg, **kw).cpu(), rec["fast_cat"], **tol)
+        torch.testing.assert_close(P.DIF_FUNCS["fast_mode"](lg, rg, **kw).cpu(), rec["fast_dif"], **tol)
+        torch.testing.assert_close(P.DIF_FUNCS["fast_mode"](lg, rg, normalize=True, p=1.0, **kw).cpu(),
+                                   rec["fast_dif_norm"], atol=1e-4, rtol=1e-5)
+        got = P.CAT_FUNCS["fast_mode"](lg, rg, disp_sample=rec["disp_sample"].to(DEV), **kw).cpu()
+        torch.testing.assert_close(got, rec["fast_cat_sampled"], **tol)
+
+
+@pytest.mark.parametrize("shape", [(1, 32, 16, 32, 12, 0, 1), (2, 5, 7, 37, 9, -3, 2), (1, 3, 2, 5, 12, -6, 1),
+                                   (1, 8, 33, 64, 300, 0, 1)])
+def test_volumes_vs_oracle_ragged(P, shape):
+    B, C, H, W, md, sd, dil = shape
+    l, r = seeded.feature_pair(B, C, H, W, seed=B + C + W)
+    kw = dict(max_disp=md, start_disp=sd, dilation=dil)
+    assert torch.equal(P.CAT_FUNCS["default"](l.to(DEV), r.to(DEV), **kw).cpu(), O.cat_volume(l, r, **kw))
+    assert torch.equal(P.DIF_FUNCS["default"](l.to(DEV), r.to(DEV), **kw).cpu(), O.dif_volume(l, r, **kw))
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 6, 32, 4, 10, 0, 1), (2, 24, 5, 21, 8, 7, -2, 2), (1, 320, 8, 48, 40, 12, 0, 1)])
+def test_gwc_volume_vs_oracle(P, shape):
+    B, C, H, W, G, md, sd, dil = shape
+    l, r = seeded.feature_pair(B, C, H, W, seed=G)
+    got = P.GWC_FUNCS["default"](l.to(DEV), r.to(DEV), max_disp=md, start_disp=sd, dilation=dil, num_groups=G).cpu()
+    torch.testing.assert_close(got, O.gwc_volume(l, r, G, md, sd, dil), atol=1e-5, rtol=1e-5)
+
+
+def test_cat_volume_full_size_properties(P):
+    """BASELINE config 2 size: [1,32,136,240] features, D=48 -> [1,64,48,136,240] (401 MB)."""
+    l, r = seeded.feature_pair(1, 32, 136, 240, seed=3)
+    vol = P.CAT_FUNCS["default"](l.to(DEV), r.to(DEV), max_disp=48)
+    assert vol.shape == (1, 64, 48, 136, 240) and vol.dtype == torch.float32
+    lg, rg = l.to(DEV), r.to(DEV)
+    for d in (0, 1, 17, 47):
+        assert torch.equal(vol[0, :32, d, :, d:], lg[0, :, :, d:])
+        assert torch.equal(vol[0, 32:, d, :, d:], rg[0, :, :, :240 - d])
+        assert float(vol[0, :, d, :, :d].abs().sum()) == 0.0
+    # checksum of checksums: every left value appears once per disparity where x >= d
+    expect = sum(float(lg[0, :, :, d:].double().sum() + rg[0, :, :, :240 - d].double().sum()) for d in range(48))
+    assert abs(float(vol.double().sum()) - expect) < 1e-6 * max(1.0, abs(expect))
+
+
+# ------------------------------------------------------------------------------- conv
+CONV_CASES = [
+    # Cin, Cout, dims, stride, transposed, bias, residual, relu
+    (64, 32, (6, 9, 13), 1, False, False, False, True),
+    (32, 32, (5, 8, 8), 1, False, True, True, False),
+    (32, 64, (8, 10, 12), 2, False, False, False, True),
+    (64, 64, (7, 9, 11), 2, False, False, False, True),      # odd extents with stride 2
+    (64, 64, (3, 4, 5), 2, True, False, True, True),
+    (64, 32, (4, 5, 6), 2, True, True, False, False),
+    (32, 1, (6, 7, 9), 1, False, False, True, False),
+    (5, 7, (4, 6, 5), 1, False, True, False, True),          # odd channel counts
+    (96, 16, (3, 5, 4), 1, False, False, False, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3d_direct_vs_torch_cpu(P, case):
+    from densematchingbenchmark_b200.ops import functional as F_
+    cin, cout, dims, stride, transposed, bias, residual, relu = case
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(2, cin, *dims, generator=g)
+    wshape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+    w = torch.randn(wshape, generator=g) * (2.0 / (cin * 27)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1 if bias else None
+    if transposed:
+        ref = F.conv_transpose3d(x, w, b, stride=stride, padding=1, output_padding=stride - 1)
+    else:
+        ref = F.conv3d(x, w, b, stride=stride, padding=1)
+    res = torch.randn(ref.shape, generator=g) if residual else None
+    if res is not None:
+        ref = ref + res
+    if relu:
+        ref = F.relu(ref)
+    wp = F_.pack_conv_weight(w, transposed).to(DEV)
+    got = F_.conv3d_fused(x.to(DEV), wp, b.to(DEV) if bias else None, (3, 3, 3), stride, 1, transposed,
+                          stride - 1 if transposed else 0, res.to(DEV) if residual else None, relu).cpu()
+    torch.testing.assert_close(got, ref, atol=2e-5, rtol=1e-4)
+
+
+def test_conv3d_direct_generic_kernel_sizes(P):
+    from densematchingbenchmark_b200.ops import functional as F_
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 6, 5, 7, 9, generator=g)
+    w = torch.randn(4, 6, 1, 3, 3, generator=g) * 0.2
+    ref = F.conv3d(x, w, None, stride=1, padding=(1, 1, 1))
+    # generic path handles a uniform pad only: emulate (0,1,1) by checking the k=(1,3,3) pad-1 result rows
+    got = F_.conv3d_fused(x.to(DEV), F_.pack_conv_weight(w).to(DEV), None, (1, 3, 3), 1, 1).cpu()
+    torch.testing.assert_close(got, ref, atol=2e-5, rtol=1e-4)
+
+
+def test_hourglass_vs_reference_golden(P, golden_dir):
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.utils.hourglass import Hourglass
+    rec = _load(golden_dir, "hourglass.pt")
+    entries = []
+    seeded._hourglass(entries, "hg", 32, bias=False)
+    sd = seeded.seeded_state_dict([(k[3:], s, r) for k, s, r in entries], seed=7)
+    hg = Hourglass(32, True)
+    hg.load_state_dict(sd)
+    hg = hg.to(DEV).eval()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 32, 8, 8, 12, generator=g)
+    pre = torch.randn(1, 64, 4, 4, 6, generator=g)
+    post = torch.randn(1, 64, 4, 4, 6, generator=g)
+    for got, want in zip(hg(x.to(DEV)), rec["first"]):
+        torch.testing.assert_close(got.cpu(), want, atol=1e-4, rtol=1e-4)
+    for got, want in zip(hg(x.to(DEV), pre.to(DEV), post.to(DEV)), rec["second"]):
+        torch.testing.assert_close(got.cpu(), want, atol=1e-4, rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------- predictors
+@pytest.mark.parametrize("case", [c[0] for c in PRED_CASES])
+def test_predictors_vs_reference_golden(P, golden_dir, case):
+    rec = _load(golden_dir, "predictors.pt")[case]
+    B, md, H, W, sd, dil, alpha, norm = rec["params"]
+    cost = rec["cost"].to(DEV)
+    kw = dict(max_disp=md, start_disp=sd, dilation=dil, alpha=alpha, normalize=norm)
+    tol = dict(atol=5e-5, rtol=1e-5)
+    torch.testing.assert_close(P.PREDICTORS["DEFAULT"](**kw)(cost).cpu(), rec["DEFAULT"], **tol)
+    torch.testing.assert_close(P.PREDICTORS["FASTER"](**kw).to(DEV)(cost).cpu(), rec["FASTER"], **tol)
+    got = P.PREDICTORS["DEFAULT"](**kw)(cost, disp_sample=rec["disp_sample"].to(DEV)).cpu()
+    torch.testing.assert_close(got, rec["DEFAULT_sampled"], **tol)
+    for radius, rdil in ((1, 1), (2, 1), (2, 2)):
+        got = P.PREDICTORS["LOCAL"](radius=radius, radius_dilation=rdil, **kw)(cost).cpu()
+        torch.testing.assert_close(got, rec["LOCAL_r%d_d%d" % (radius, rdil)], **tol)
+
+
+def test_predictor_errors_like_reference(P):
+    pred = P.PREDICTORS["FASTER"](max_disp=8).to(DEV)
+    with pytest.raises(ValueError):
+        pred(torch.zeros(1, 1, 8, 4, 4, device=DEV))
+    with pytest.raises(AssertionError):
+        P.PREDICTORS["DEFAULT"](max_disp=8)(torch.zeros(1, 7, 4, 4, device=DEV))
+    with pytest.raises(Exception):
+        P.PREDICTORS["DEFAULT"](max_disp=8)(torch.zeros(1, 8, 4, 4))     # CPU tensor: no CPU path
+
+
+@pytest.mark.parametrize("shape", [(1, 12, 16, 32, 48, 64, 128), (2, 5, 6, 7, 20, 24, 28), (1, 3, 4, 5, 9, 7, 11)])
+def test_upsample_regress_trilinear_vs_oracle(P, shape):
+    from densematchingbenchmark_b200.ops import functional as F_
+    B, Dl, Hl, Wl, D, H, W = shape
+    g = torch.Generator().manual_seed(D)
+    low = torch.randn(B, 1, Dl, Hl, Wl, generator=g) * 3
+    want_cost = F.interpolate(low, [D, H, W], mode="trilinear", align_corners=True).squeeze(1)
+    want_disp = O.soft_argmin(want_cost, D)
+    cost, disp = F_.upsample_regress(low.to(DEV), (D, H, W), "trilinear", want_cost=True, want_disp=True)
+    torch.testing.assert_close(cost.cpu(), want_cost, atol=2e-5, rtol=1e-5)
+    torch.testing.assert_close(disp.cpu(), want_disp, atol=1e-4, rtol=1e-5)
+    _, disp2 = F_.upsample_regress(low.to(DEV), (D, H, W), "trilinear", want_cost=False, want_disp=True)
+    assert torch.equal(disp2, disp)
+    torch.testing.assert_close(O.trilinear_up(low, (D, H, W)).squeeze(1), want_cost, atol=1e-5, rtol=1e-5)
+
+
+def test_upsample_regress_deconv_vs_oracle(P):
+    from densematchingbenchmark_b200.ops import functional as F_
+    g = torch.Generator().manual_seed(8)
+    low = torch.randn(2, 1, 6, 5, 7, generator=g) * 2
+    w = torch.randn(1, 1, 8, 8, 8, generator=g) * 0.2
+    want_cost = F.conv_transpose3d(low, w, None, stride=4, padding=2).squeeze(1)
+    cost, disp = F_.upsample_regress(low.to(DEV), (24, 20, 28), "deconv", w.to(DEV), want_cost=True, want_disp=True,
+                                     alpha=0.7)
+    torch.testing.assert_close(cost.cpu(), want_cost, atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(disp.cpu(), O.soft_argmin(want_cost, 24, alpha=0.7), atol=1e-4, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------- aggregators
+@pytest.mark.parametrize("agg", ["PSMNet", "AcfNet"])
+@pytest.mark.parametrize("variant", ["plain", "sharp"])
+@pytest.mark.parametrize("defer", [True, False])
+def test_config1_vs_reference_golden(P, golden_dir, agg, variant, defer):
+    """BASELINE config 1: cat cost volume + aggregator + soft-argmin on [1,32,16,32] features."""
+    rec = _load(golden_dir, "aggregators.pt")["%s_%s" % (agg, variant)]
+    cfg = _cfg(P, agg)
+    proc = P.build_cost_processor(cfg)
+    pred = P.build_disp_predictor(cfg)
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries(agg, 64), seed=rec["seed"], sharpen=rec["sharpen"])
+    proc.aggregator.load_state_dict(sd)
+    proc = proc.to(DEV).eval()
+    proc.aggregator.engine = "direct"
+    pred = pred.to(DEV).eval()
+    proc.aggregator.defer_upsample = defer
+    l, r = seeded.feature_pair(1, 32, 16, 32, seed=100 + rec["seed"], scale=0.5, shift=rec["shift"])
+    costs = proc(l.to(DEV), r.to(DEV))
+    assert len(costs) == 3 and all(tuple(c.shape) == (1, 48, 64, 128) for c in costs)
+    assert isinstance(costs[0], P.DeferredCost) == defer
+    disps = [pred(c) for c in costs]
+    for dsp, want in zip(disps, rec["disps"]):
+        assert tuple(dsp.shape) == (1, 1, 64, 128)
+        assert float((dsp.cpu() - want).abs().max()) < 1e-3
+    for c, want, amax in zip(costs, rec["cost_samples"], rec["cost_absmax"]):
+        dense = c[:, ::3, ::4, ::4]          # a DeferredCost materialises here
+        torch.testing.assert_close(dense.cpu(), want, atol=2e-5 * max(1.0, amax), rtol=1e-4)
+
+
+def test_gc_and_stereonet_aggregators_vs_torch_modules(P):
+    """Remaining GeneralizedStereoModel aggregators: compare against the same architecture run with
+    torch CPU ops on the module's own parameters (they hold ordinary nn.Conv3d / BatchNorm3d)."""
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators.builder import AGGREGATORS
+    torch.manual_seed(0)
+    st = AGGREGATORS["StereoNet"](max_disp=192, in_planes=32, batch_norm=True, num=4).eval()
+    for m in st.modules():
+        if isinstance(m, torch.nn.BatchNorm3d):
+            m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
+    x = torch.randn(1, 32, 6, 10, 12)
+    with torch.no_grad():
+        ref = x
+        for layer in st.classify:
+            ref = F.relu(F.batch_norm(F.conv3d(ref, layer[0].weight, layer[0].bias, padding=1), layer[1].running_mean,
+                                      layer[1].running_var, layer[1].weight, layer[1].bias, False, 0.0, layer[1].eps))
+        ref = F.conv3d(ref, st.lastconv.weight, st.lastconv.bias, padding=1).squeeze(1)
+    got = st.to(DEV)(x.to(DEV))[0].cpu()
+    torch.testing.assert_close(got, ref, atol=1e-4, rtol=1e-4)
+
+    gc = AGGREGATORS["GCNet"](max_disp=32, in_planes=8, batch_norm=True).eval()
+    x = torch.randn(1, 8, 16, 32, 32)
+    with torch.no_grad():
+        def unit(layer, t):
+            conv = layer[0]
+            if isinstance(conv, torch.nn.ConvTranspose3d):
+                y = F.conv_transpose3d(t, conv.weight, conv.bias, stride=2, padding=1, output_padding=1)
+            else:
+                y = F.conv3d(t, conv.weight, conv.bias, stride=conv.stride, padding=1)
+            bn = layer[1]
+            y = F.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+            return F.relu(y)
+        v18 = x; v19 = unit(gc.layer19, v18); v20 = unit(gc.layer20, v19)
+        v21 = unit(gc.layer21, torch.cat([v18, v20], 1)); v22 = unit(gc.layer22, v21); v23 = unit(gc.layer23, v22)
+        v24 = unit(gc.layer24, torch.cat([v21, v23], 1)); v25 = unit(gc.layer25, v24); v26 = unit(gc.layer26, v25)
+        v27 = unit(gc.layer27, torch.cat([v24, v26], 1)); v28 = unit(gc.layer28, v27); v29 = unit(gc.layer29, v28)
+        v30 = unit(gc.layer30, torch.cat([v27, v29], 1)); v31 = unit(gc.layer31, v30); v32 = unit(gc.layer32, v31)
+        v33 = unit(gc.layer33, v32); v34 = unit(gc.layer34, v33 + v29); v35 = unit(gc.layer35, v34 + v26)
+        v36 = unit(gc.layer36, v35 + v23)
+        ref = F.conv_transpose3d(v36 + v20, gc.layer37.weight, gc.layer37.bias, stride=2, padding=1,
+                                 output_padding=1).squeeze(1)
+    got = gc.to(DEV)(x.to(DEV))[0].cpu()
+    torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-3)
+
+
+def test_training_mode_fails_loudly(P):
+    proc = P.build_cost_processor(_cfg(P)).to(DEV).train()
+    proc.aggregator.engine = "direct"
+    l, r = seeded.feature_pair(1, 32, 8, 16, seed=1)
+    with pytest.raises(NotImplementedError):
+        proc(l.to(DEV), r.to(DEV))
+
+
+def test_medium_size_psm_hot_path_vs_oracle(P):
+    """A quarter of BASELINE config 2 (272x480 image, D=192): CUDA path vs the CPU oracle on the
+    same seeded weights (sharpened) and a structured stereo pair."""
+    cfg = _cfg(P, "PSMNet", feat_disp=48, max_disp=192)
+    proc = P.build_cost_processor(cfg)
+    pred = P.build_disp_predictor(cfg)
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=3, sharpen=4.0)
+    proc.aggregator.load_state_dict(sd)
+    proc = proc.to(DEV).eval(); pred = pred.to(DEV).eval()
+    proc.aggregator.engine = "direct"
+    l, r = seeded.feature_pair(1, 32, 68, 120, seed=21, scale=0.5, shift=9)
+    disps = [pred(c).cpu() for c in proc(l.to(DEV), r.to(DEV))]
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    _, want = O.psm_hot_path(sd, l, r, 192, prefix="")
+    for got, w in zip(disps, want):
+        assert float((got - w).abs().max()) < 1e-3
+        assert abs(O.epe(got, w + 1.0, 0, 1e9) - 1.0) < 1e-3   # |dEPE| against a shifted pseudo-GT
+
+
+# ------------------------------------------------------------------------------- scans
+@pytest.mark.parametrize("shape", [(2, 3, 5, 6), (1, 8, 34, 60), (1, 2, 1, 7), (1, 2, 7, 1)])
+def test_spn_forward_backward_vs_oracle(P, shape):
+    from densematchingbenchmark_b200.ops import GateRecurrent2dnoind
+    N, C, H, W = shape
+    g = torch.Generator().manual_seed(H * W)
+    X = torch.randn(N, C, H, W, generator=g)
+    G = [torch.rand(N, C, H, W, generator=g) * 0.3 for _ in range(3)]
+    go = torch.randn(N, C, H, W, generator=g)
+    for horizontal in (True, False):
+        for reverse in (False, True):
+            want = O.spn_scan(X, *G, horizontal, reverse)
+            wg = O.spn_scan_backward(X, *G, want, go, horizontal, reverse)
+            Xg = X.to(DEV).requires_grad_(True)
+            Gg = [t.to(DEV).requires_grad_(True) for t in G]
+            out = GateRecurrent2dnoind(horizontal, reverse)(Xg, *Gg)
+            torch.testing.assert_close(out.detach().cpu(), want, atol=1e-5, rtol=1e-5)
+            out.backward(go.to(DEV))
+            for got, w in zip([Xg.grad] + [t.grad for t in Gg], wg):
+                torch.testing.assert_close(got.cpu(), w, atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 2, 6, 5, 7), (2, 3, 16, 9, 12), (1, 2, 70, 6, 10)])
+def test_sga_vs_oracle(P, shape):
+    from densematchingbenchmark_b200.ops import SGA
+    B, C, D, H, W = shape
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(B, C, D, H, W, generator=g)
+    gd = torch.randn(B, 4 * 5 * C, H, W, generator=g)
+    got = SGA()(x.to(DEV), gd.to(DEV)).cpu()
+    torch.testing.assert_close(got, O.sga(x, gd), atol=1e-5, rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 5, 7, 2), (2, 12, 9, 33, 2), (1, 5, 6, 8, 1)])
+def test_lga_vs_oracle(P, shape):
+    from densematchingbenchmark_b200.ops import LGA
+    B, D, H, W, radius = shape
+    K = 2 * radius + 1
+    g = torch.Generator().manual_seed(W)
+    x = torch.randn(B, D, H, W, generator=g)
+    gd = torch.randn(B, 3 * K * K, H, W, generator=g)
+    got = LGA(radius)(x.to(DEV), gd.to(DEV)).cpu()
+    torch.testing.assert_close(got, O.lga(x, gd, radius), atol=1e-5, rtol=1e-4)
+
+
+def test_bad_arguments_return_errors_not_aborts(P):
+    from densematchingbenchmark_b200 import _cabi as C
+    with pytest.raises(C.DmbB200Error):
+        C.call("dmb_b200_gwc_volume", None, None, None, 1, 6, 4, 4, 4, C.int_array([0]), 1, None)
+    z = torch.zeros(1, 6, 4, 4, device=DEV)
+    with pytest.raises(C.DmbB200Error):      # 6 channels are not divisible into 4 groups
+        C.call("dmb_b200_gwc_volume", C.ptr(z), C.ptr(z), C.ptr(z), 1, 6, 4, 4, 4, C.int_array([0]), 1, None)
+    with pytest.raises(ValueError):
+        P.CAT_FUNCS["default"](z, torch.zeros(1, 6, 4, 5, device=DEV), max_disp=4)

@@ -1,0 +1,189 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares, argument
+validation returns error codes (no GPU needed), and the host-side logic (registry tables, config
+handling, state-dict layout, BN folding, weight packing, DeferredCost dispatch)."""
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dmb_oracle as O
+import seeded
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import __graft_entry__
+    __graft_entry__.build()
+    import densematchingbenchmark_b200 as pkg
+    return pkg
+
+
+def test_library_exports_every_declared_symbol(P):
+    from densematchingbenchmark_b200 import _cabi as C
+    lib = C.load()
+    header = open(os.path.join(ROOT, "include", "dmb_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(dmb_b200_\w+)\s*\(", header)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    bound = set(C.SIGNATURES) | set(C.OTHER)
+    assert set(declared) == bound, "ctypes table and header disagree: %s" % (set(declared) ^ bound)
+    assert lib.dmb_b200_abi_version() >= 1
+
+
+def test_argument_validation_without_gpu(P):
+    from densematchingbenchmark_b200 import _cabi as C
+    with pytest.raises(C.DmbB200Error) as e:
+        C.call("dmb_b200_cat_volume", None, None, None, 1, 4, 4, 4, C.int_array([0]), 1, None)
+    assert "null pointer" in str(e.value)
+    with pytest.raises(C.DmbB200Error):
+        C.call("dmb_b200_upsample_regress", None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 0, 1.0, 1, 0.0, 1.0, None, None)
+    with pytest.raises(C.DmbB200Error):   # CPU tensors are rejected by the binding: no CPU path
+        P.CAT_FUNCS["default"](torch.zeros(1, 2, 3, 4), torch.zeros(1, 2, 3, 4), max_disp=2)
+
+
+def test_tables_cover_reference_keys(P):
+    assert {"Concatenation", "Difference", "Correlation", "GroupWiseCorrelation"} <= set(P.PROCESSORS)
+    assert set(P.CAT_FUNCS) == {"default", "fast_mode"} and set(P.DIF_FUNCS) == {"default", "fast_mode"}
+    assert {"PSMNet", "AcfNet", "GCNet", "StereoNet"} <= set(P.AGGREGATORS)
+    assert set(P.PREDICTORS) == {"DEFAULT", "FASTER", "LOCAL"}
+
+
+def _cfg(P, agg="PSMNet"):
+    return P.ConfigDict(model=dict(
+        batch_norm=True,
+        cost_processor=dict(type="Concatenation",
+                            cost_computation=dict(type="default", max_disp=12, start_disp=0, dilation=1),
+                            cost_aggregator=dict(type=agg, max_disp=48, in_planes=64)),
+        disp_predictor=dict(type="FASTER", max_disp=48, start_disp=0, dilation=1, alpha=1.0, normalize=True)))
+
+
+@pytest.mark.parametrize("agg", ["PSMNet", "AcfNet"])
+def test_state_dict_layout_matches_reference(P, agg):
+    proc = P.build_cost_processor(_cfg(P, agg))
+    entries = seeded.aggregator_entries(agg, 64)
+    sd = proc.aggregator.state_dict()
+    assert list(sd.keys()) == [k for k, _, _ in entries]
+    for k, shape, _ in entries:
+        assert tuple(sd[k].shape) == tuple(shape)
+    proc.aggregator.load_state_dict(seeded.seeded_state_dict(entries, 0))     # loads unchanged
+    pred = P.build_disp_predictor(_cfg(P, agg))
+    assert list(pred.state_dict().keys()) == ["disp_regression.weight"]
+    assert torch.equal(pred.state_dict()["disp_regression.weight"].reshape(-1), O.disp_samples(48))
+    assert not pred.disp_regression.weight.requires_grad
+
+
+def test_builder_errors_like_reference(P):
+    cfg = _cfg(P)
+    cfg.model.cost_processor.type = "Nope"
+    with pytest.raises(AssertionError):
+        P.build_cost_processor(cfg)
+    cfg = _cfg(P)
+    cfg.model.cost_processor.cost_aggregator.type = "Nope"
+    with pytest.raises(AssertionError):
+        P.build_cost_processor(cfg)
+    cfg = _cfg(P)
+    cfg.model.disp_predictor.type = "Nope"
+    with pytest.raises(AssertionError):
+        P.build_disp_predictor(cfg)
+    # building must not consume the caller's config (reference copies before pop, builder.py:26-27)
+    cfg = _cfg(P)
+    P.build_cost_processor(cfg)
+    assert cfg.model.cost_processor.cost_computation.type == "default"
+
+
+def test_disp_indices_match_oracle(P):
+    from densematchingbenchmark_b200.ops import functional as F_
+    for md, sd, dil in ((48, 0, 1), (5, -2, 2), (10, 0, 3), (9, -4, 1), (192, 0, 1), (7, 3, 4)):
+        assert F_.disp_indices(md, sd, dil) == O.disp_indices(md, sd, dil)
+
+
+def test_bn_folding_and_weight_packing(P):
+    from densematchingbenchmark_b200.modeling.stereo.layers.basic_layers import conv3d_bn_relu, deconv3d_bn
+    torch.manual_seed(0)
+    for unit, transposed in ((conv3d_bn_relu(True, 6, 5, 3, 1, 1, bias=True), False),
+                             (deconv3d_bn(True, 6, 4, kernel_size=3, padding=1, output_padding=1, stride=2, bias=False), True)):
+        unit.eval()
+        unit[1].running_mean.normal_(0, 0.2); unit[1].running_var.uniform_(0.5, 2.0)
+        unit[1].weight.data.uniform_(0.5, 1.5); unit[1].bias.data.normal_(0, 0.1)
+        x = torch.randn(1, 6, 4, 5, 6)
+        with torch.no_grad():
+            conv = unit[0]
+            if transposed:
+                y = F.conv_transpose3d(x, conv.weight, conv.bias, stride=2, padding=1, output_padding=1)
+            else:
+                y = F.conv3d(x, conv.weight, conv.bias, padding=1)
+            want = unit[1](y)
+        wp, b = unit.folded()
+        K3, Cin, Cout = wp.shape
+        # un-pack and apply with torch to check the folded parameters themselves
+        if transposed:
+            w = wp.reshape(3, 3, 3, Cin, Cout).permute(3, 4, 0, 1, 2)
+            got = F.conv_transpose3d(x, w, b, stride=2, padding=1, output_padding=1)
+        else:
+            w = wp.reshape(3, 3, 3, Cin, Cout).permute(4, 3, 0, 1, 2)
+            got = F.conv3d(x, w, b, padding=1)
+        torch.testing.assert_close(got, want, atol=1e-5, rtol=1e-5)
+        again = unit.folded()
+        assert again[0] is wp                       # cached
+        unit[1].running_mean.add_(1.0)              # in-place change invalidates the cache
+        assert unit.folded()[0] is not wp
+
+
+def test_deferred_cost_dispatch(P, monkeypatch):
+    """Any op other than our predictors materialises the dense cost exactly once."""
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators import deferred
+    calls = {"n": 0}
+
+    def fake_upsample(low, out_dhw, mode="trilinear", up_weight=None, want_cost=True, want_disp=False, **kw):
+        calls["n"] += 1
+        cost = F.interpolate(low.unsqueeze(1), list(out_dhw), mode="trilinear", align_corners=True).squeeze(1)
+        return (cost if want_cost else None), (O.soft_argmin(cost, out_dhw[0]) if want_disp else None)
+
+    monkeypatch.setattr(deferred.F_, "upsample_regress", fake_upsample)
+    low = torch.randn(1, 3, 4, 5)
+    dc = deferred.DeferredCost(low, (12, 16, 20), "trilinear")
+    assert dc.dim() == 4 and tuple(dc.shape) == (1, 12, 16, 20) and dc.shape[1] == 12
+    want = F.interpolate(low.unsqueeze(1), [12, 16, 20], mode="trilinear", align_corners=True).squeeze(1)
+    torch.testing.assert_close(dc.regress(), O.soft_argmin(want, 12))        # fused route, nothing materialised
+    assert dc._dense is None
+    torch.testing.assert_close(torch.softmax(dc, dim=1), torch.softmax(want, dim=1))
+    torch.testing.assert_close(dc[:, ::2] * 2.0, want[:, ::2] * 2.0)
+    torch.testing.assert_close(dc.cpu().clone(), want)
+    assert calls["n"] == 2       # one regress + one materialisation
+
+
+def test_training_forward_is_refused_on_cpu_too(P):
+    from densematchingbenchmark_b200.modeling.stereo.layers.basic_layers import conv3d_bn
+    unit = conv3d_bn(True, 4, 4, 3, 1, 1).train()
+    with pytest.raises(NotImplementedError):
+        unit(torch.zeros(1, 4, 2, 2, 2))
+
+
+def test_spn_module_rejects_cpu(P):
+    from densematchingbenchmark_b200.ops import GateRecurrent2dnoind
+    z = torch.zeros(1, 1, 2, 2)
+    with pytest.raises(RuntimeError):
+        GateRecurrent2dnoind(True, False)(z, z, z, z)
+
+
+@pytest.mark.ref
+def test_dropin_swaps_reference_tables(P):
+    """With the reference importable (build container only), install_into_dmb() makes the stock
+    config resolve to our classes and the reference checkpoint layout still loads."""
+    import ref_import
+    ref_import.install()
+    replaced = P.install_into_dmb("dmb")
+    assert "PSMNet" in replaced["AGGREGATORS"]
+    cfg = ref_import.load_config("configs/PSMNet/scene_flow.py")
+    from dmb.modeling.stereo.cost_processors import build_cost_processor
+    from dmb.modeling.stereo.disp_predictors import build_disp_predictor
+    proc = build_cost_processor(cfg)
+    assert type(proc).__module__.startswith("densematchingbenchmark_b200")
+    assert type(proc.aggregator).__module__.startswith("densematchingbenchmark_b200")
+    assert type(build_disp_predictor(cfg)).__module__.startswith("densematchingbenchmark_b200")
