@@ -1,13 +1,553 @@
-// tcgen05 implicit-GEMM trunk -- placeholder entry points (the real kernels replace this file).
+// 3x3x3 convolution of the PSMNet/AcfNet trunk as an implicit GEMM on tcgen05 (sm_100a).
+//
+// Replaces cuDNN behind conv3d_bn[_relu] (dmb/modeling/stereo/layers/basic_layers.py:68-177) for the
+// stride-1 layers of PSMAggregator / AcfAggregator / Hourglass
+// (dmb/modeling/stereo/cost_processors/aggregators/PSMNet.py:30-53, utils/hourglass.py:40-52).
+// Oracle: oracle/dmb_oracle.py:conv_unit.
+//
+// Data layout ("blocked channels-last"): activations live in HBM as [B][C/8][D][H][W][8] bf16,
+// optionally as a (hi, lo) pair with x ~= hi + lo (hi = bf16(x), lo = bf16(x - hi)), which carries
+// ~16 mantissa bits through bf16 tensor-core MMAs with fp32 accumulation ("bf16x3": hi*hi + hi*lo
+// + lo*hi).  In this layout the 8 channels of one voxel are 16 contiguous bytes and consecutive
+// voxels along W follow at a 16-byte pitch -- exactly the UMMA "no-swizzle K-major" core-matrix
+// layout (8 rows x 16 bytes), so ONE TMA box per depth plane (halo tile of (16+2)x(8+2) voxels x
+// 32 channels, zero-filled outside the volume) serves all 9 in-plane taps: a tap is just a byte
+// offset on the shared-memory descriptor.  Depth planes stream through a 4-deep ring (each plane
+// is read from L2 ~1.4x instead of 27x).
+//
+// One pass = 32 input channels -> 32 output channels (the trunk's 64-channel layers run as
+// several passes that accumulate in place).  Per output plane tile (16x8 voxels = M 128):
+//   plain : 27 taps x 2 K-steps  MMAs  M128 N32 K16
+//   split : per (tap, K-step)   A_hi x [W_hi | W_lo] (N64)  +  A_lo x W_hi (N32, same columns)
+// accumulating in TMEM (double buffered), epilogue = bias + residual + ReLU + bf16 split + store.
+//
+// Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (warp 1 also
+// owns the TMEM allocation), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cuda.h>
+
 #include "common.cuh"
+
+namespace dmb {
+namespace tc {
+
+constexpr int TH = 16, TW = 8;              // output tile (in-plane), M = TH*TW = 128
+constexpr int HH = TH + 2, HW = TW + 2;     // halo tile
+constexpr int CB = 4;                       // 8-channel blocks per pass (32 input channels)
+constexpr int NB = 32;                      // output channels per pass
+constexpr int PLANE_BYTES = CB * HH * HW * 16;   // 11520
+constexpr uint32_t LBO_A = HH * HW * 16;    // byte distance between 8-channel blocks (K direction)
+constexpr uint32_t SBO_A = HW * 16;         // byte distance between groups of 8 rows (next h)
+constexpr int NSTAGE = 4;
+constexpr int TAPS = 27;
+constexpr int NTHREADS = 192;
+constexpr int TMEM_COLS = 128;
+
+struct Params {
+    const void* w_blob;        // this pass' packed weights
+    const float* bias;         // [32] or null
+    const uint4* res_hi;       // residual (blocked) or null
+    const uint4* res_lo;
+    uint4* y_hi;
+    uint4* y_lo;
+    float* y_f32;              // Cout==1 mode (NCDHW fp32), else null
+    const float* res_f32;
+    int B, D, H, W;
+    int in_cb0;                // first 8-channel block of the input tensor used by this pass
+    int y_cb0, y_cbs;          // first block / total blocks of y
+    int res_cb0, res_cbs;      // same for the residual tensor
+    int tiles_h, tiles_w, nseg, seg_len, n_items;
+    int relu;
+    int n_valid_out;           // output channels that exist (1 in y_f32 mode, else 32)
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+        "%7}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor layout):
+// [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout type 0
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack8(const uint4& q, float* f) {
+    const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(u[i] << 16);
+        f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+    }
+}
+
+template <bool SPLIT>
+struct Smem {
+    static constexpr int ROWS = SPLIT ? 2 * NB : NB;               // B-operand rows per channel block
+    static constexpr int TAP_BYTES = CB * ROWS * 16;               // 2048 / 4096
+    static constexpr int W_BYTES = TAPS * TAP_BYTES;               // 55296 / 110592
+    static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;
+    static constexpr int PLANES_OFF = W_BYTES;
+    static constexpr int BAR_OFF = PLANES_OFF + NSTAGE * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256;
+    static constexpr uint32_t LBO_B = ROWS * 16;
+    static constexpr uint32_t SBO_B = 128;
+    static constexpr int ACC_COLS = SPLIT ? 64 : 32;
+};
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
+    using S = Smem<SPLIT>;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* w_smem = smem;
+    unsigned char* planes = smem + S::PLANES_OFF;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // [NSTAGE]
+    uint64_t* empty = full + NSTAGE;                                    // [NSTAGE]
+    uint64_t* tfull = empty + NSTAGE;                                   // [2]
+    uint64_t* tempty = tfull + 2;                                       // [2]
+    uint64_t* wbar = tempty + 2;                                        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull[i], 1);
+            mbar_init(&tempty[i], 4);
+        }
+        mbar_init(wbar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {   // TMEM allocation (whole warp, .sync.aligned)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int items_per_b = p.tiles_w * p.tiles_h * p.nseg;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            // weights: packed in global exactly as they sit in shared memory
+            mbar_expect_tx(wbar, S::W_BYTES);
+            for (int t = 0; t < TAPS; ++t)
+                bulk_g2s(w_smem + t * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
+                         S::TAP_BYTES, wbar);
+            uint32_t n = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const int b = item / items_per_b;
+                int r = item - b * items_per_b;
+                const int seg = r / (p.tiles_w * p.tiles_h);
+                r -= seg * p.tiles_w * p.tiles_h;
+                const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
+                const int d0 = seg * p.seg_len;
+                const int d1 = min(p.D, d0 + p.seg_len);
+                const int h0 = th * TH, w0 = tw * TW;
+                for (int pl = d0 - 1; pl <= d1; ++pl, ++n) {
+                    const uint32_t slot = n % NSTAGE;
+                    const uint32_t ph = (n / NSTAGE) & 1;
+                    mbar_wait(&empty[slot], ph ^ 1);
+                    mbar_expect_tx(&full[slot], S::STAGE_BYTES);
+                    unsigned char* dst = planes + slot * S::STAGE_BYTES;
+                    tma_load_5d(dst, &map_hi, &full[slot], 8 * (w0 - 1), h0 - 1, pl, p.in_cb0, b);
+                    if (SPLIT) tma_load_5d(dst + PLANE_BYTES, &map_lo, &full[slot], 8 * (w0 - 1), h0 - 1, pl, p.in_cb0, b);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            constexpr uint32_t idesc_main = make_idesc(S::ROWS);
+            constexpr uint32_t idesc_lo = make_idesc(NB);
+            mbar_wait(wbar, 0);
+            const uint32_t w_addr = smem_u32(w_smem);
+            const uint32_t planes_addr = smem_u32(planes);
+            uint32_t n_base = 0, t = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int r = item % items_per_b;
+                const int seg = r / (p.tiles_w * p.tiles_h);
+                const int d0 = seg * p.seg_len;
+                const int d1 = min(p.D, d0 + p.seg_len);
+                const int nout = d1 - d0;
+                int waited = 0;
+                for (int od = 0; od < nout; ++od, ++t) {
+                    while (waited < od + 3) {
+                        const uint32_t n = n_base + waited;
+                        mbar_wait(&full[n % NSTAGE], (n / NSTAGE) & 1);
+                        ++waited;
+                    }
+                    const uint32_t buf = t & 1;
+                    mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
+                    tcgen05_fence_after();
+                    const uint32_t acc = tmem_base + buf * S::ACC_COLS;
+                    uint32_t first = 1;
+#pragma unroll 1
+                    for (int kd = 0; kd < 3; ++kd) {
+                        const uint32_t slot = (n_base + od + kd) % NSTAGE;
+                        const uint32_t a_hi = planes_addr + slot * S::STAGE_BYTES;
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int kw = 0; kw < 3; ++kw) {
+                                const int tap = (kd * 3 + kh) * 3 + kw;
+                                const uint32_t a_off = (kh * HW + kw) * 16;
+#pragma unroll
+                                for (int kk = 0; kk < CB / 2; ++kk) {
+                                    const uint64_t db = make_desc(w_addr + tap * S::TAP_BYTES + 2 * kk * S::LBO_B, S::LBO_B, S::SBO_B);
+                                    const uint64_t da = make_desc(a_hi + a_off + 2 * kk * LBO_A, LBO_A, SBO_A);
+                                    tcgen05_mma_bf16(acc, da, db, idesc_main, first ? 0u : 1u);
+                                    first = 0;
+                                    if (SPLIT) {
+                                        const uint64_t dl = make_desc(a_hi + PLANE_BYTES + a_off + 2 * kk * LBO_A, LBO_A, SBO_A);
+                                        tcgen05_mma_bf16(acc, dl, db, idesc_lo, 1u);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    tcgen05_commit(&tfull[buf]);
+                    tcgen05_commit(&empty[(n_base + od) % NSTAGE]);          // plane d-1 is done
+                    if (od == nout - 1) {
+                        tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
+                        tcgen05_commit(&empty[(n_base + od + 2) % NSTAGE]);
+                    }
+                }
+                n_base += nout + 2;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================ epilogue =====================================
+        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        const int hl = m >> 3, wl = m & 7;
+        float bias[NB];
+#pragma unroll
+        for (int c = 0; c < NB; ++c) bias[c] = (p.bias && c < p.n_valid_out) ? __ldg(p.bias + c) : 0.f;
+        const size_t plane_sz = (size_t)p.H * p.W;
+        uint32_t t = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const int b = item / items_per_b;
+            int r = item - b * items_per_b;
+            const int seg = r / (p.tiles_w * p.tiles_h);
+            r -= seg * p.tiles_w * p.tiles_h;
+            const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
+            const int d0 = seg * p.seg_len;
+            const int d1 = min(p.D, d0 + p.seg_len);
+            const int h = th * TH + hl, w = tw * TW + wl;
+            const bool valid = h < p.H && w < p.W;
+            for (int d = d0; d < d1; ++d, ++t) {
+                const uint32_t buf = t & 1;
+                mbar_wait(&tfull[buf], (t >> 1) & 1);
+                tcgen05_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
+                uint32_t r0[32];
+                float v[NB];
+                tmem_ld32(taddr, r0);
+                if (SPLIT) {
+                    uint32_t r1[32];
+                    tmem_ld32(taddr + 32, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                } else {
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]);
+                }
+                // the accumulator buffer is free as soon as it sits in registers
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                if (!valid) continue;
+                const size_t vox = (size_t)d * plane_sz + (size_t)h * p.W + w;
+                if (p.y_f32) {
+                    float o = v[0] + bias[0];
+                    const size_t oi = (size_t)b * p.D * plane_sz + vox;
+                    if (p.res_f32) o += __ldg(p.res_f32 + oi);
+                    if (p.relu) o = fmaxf(o, 0.f);
+                    p.y_f32[oi] = o;
+                    continue;
+                }
+#pragma unroll
+                for (int c = 0; c < NB; ++c) v[c] += bias[c];
+                if (p.res_hi) {
+#pragma unroll
+                    for (int cb = 0; cb < CB; ++cb) {
+                        const size_t ri = ((size_t)(b * p.res_cbs + p.res_cb0 + cb) * p.D) * plane_sz + vox;
+                        float f[8];
+                        unpack8(__ldg(p.res_hi + ri), f);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
+                        if (p.res_lo) {
+                            unpack8(__ldg(p.res_lo + ri), f);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
+                        }
+                    }
+                }
+                if (p.relu) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) v[c] = fmaxf(v[c], 0.f);
+                }
+#pragma unroll
+                for (int cb = 0; cb < CB; ++cb) {
+                    const size_t yi = ((size_t)(b * p.y_cbs + p.y_cb0 + cb) * p.D) * plane_sz + vox;
+                    float hi[8], lo[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float x = v[cb * 8 + e];
+                        const float hv = __bfloat162float(__float2bfloat16_rn(x));
+                        hi[e] = hv;
+                        lo[e] = x - hv;
+                    }
+                    p.y_hi[yi] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
+                                            pack_bf16x2(hi[6], hi[7]));
+                    if (p.y_lo)
+                        p.y_lo[yi] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]),
+                                                pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+                }
+            }
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- weight packing ---------------------------------------------------------------------------
+// w: [27][Cin][Cout] fp32  ->  blobs[(ob*IB + ib)] = [27][CB][ROWS][8] bf16, ROWS = 32 (plain) or 64 (hi rows, lo rows)
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout,
+                                    int split) {
+    const int rows = split ? 2 * NB : NB;
+    const int IB = Cin / 32, OB = (Cout + 31) / 32;
+    const size_t blob = (size_t)TAPS * CB * rows * 8;
+    const size_t total = blob * IB * OB;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int e = r % 8; r /= 8;
+        const int row = r % rows; r /= rows;
+        const int cb = r % CB; r /= CB;
+        const int tap = r % TAPS; r /= TAPS;
+        const int ib = r % IB;
+        const int ob = r / IB;
+        const int co = ob * 32 + (row % NB);
+        const int ci = ib * 32 + cb * 8 + e;
+        float v = (co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] : 0.f;
+        __nv_bfloat16 hi, lo;
+        split_bf16(v, hi, lo);
+        out[i] = (row < NB) ? hi : lo;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(DMB_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled entry point unavailable");
+    const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CBS, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
+                                   (cuuint64_t)CBS * D * H * W * 16};
+    const cuuint32_t box[5] = {HW * 8, HH, 1, CB, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DMB_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return DMB_OK;
+}
+
+static int device_ok() {
+    static int cached = -1;
+    if (cached < 0) {
+        int dev = 0, major = 0;
+        cached = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
+            encode_fn() != nullptr)
+            cached = 1;
+    }
+    return cached;
+}
+
+}  // namespace tc
+}  // namespace dmb
+
 using namespace dmb;
-extern "C" int dmb_b200_conv3d_tc(const void*, const void*, const void*, const void*, const float*, const void*,
-                                  const void*, void*, void*, float*, int, int, int, const int*, const int*, int, int,
-                                  void*) {
-    return fail(DMB_ERR_UNSUPPORTED, "conv3d_tc: not built yet");
+using namespace dmb::tc;
+
+extern "C" int dmb_b200_conv3d_tc_available(void) { return device_ok(); }
+
+extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split) {
+    if (Cin <= 0 || Cout <= 0 || Cin % 32) return 0;
+    const int64_t blob = (int64_t)TAPS * CB * (split ? 64 : 32) * 16;
+    return blob * (Cin / 32) * ((Cout + 31) / 32);
 }
-extern "C" int dmb_b200_conv3d_tc_pack_weights(const float*, void*, void*, int, int, void*) {
-    return fail(DMB_ERR_UNSUPPORTED, "conv3d_tc_pack_weights: not built yet");
+
+extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split,
+                                               void* stream) {
+    DMB_REQUIRE(w_packed && w_blob, "conv3d_tc_pack_weights: null pointer");
+    DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc_pack_weights: Cin=%d must be a multiple of 32", Cin);
+    DMB_REQUIRE(Cout > 0 && (Cout % 32 == 0 || Cout < 32), "conv3d_tc_pack_weights: Cout=%d must be <32 or a multiple of 32", Cout);
+    const int64_t n = dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, split) / 2;
+    pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w_packed, (__nv_bfloat16*)w_blob, Cin, Cout,
+                                                                                split ? 1 : 0);
+    return check_launch("pack_weights_kernel");
 }
-extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout) { return (int64_t)27 * (Cout < 16 ? 16 : Cout) * Cin * 2; }
-extern "C" int dmb_b200_conv3d_tc_available(void) { return 0; }
+
+extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, const float* bias,
+                                  const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
+                                  float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu,
+                                  void* stream) {
+    DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
+    DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
+    DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc: Cin=%d must be a multiple of 32", Cin);
+    const bool scalar_out = (Cout == 1);
+    DMB_REQUIRE(scalar_out || (Cout > 0 && Cout % 32 == 0), "conv3d_tc: Cout=%d must be 1 or a multiple of 32", Cout);
+    if (scalar_out)
+        DMB_REQUIRE(y_f32 && !y_hi, "conv3d_tc: Cout==1 writes y_f32 only");
+    else
+        DMB_REQUIRE(y_hi && !y_f32 && !res_f32, "conv3d_tc: Cout>=32 writes the blocked bf16 output");
+    DMB_REQUIRE(!res_lo || res_hi, "conv3d_tc: res_lo without res_hi");
+    if (!device_ok()) return fail(DMB_ERR_UNSUPPORTED, "conv3d_tc: needs an sm_100 device and a TMA-capable driver");
+    const bool split = x_lo != nullptr;
+    DMB_REQUIRE(scalar_out || split == (y_lo != nullptr), "conv3d_tc: x_lo and y_lo must both be given or both be NULL");
+
+    const int IB = Cin / 32, OB = scalar_out ? 1 : Cout / 32;
+    CUtensorMap map_hi, map_lo;
+    int rc = make_map(&map_hi, x_hi, B, Cin / 8, D, H, W);
+    if (rc) return rc;
+    rc = make_map(&map_lo, split ? x_lo : x_hi, B, Cin / 8, D, H, W);
+    if (rc) return rc;
+
+    Params p;
+    p.B = B; p.D = D; p.H = H; p.W = W;
+    p.n_valid_out = scalar_out ? 1 : 32;
+    p.tiles_h = (int)cdiv(H, TH);
+    p.tiles_w = (int)cdiv(W, TW);
+    // depth segments: enough work items to balance 148 persistent CTAs, segments >= 6 planes
+    const int cols = p.tiles_h * p.tiles_w * B;
+    int nseg = (int)cdiv((int64_t)sm_count() * 8, cols);
+    if (nseg > D / 6) nseg = D / 6;
+    if (nseg < 1) nseg = 1;
+    p.seg_len = (int)cdiv(D, nseg);
+    p.nseg = (int)cdiv(D, p.seg_len);
+    p.n_items = cols * p.nseg;
+    const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+
+    const size_t blob = (size_t)TAPS * CB * (split ? 64 : 32) * 16;
+    const size_t smem = split ? Smem<true>::TOTAL : Smem<false>::TOTAL;
+    if (split)
+        DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+        DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    for (int ob = 0; ob < OB; ++ob) {
+        for (int ib = 0; ib < IB; ++ib) {
+            const bool first = ib == 0, last = ib == IB - 1;
+            p.w_blob = reinterpret_cast<const unsigned char*>(w_blob) + (size_t)(ob * IB + ib) * blob;
+            p.bias = (first && bias) ? bias + ob * 32 : nullptr;
+            p.in_cb0 = ib * CB;
+            p.relu = (last && relu) ? 1 : 0;
+            p.y_hi = reinterpret_cast<uint4*>(y_hi);
+            p.y_lo = reinterpret_cast<uint4*>(y_lo);
+            p.y_cb0 = ob * CB;
+            p.y_cbs = scalar_out ? 0 : Cout / 8;
+            p.y_f32 = y_f32;
+            if (first) {                       // external residual joins on the first pass
+                p.res_hi = reinterpret_cast<const uint4*>(res_hi);
+                p.res_lo = reinterpret_cast<const uint4*>(res_lo);
+                p.res_cb0 = ob * CB;
+                p.res_cbs = p.y_cbs;
+                p.res_f32 = res_f32;
+            } else {                           // later passes accumulate onto the output in place
+                p.res_hi = reinterpret_cast<const uint4*>(y_hi);
+                p.res_lo = reinterpret_cast<const uint4*>(y_lo);
+                p.res_cb0 = ob * CB;
+                p.res_cbs = p.y_cbs;
+                p.res_f32 = y_f32;
+            }
+            if (split)
+                conv3d_tc_kernel<true><<<grid, NTHREADS, smem, as_stream(stream)>>>(map_hi, map_lo, p);
+            else
+                conv3d_tc_kernel<false><<<grid, NTHREADS, smem, as_stream(stream)>>>(map_hi, map_lo, p);
+            rc = check_launch("conv3d_tc_kernel");
+            if (rc) return rc;
+        }
+    }
+    return DMB_OK;
+}

@@ -272,90 +272,104 @@ __global__ void __launch_bounds__(256) warp_volume_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------
-// channels-last bf16 (hi[,lo]) layout helpers and the channels-last cat volume
+// blocked channels-last bf16 (hi[,lo]) layout of the tensor-core trunk: [B][C/8][S][8], S = D*H*W
 // ---------------------------------------------------------------------------------------
-// x: [B,C,S] fp32 (S = D*H*W) -> y: [B,S,C] bf16 hi/lo.  32x32 smem transpose tiles.
-__global__ void __launch_bounds__(256) ncs_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
-                                                        __nv_bfloat16* __restrict__ lo, int C, size_t S) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const size_t s0 = (size_t)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    for (int j = ty; j < 32; j += 8) {
-        const int c = c0 + j;
-        const size_t s = s0 + tx;
-        tile[j][tx] = (c < C && s < S) ? x[((size_t)b * C + c) * S + s] : 0.f;
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    float h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+        l[e] = v[e] - h[e];
     }
-    __syncthreads();
-    for (int j = ty; j < 32; j += 8) {
-        const size_t s = s0 + j;
-        const int c = c0 + tx;
-        if (s < S && c < C) {
-            __nv_bfloat16 h, l;
-            split_bf16(tile[tx][j], h, l);
-            const size_t o = ((size_t)b * S + s) * C + c;
-            hi[o] = h;
-            if (lo) lo[o] = l;
-        }
-    }
+    hi = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
+    lo = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
 }
 
-__global__ void __launch_bounds__(256) cl_to_ncs_kernel(const __nv_bfloat16* __restrict__ hi,
-                                                        const __nv_bfloat16* __restrict__ lo, float* __restrict__ y,
-                                                        int C, size_t S) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const size_t s0 = (size_t)blockIdx.x * 32;
-    const int c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int j = ty; j < 32; j += 8) {
-        const size_t s = s0 + j;
-        const int c = c0 + tx;
-        float v = 0.f;
-        if (s < S && c < C) {
-            const size_t o = ((size_t)b * S + s) * C + c;
-            v = __bfloat162float(hi[o]);
-            if (lo) v += __bfloat162float(lo[o]);
-        }
-        tile[j][tx] = v;
-    }
-    __syncthreads();
-    for (int j = ty; j < 32; j += 8) {
-        const int c = c0 + j;
-        const size_t s = s0 + tx;
-        if (c < C && s < S) y[((size_t)b * C + c) * S + s] = tile[tx][j];
-    }
-}
-
-// feats: [B,H,W,C] bf16 (channels last); out: [B,D,H,W,2C] bf16.  One thread per 16 bytes
-// (8 channels) of one voxel and plane; every load and store is a 16-byte vector access.
-__global__ void __launch_bounds__(256) cat_volume_cl_kernel(const uint4* __restrict__ l_hi, const uint4* __restrict__ l_lo,
-                                                            const uint4* __restrict__ r_hi, const uint4* __restrict__ r_lo,
-                                                            uint4* __restrict__ o_hi, uint4* __restrict__ o_lo,
-                                                            int B, int C8, int H, int W, int D, DispList dl) {
-    const int V = 2 * C8;                       // 16-byte vectors per voxel
-    const size_t total = (size_t)B * D * H * W * V;
+// x: [B,C,S] fp32 -> hi/lo: [B][C/8][S][8] bf16.  One thread per (b, cb, s): 8 strided-by-S reads
+// (coalesced across s) and one 16-byte store per plane.
+__global__ void __launch_bounds__(256) ncs_to_blocked_kernel(const float* __restrict__ x, uint4* __restrict__ hi,
+                                                             uint4* __restrict__ lo, int C, size_t S, size_t total) {
+    const int CBS = C / 8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int v = i % V;
-        size_t r = i / V;
-        const int x = r % W; r /= W;
-        const int y = r % H; r /= H;
-        const int k = r % D;
-        const int b = r / D;
-        const int d = dl.d[k];
-        uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
-        if (col_valid(x, d, W)) {
-            if (v < C8) {
-                const size_t s = (((size_t)b * H + y) * W + x) * C8 + v;
-                h = __ldg(l_hi + s);
-                if (o_lo) l = __ldg(l_lo + s);
-            } else {
-                const size_t s = (((size_t)b * H + y) * W + (x - d)) * C8 + (v - C8);
-                h = __ldg(r_hi + s);
-                if (o_lo) l = __ldg(r_lo + s);
+        const size_t s = i % S;
+        const size_t r = i / S;
+        const int cb = r % CBS;
+        const size_t b = r / CBS;
+        const float* src = x + (b * C + (size_t)cb * 8) * S + s;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e * S);
+        uint4 h, l;
+        split8(v, h, l);
+        hi[i] = h;
+        if (lo) lo[i] = l;
+    }
+}
+
+__global__ void __launch_bounds__(256) blocked_to_ncs_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo,
+                                                             float* __restrict__ y, int C, size_t S, size_t total) {
+    const int CBS = C / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = i % S;
+        const size_t r = i / S;
+        const int cb = r % CBS;
+        const size_t b = r / CBS;
+        const uint4 h = __ldg(hi + i);
+        const uint32_t hu[4] = {h.x, h.y, h.z, h.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[2 * k] = __uint_as_float(hu[k] << 16);
+            v[2 * k + 1] = __uint_as_float(hu[k] & 0xFFFF0000u);
+        }
+        if (lo) {
+            const uint4 l = __ldg(lo + i);
+            const uint32_t lu[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[2 * k] += __uint_as_float(lu[k] << 16);
+                v[2 * k + 1] += __uint_as_float(lu[k] & 0xFFFF0000u);
             }
         }
+        float* dst = y + (b * C + (size_t)cb * 8) * S + s;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dst[e * S] = v[e];
+    }
+}
+
+// cat volume straight into the blocked layout: out [B][2C/8][D][H][W][8] from fp32 NCHW features.
+// One thread per (b, cb, k, y, x).
+__global__ void __launch_bounds__(256) cat_volume_blocked_kernel(const float* __restrict__ left,
+                                                                 const float* __restrict__ right,
+                                                                 uint4* __restrict__ o_hi, uint4* __restrict__ o_lo,
+                                                                 int B, int C, int H, int W, int D, DispList dl,
+                                                                 size_t total) {
+    const int CBS = 2 * C / 8, CB_L = C / 8;
+    const size_t plane = (size_t)H * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t r = i;
+        const int x = r % W; r /= W;
+        const int y = r % H; r /= H;
+        const int k = r % D; r /= D;
+        const int cb = r % CBS;
+        const int b = r / CBS;
+        const int d = dl.d[k];
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        if (col_valid(x, d, W)) {
+            const bool is_r = cb >= CB_L;
+            const float* src = (is_r ? right : left) + ((size_t)b * C + (size_t)(is_r ? cb - CB_L : cb) * 8) * plane +
+                               (size_t)y * W + (is_r ? x - d : x);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e * plane);
+        }
+        uint4 h, l;
+        split8(v, h, l);
         __stcs(o_hi + i, h);
         if (o_lo) __stcs(o_lo + i, l);
     }
@@ -426,47 +440,46 @@ extern "C" int dmb_b200_warp_volume(const float* left, const float* right, const
     return check_launch("warp_volume_kernel");
 }
 
-extern "C" int dmb_b200_ncdhw_to_cl(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W,
-                                    void* stream) {
-    DMB_REQUIRE(x && y_hi, "ncdhw_to_cl: null pointer");
-    DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ncdhw_to_cl: non-positive dimension");
-    const size_t S = (size_t)D * H * W;
-    DMB_REQUIRE(B <= 65535 && cdiv(C, 32) <= 65535, "ncdhw_to_cl: grid dimension too large");
-    dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(C, 32), B);
-    ncs_to_cl_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, C, S);
-    return check_launch("ncs_to_cl_kernel");
+static unsigned grid_for(size_t total) {
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)sm_count() * 16;
+    return (unsigned)(blocks > cap ? cap : blocks);
 }
 
-extern "C" int dmb_b200_cl_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W,
-                                    void* stream) {
-    DMB_REQUIRE(x_hi && y, "cl_to_ncdhw: null pointer");
-    DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "cl_to_ncdhw: non-positive dimension");
-    const size_t S = (size_t)D * H * W;
-    DMB_REQUIRE(B <= 65535 && cdiv(C, 32) <= 65535, "cl_to_ncdhw: grid dimension too large");
-    dim3 grid((unsigned)cdiv(S, 32), (unsigned)cdiv(C, 32), B);
-    cl_to_ncs_kernel<<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, y, C, S);
-    return check_launch("cl_to_ncs_kernel");
+extern "C" int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W,
+                                         void* stream) {
+    DMB_REQUIRE(x && y_hi, "ncdhw_to_blocked: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ncdhw_to_blocked: non-positive dimension");
+    DMB_REQUIRE(C % 8 == 0, "ncdhw_to_blocked: C=%d must be a multiple of 8", C);
+    const size_t S = (size_t)D * H * W, total = (size_t)B * (C / 8) * S;
+    ncs_to_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)y_hi, (uint4*)y_lo, C, S, total);
+    return check_launch("ncs_to_blocked_kernel");
 }
 
-extern "C" int dmb_b200_cat_volume_cl(const void* l_hi, const void* l_lo, const void* r_hi, const void* r_lo,
-                                      void* out_hi, void* out_lo, int B, int C, int H, int W,
-                                      const int* disp_idx_host, int D, void* stream) {
-    DMB_REQUIRE(l_hi && r_hi && out_hi && disp_idx_host, "cat_volume_cl: null pointer");
-    DMB_REQUIRE(!out_lo || (l_lo && r_lo), "cat_volume_cl: out_lo given without l_lo/r_lo");
-    DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "cat_volume_cl: non-positive dimension");
-    DMB_REQUIRE(C % 8 == 0, "cat_volume_cl: C=%d must be a multiple of 8", C);
-    DMB_REQUIRE(D <= kMaxDisp, "cat_volume_cl: D=%d exceeds %d", D, kMaxDisp);
+extern "C" int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W,
+                                         void* stream) {
+    DMB_REQUIRE(x_hi && y, "blocked_to_ncdhw: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "blocked_to_ncdhw: non-positive dimension");
+    DMB_REQUIRE(C % 8 == 0, "blocked_to_ncdhw: C=%d must be a multiple of 8", C);
+    const size_t S = (size_t)D * H * W, total = (size_t)B * (C / 8) * S;
+    blocked_to_ncs_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)x_hi, (const uint4*)x_lo, y, C, S,
+                                                                         total);
+    return check_launch("blocked_to_ncs_kernel");
+}
+
+extern "C" int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out_hi, void* out_lo, int B,
+                                           int C, int H, int W, const int* disp_idx_host, int D, void* stream) {
+    DMB_REQUIRE(left && right && out_hi && disp_idx_host, "cat_volume_blocked: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "cat_volume_blocked: non-positive dimension");
+    DMB_REQUIRE(C % 8 == 0, "cat_volume_blocked: C=%d must be a multiple of 8", C);
+    DMB_REQUIRE(D <= kMaxDisp, "cat_volume_blocked: D=%d exceeds %d", D, kMaxDisp);
     DispList dl;
     for (int i = 0; i < D; ++i) {
         int d = disp_idx_host[i];
         dl.d[i] = d >= W ? W : (d <= -W ? -W : d);
     }
-    const size_t total = (size_t)B * D * H * W * (C / 4);
-    size_t blocks = (total + 255) / 256;
-    const size_t cap = (size_t)sm_count() * 16;
-    if (blocks > cap) blocks = cap;
-    cat_volume_cl_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(
-        (const uint4*)l_hi, (const uint4*)l_lo, (const uint4*)r_hi, (const uint4*)r_lo, (uint4*)out_hi, (uint4*)out_lo, B,
-        C / 8, H, W, D, dl);
-    return check_launch("cat_volume_cl_kernel");
+    const size_t total = (size_t)B * (2 * C / 8) * D * H * W;
+    cat_volume_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(left, right, (uint4*)out_hi, (uint4*)out_lo,
+                                                                             B, C, H, W, D, dl, total);
+    return check_launch("cat_volume_blocked_kernel");
 }

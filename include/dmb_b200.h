@@ -15,7 +15,7 @@
  *     stream) -- contrast the reference op which always uses the legacy stream
  *     (gaterecurrent2dnoind_kernel.cu:542);
  *   - tensors are dense, contiguous, in the layout stated per function; "NCDHW" etc. are the
- *     reference layouts, "NDHWC" (channels last) is the internal layout of the tensor-core trunk;
+ *     reference layouts, "blocked" = [B][C/8][D][H][W][8] bf16 is the internal layout of the tensor-core trunk;
  *   - all pointers are device pointers unless the name ends in `_host`;
  *   - the library is re-entrant per (device, stream); it keeps no global mutable state besides
  *     lazily-resolved driver entry points and per-device attribute caches.
@@ -147,36 +147,34 @@ int dmb_b200_lga(const float* x, const float* guidance, float* out,
  * pair that carries ~16 mantissa bits through bf16 MMAs with fp32 accumulation.
  * ---------------------------------------------------------------------------------------- */
 
-/* cat volume straight into the trunk's layout.  l_hi.. r_lo: channels-last features [B,H,W,C] bf16
- * (made by dmb_b200_ncdhw_to_cl with D=1); out_hi/out_lo: [B,D,H,W,2C] bf16.  *_lo == NULL =>
- * plain bf16 (no split).  C % 8 == 0. */
-int dmb_b200_cat_volume_cl(const void* l_hi, const void* l_lo, const void* r_hi, const void* r_lo,
-                           void* out_hi, void* out_lo,
-                           int B, int C, int H, int W, const int* disp_idx_host, int D, void* stream);
+/* cat volume straight into the trunk's blocked layout: out_hi/out_lo [B][2C/8][D][H][W][8] bf16
+ * from the float32 NCHW features (out_lo NULL => plain bf16, no split).  C % 8 == 0. */
+int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out_hi, void* out_lo,
+                                int B, int C, int H, int W, const int* disp_idx_host, int D, void* stream);
 
-/* 3x3x3 convolution / stride-2 convolution / stride-2 transposed convolution on tcgen05.
- * x_hi/x_lo: [B,Di,Hi,Wi,Cin] bf16; w_hi/w_lo: packed by dmb_b200_conv3d_tc_pack_weights;
- * bias [Cout] f32 or NULL; res_hi/res_lo residual (same shape as y) or NULL; relu 0/1;
- * y_hi/y_lo: [B,Do,Ho,Wo,Cout] bf16.  *_lo == NULL selects plain bf16 for that tensor.
- * y_f32 (nullable): also/only write y as [B,Cout,Do,Ho,Wo] float32 (NCDHW; used for Cout==1).
- * kind: 0 = stride-1 conv, 1 = stride-2 conv, 2 = stride-2 transposed conv (k3,p1,op1). */
-int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
-                       const float* bias, const void* res_hi, const void* res_lo,
-                       void* y_hi, void* y_lo, float* y_f32,
-                       int B, int Cin, int Cout, const int* dims_in, const int* dims_out,
-                       int kind, int relu, void* stream);
-/* w: [27][Cin][Cout] float32 (same packing as conv3d_direct) -> w_hi/w_lo bf16 in the layout the
- * kernel's TMA descriptor expects ([27][Cout_pad][Cin], K-major). Cout_pad = max(Cout,16). */
-int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_hi, void* w_lo,
-                                    int Cin, int Cout, void* stream);
-/* bytes of one packed weight plane */
-int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout);
-/* 1 if this device/build can run the tcgen05 path */
+/* 3x3x3 stride-1 pad-1 convolution on tcgen05, blocked channels-last activations.
+ * x_hi/x_lo: [B][Cin/8][D][H][W][8] bf16 (x_lo NULL => plain bf16, else the (hi,lo) split pair).
+ * w_blob: packed by dmb_b200_conv3d_tc_pack_weights with the same `split`.
+ * bias [Cout] f32 or NULL (BatchNorm folded by the caller, as for conv3d_direct).
+ * Cout % 32 == 0: y_hi/y_lo [B][Cout/8][D][H][W][8] bf16 (+ optional residual res_hi/res_lo of the
+ *                 same geometry, added before the ReLU);
+ * Cout == 1     : y_f32 [B,1,D,H,W] float32 (+ optional res_f32 of the same shape) -- the 32->1
+ *                 classifier heads (aggregators/PSMNet.py:41-52).
+ * Cin % 32 == 0.  64-channel layers run as several 32->32 passes accumulating in place. */
+int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, const float* bias,
+                       const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
+                       float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu, void* stream);
+/* w_packed: [27][Cin][Cout] float32 (the conv3d_direct packing) -> w_blob (bf16), one
+ * [27][4][32|64][8] block per (32 out, 32 in) channel pair; split=1 stores hi rows then lo rows. */
+int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split, void* stream);
+/* bytes of the packed blob */
+int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split);
+/* 1 if this device/driver can run the tcgen05 path */
 int dmb_b200_conv3d_tc_available(void);
 
-/* layout helpers for the trunk boundary */
-int dmb_b200_ncdhw_to_cl(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, void* stream);
-int dmb_b200_cl_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W, void* stream);
+/* layout helpers for the trunk boundary: [B,C,D,H,W] float32 <-> [B][C/8][D][H][W][8] bf16 (hi[,lo]) */
+int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, void* stream);
+int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

@@ -200,7 +200,7 @@ def test_upsample_regress_trilinear_vs_oracle(P, shape):
     torch.testing.assert_close(cost.cpu(), want_cost, atol=2e-5, rtol=1e-5)
     torch.testing.assert_close(disp.cpu(), want_disp, atol=1e-4, rtol=1e-5)
     _, disp2 = F_.upsample_regress(low.to(DEV), (D, H, W), "trilinear", want_cost=False, want_disp=True)
-    assert torch.equal(disp2, disp)
+    torch.testing.assert_close(disp2, disp, atol=1e-5, rtol=1e-6)   # other template instance: FMA contraction may differ
     torch.testing.assert_close(O.trilinear_up(low, (D, H, W)).squeeze(1), want_cost, atol=1e-5, rtol=1e-5)
 
 
@@ -370,3 +370,94 @@ def test_bad_arguments_return_errors_not_aborts(P):
         C.call("dmb_b200_gwc_volume", C.ptr(z), C.ptr(z), C.ptr(z), 1, 6, 4, 4, 4, C.int_array([0]), 1, None)
     with pytest.raises(ValueError):
         P.CAT_FUNCS["default"](z, torch.zeros(1, 6, 4, 5, device=DEV), max_disp=4)
+
+
+# ------------------------------------------------------------------------------- tcgen05 trunk
+def _tc_or_skip():
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators import tc_engine
+    if not tc_engine.tc_available():
+        pytest.skip("tcgen05 path unavailable on this device")
+    return tc_engine
+
+
+def test_blocked_layout_roundtrip(P):
+    tc = _tc_or_skip()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 16, 3, 5, 7, generator=g)
+    blk = tc.Blocked.from_ncdhw(x.to(DEV), True)
+    back = blk.to_ncdhw().cpu()
+    assert float((back - x).abs().max()) < 2e-5 * float(x.abs().max())          # hi+lo carries ~16 bits
+    hi = blk.hi.view(2, 2, 3, 5, 7, 8).float().cpu()
+    want = x.view(2, 2, 8, 3, 5, 7).permute(0, 1, 3, 4, 5, 2)
+    torch.testing.assert_close(hi, want.bfloat16().float())
+    plain = tc.Blocked.from_ncdhw(x.to(DEV), False)
+    torch.testing.assert_close(plain.to_ncdhw().cpu(), x.bfloat16().float())
+
+
+TC_CASES = [
+    # Cin, Cout, dims, bias, residual, relu
+    (32, 32, (4, 16, 8), False, False, False),        # exactly one tile, one depth segment
+    (32, 32, (5, 19, 13), True, False, True),         # ragged tile edges
+    (64, 32, (6, 20, 24), False, False, True),        # two input passes accumulating in place
+    (32, 32, (7, 33, 17), True, True, False),         # residual, several tiles
+    (64, 64, (6, 18, 16), True, True, True),          # 2x2 passes
+    (32, 1, (6, 17, 12), False, True, False),         # classifier head, fp32 output + fp32 residual
+    (32, 32, (14, 40, 24), False, False, True),       # several depth segments per column
+]
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv3d_tc_vs_torch_cpu(P, case, split):
+    tc = _tc_or_skip()
+    cin, cout, dims, bias, residual, relu = case
+    g = torch.Generator().manual_seed(cin + cout + dims[1])
+    x = torch.randn(2, cin, *dims, generator=g)
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) * (2.0 / (cin * 27)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1 if bias else None
+    res = torch.randn(2, cout, *dims, generator=g) if residual else None
+    conv = torch.nn.Conv3d(cin, cout, 3, 1, 1, bias=bias)
+    conv.weight.data.copy_(w)
+    if bias:
+        conv.bias.data.copy_(b)
+    conv = conv.to(DEV)
+    if not split:   # plain bf16: compare against bf16-rounded operands with fp32 accumulation
+        xr, wr = x.bfloat16().float(), w.bfloat16().float()
+        rr = res.bfloat16().float() if (res is not None and cout > 1) else res
+    else:
+        xr, wr, rr = x, w, res
+    ref = F.conv3d(xr, wr, b, padding=1)
+    if rr is not None:
+        ref = ref + rr
+    if relu:
+        ref = F.relu(ref)
+    xb = tc.Blocked.from_ncdhw(x.to(DEV), split)
+    if cout == 1:
+        got = tc.conv_tc(conv, xb, relu=relu, res_f32=res.to(DEV) if residual else None).cpu()
+        tol = 3e-5 if split else 2e-5
+    else:
+        rb = tc.Blocked.from_ncdhw(res.to(DEV), split) if residual else None
+        got = tc.conv_tc(conv, xb, rb, relu=relu).to_ncdhw().cpu()
+        tol = 3e-5 if split else 1.2e-2       # plain: the OUTPUT is rounded to bf16 once more
+    err = float((got - ref).abs().max())
+    assert err < tol * max(1.0, float(ref.abs().max())), err
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 0.5)])
+def test_config1_tc_engine_vs_reference_golden(P, golden_dir, precision, tol):
+    _tc_or_skip()
+    rec = _load(golden_dir, "aggregators.pt")["PSMNet_sharp"]
+    cfg = _cfg(P, "PSMNet")
+    proc = P.build_cost_processor(cfg)
+    pred = P.build_disp_predictor(cfg)
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=rec["seed"], sharpen=rec["sharpen"])
+    proc.aggregator.load_state_dict(sd)
+    proc = proc.to(DEV).eval(); pred = pred.to(DEV).eval()
+    proc.aggregator.engine = "tc"
+    proc.aggregator.precision = precision
+    l, r = seeded.feature_pair(1, 32, 16, 32, seed=100 + rec["seed"], scale=0.5, shift=rec["shift"])
+    disps = [pred(c).cpu() for c in proc(l.to(DEV), r.to(DEV))]
+    worst = max(float((d - w).abs().max()) for d, w in zip(disps, rec["disps"]))
+    mean = max(float((d - w).abs().mean()) for d, w in zip(disps, rec["disps"]))
+    print("tc engine %s: max |d_disp| %.3e mean %.3e" % (precision, worst, mean))
+    assert worst < tol
