@@ -18,12 +18,14 @@
 // One pass = 32 input channels -> 32 output channels (the trunk's 64-channel layers run as
 // several passes that accumulate in place).  Per output plane tile (16x8 voxels = M 128):
 //   plain : 27 taps x 2 K-steps  MMAs  M128 N32 K16
-//   split : per (tap, K-step)   A_hi x [W_hi | W_lo] (N64)  +  A_lo x W_hi (N32, same columns)
-// accumulating in TMEM (double buffered), epilogue = bias + residual + ReLU + bf16 split + store.
+//   split : per (tap, K-step)   A_hi x [W_hi | W_lo] (N64)  +  A_lo x W_hi (N32, own columns)
+// accumulating in TMEM (one short chain per depth tap, double buffered), epilogue = sum of the
+// chains + bias + residual + ReLU + 16-bit split + store.
 //
 // Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (warp 1 also
 // owns the TMEM allocation), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -40,7 +42,7 @@ constexpr uint32_t SBO_A = HW * 16;         // byte distance between groups of 8
 constexpr int NSTAGE = 4;
 constexpr int TAPS = 27;
 constexpr int NTHREADS = 192;
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = 512;
 
 struct Params {
     const void* w_blob;        // this pass' packed weights
@@ -58,6 +60,7 @@ struct Params {
     int tiles_h, tiles_w, nseg, seg_len, n_items;
     int relu;
     int n_valid_out;           // output channels that exist (1 in y_f32 mode, else 32)
+    float acc_scale;           // 2^-k undoing the power-of-two weight pre-scaling (exact)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -104,20 +107,38 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, 
            (1ull << 46);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// fmt: 0 = F16, 1 = BF16 (UMMA::F16F32Format)
+__host__ __device__ constexpr uint32_t make_idesc(int n, uint32_t fmt) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+// 16-bit element codecs: FP16 = true -> IEEE half (11-bit significand), false -> bfloat16 (8-bit)
+template <bool FP16>
+__device__ __forceinline__ float round16(float x) {
+    return FP16 ? __half2float(__float2half_rn(x)) : __bfloat162float(__float2bfloat16_rn(x));
+}
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if (FP16) {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+template <bool FP16>
 __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(u[i] << 16);
-        f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+        if (FP16) {
+            const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+            f[2 * i] = t.x;
+            f[2 * i + 1] = t.y;
+        } else {
+            f[2 * i] = __uint_as_float(u[i] << 16);
+            f[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+        }
     }
 }
 
@@ -132,10 +153,16 @@ struct Smem {
     static constexpr int TOTAL = BAR_OFF + 256;
     static constexpr uint32_t LBO_B = ROWS * 16;
     static constexpr uint32_t SBO_B = 128;
-    static constexpr int ACC_COLS = SPLIT ? 64 : 32;
+    // The tensor core adds each K=16 partial product into the fp32 accumulator with truncation
+    // (measured: error biased toward zero, growing with the chain length).  Accumulation chains are
+    // therefore kept short: one accumulator per depth tap kd (18 MMAs deep) and, in split mode, a
+    // separate one for the small lo*hi term; the epilogue adds them with round-to-nearest.
+    static constexpr int KD_COLS = SPLIT ? 64 : 32;                // [hi*Whi | hi*Wlo] of one kd
+    static constexpr int LH_COL = 3 * KD_COLS;                     // lo*Whi (split only)
+    static constexpr int ACC_COLS = SPLIT ? 3 * 64 + 32 : 3 * 32;  // 224 / 96 columns per buffer
 };
 
-template <bool SPLIT>
+template <bool SPLIT, bool FP16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
     using S = Smem<SPLIT>;
@@ -210,8 +237,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
-            constexpr uint32_t idesc_main = make_idesc(S::ROWS);
-            constexpr uint32_t idesc_lo = make_idesc(NB);
+            constexpr uint32_t idesc_main = make_idesc(S::ROWS, FP16 ? 0u : 1u);
+            constexpr uint32_t idesc_lo = make_idesc(NB, FP16 ? 0u : 1u);
             mbar_wait(wbar, 0);
             const uint32_t w_addr = smem_u32(w_smem);
             const uint32_t planes_addr = smem_u32(planes);
@@ -232,12 +259,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                     const uint32_t buf = t & 1;
                     mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
                     tcgen05_fence_after();
-                    const uint32_t acc = tmem_base + buf * S::ACC_COLS;
-                    uint32_t first = 1;
+                    const uint32_t acc0 = tmem_base + buf * S::ACC_COLS;
+                    uint32_t first_lo = 1;
 #pragma unroll 1
                     for (int kd = 0; kd < 3; ++kd) {
                         const uint32_t slot = (n_base + od + kd) % NSTAGE;
                         const uint32_t a_hi = planes_addr + slot * S::STAGE_BYTES;
+                        const uint32_t acc = acc0 + kd * S::KD_COLS;
+                        uint32_t first = 1;
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
@@ -252,7 +281,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                                     first = 0;
                                     if (SPLIT) {
                                         const uint64_t dl = make_desc(a_hi + PLANE_BYTES + a_off + 2 * kk * LBO_A, LBO_A, SBO_A);
-                                        tcgen05_mma_bf16(acc, dl, db, idesc_lo, 1u);
+                                        tcgen05_mma_bf16(acc0 + S::LH_COL, dl, db, idesc_lo, first_lo ? 0u : 1u);
+                                        first_lo = 0;
                                     }
                                 }
                             }
@@ -294,19 +324,40 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                 mbar_wait(&tfull[buf], (t >> 1) & 1);
                 tcgen05_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
-                uint32_t r0[32];
+                uint32_t r0[32], r1[32];
                 float v[NB];
-                tmem_ld32(taddr, r0);
                 if (SPLIT) {
-                    uint32_t r1[32];
+                    // small terms first: hi*Wlo of the three kd chains + lo*Whi, then the hi*Whi chains
+                    float sm[NB];
+                    tmem_ld32(taddr + 32, r0);
+                    tmem_ld32(taddr + 64 + 32, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) sm[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                    tmem_ld32(taddr + 128 + 32, r0);
+                    tmem_ld32(taddr + S::LH_COL, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) sm[c] += __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                    tmem_ld32(taddr, r0);
+                    tmem_ld32(taddr + 64, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                    tmem_ld32(taddr + 128, r0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) v[c] = ((v[c] + __uint_as_float(r0[c])) + sm[c]) * p.acc_scale;
+                } else {
+                    tmem_ld32(taddr, r0);
                     tmem_ld32(taddr + 32, r1);
                     tmem_ld_wait();
 #pragma unroll
                     for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
-                } else {
+                    tmem_ld32(taddr + 64, r0);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]);
+                    for (int c = 0; c < NB; ++c) v[c] = (v[c] + __uint_as_float(r0[c])) * p.acc_scale;
                 }
                 // the accumulator buffer is free as soon as it sits in registers
                 tcgen05_fence_before();
@@ -329,11 +380,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
                     for (int cb = 0; cb < CB; ++cb) {
                         const size_t ri = ((size_t)(b * p.res_cbs + p.res_cb0 + cb) * p.D) * plane_sz + vox;
                         float f[8];
-                        unpack8(__ldg(p.res_hi + ri), f);
+                        unpack8<FP16>(__ldg(p.res_hi + ri), f);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
                         if (p.res_lo) {
-                            unpack8(__ldg(p.res_lo + ri), f);
+                            unpack8<FP16>(__ldg(p.res_lo + ri), f);
 #pragma unroll
                             for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
                         }
@@ -350,15 +401,15 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const float x = v[cb * 8 + e];
-                        const float hv = __bfloat162float(__float2bfloat16_rn(x));
+                        const float hv = round16<FP16>(x);
                         hi[e] = hv;
                         lo[e] = x - hv;
                     }
-                    p.y_hi[yi] = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), pack_bf16x2(hi[4], hi[5]),
-                                            pack_bf16x2(hi[6], hi[7]));
+                    p.y_hi[yi] = make_uint4(pack2<FP16>(hi[0], hi[1]), pack2<FP16>(hi[2], hi[3]), pack2<FP16>(hi[4], hi[5]),
+                                            pack2<FP16>(hi[6], hi[7]));
                     if (p.y_lo)
-                        p.y_lo[yi] = make_uint4(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]),
-                                                pack_bf16x2(lo[4], lo[5]), pack_bf16x2(lo[6], lo[7]));
+                        p.y_lo[yi] = make_uint4(pack2<FP16>(lo[0], lo[1]), pack2<FP16>(lo[2], lo[3]),
+                                                pack2<FP16>(lo[4], lo[5]), pack2<FP16>(lo[6], lo[7]));
                 }
             }
         }
@@ -374,8 +425,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 
 // ---- weight packing ---------------------------------------------------------------------------
 // w: [27][Cin][Cout] fp32  ->  blobs[(ob*IB + ib)] = [27][CB][ROWS][8] bf16, ROWS = 32 (plain) or 64 (hi rows, lo rows)
-__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cin, int Cout,
-                                    int split) {
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cin, int Cout,
+                                    int split, int fp16, float scale) {
     const int rows = split ? 2 * NB : NB;
     const int IB = Cin / 32, OB = (Cout + 31) / 32;
     const size_t blob = (size_t)TAPS * CB * rows * 8;
@@ -390,10 +441,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
         const int ob = r / IB;
         const int co = ob * 32 + (row % NB);
         const int ci = ib * 32 + cb * 8 + e;
-        float v = (co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] : 0.f;
-        __nv_bfloat16 hi, lo;
-        split_bf16(v, hi, lo);
-        out[i] = (row < NB) ? hi : lo;
+        const float v = (co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] * scale : 0.f;
+        if (fp16) {
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            out[i] = (row < NB) ? __half_as_ushort(hi) : __half_as_ushort(lo);
+        } else {
+            __nv_bfloat16 hi, lo;
+            split_bf16(v, hi, lo);
+            out[i] = (row < NB) ? __bfloat16_as_ushort(hi) : __bfloat16_as_ushort(lo);
+        }
     }
 }
 
@@ -416,7 +473,7 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W) {
+static int make_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W, int fp16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(DMB_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled entry point unavailable");
     const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CBS, (cuuint64_t)B};
@@ -424,7 +481,7 @@ static int make_map(CUtensorMap* map, const void* base, int B, int CBS, int D, i
                                    (cuuint64_t)CBS * D * H * W * 16};
     const cuuint32_t box[5] = {HW * 8, HH, 1, CB, 1};
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(DMB_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -459,29 +516,39 @@ extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split)
 }
 
 extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split,
-                                               void* stream) {
+                                               int fp16, float scale, void* stream) {
     DMB_REQUIRE(w_packed && w_blob, "conv3d_tc_pack_weights: null pointer");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc_pack_weights: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(Cout > 0 && (Cout % 32 == 0 || Cout < 32), "conv3d_tc_pack_weights: Cout=%d must be <32 or a multiple of 32", Cout);
+    DMB_REQUIRE(scale > 0.f, "conv3d_tc_pack_weights: scale must be positive");
     const int64_t n = dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, split) / 2;
-    pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w_packed, (__nv_bfloat16*)w_blob, Cin, Cout,
-                                                                                split ? 1 : 0);
+    pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w_packed, (uint16_t*)w_blob, Cin, Cout,
+                                                                                split ? 1 : 0, fp16 ? 1 : 0, scale);
     return check_launch("pack_weights_kernel");
 }
 
-extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, const float* bias,
-                                  const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
-                                  float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu,
-                                  void* stream) {
+template <bool SPLIT, bool FP16>
+static int launch_pass(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const Params& p, int grid, void* stream) {
+    const size_t smem = Smem<SPLIT>::TOTAL;
+    DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<SPLIT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_tc_kernel<SPLIT, FP16><<<grid, NTHREADS, smem, as_stream(stream)>>>(map_hi, map_lo, p);
+    return check_launch("conv3d_tc_kernel");
+}
+
+extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
+                                  const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
+                                  int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu,
+                                  int fp16, void* stream) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc: Cin=%d must be a multiple of 32", Cin);
+    DMB_REQUIRE(w_scale > 0.f, "conv3d_tc: w_scale must be positive");
     const bool scalar_out = (Cout == 1);
     DMB_REQUIRE(scalar_out || (Cout > 0 && Cout % 32 == 0), "conv3d_tc: Cout=%d must be 1 or a multiple of 32", Cout);
     if (scalar_out)
         DMB_REQUIRE(y_f32 && !y_hi, "conv3d_tc: Cout==1 writes y_f32 only");
     else
-        DMB_REQUIRE(y_hi && !y_f32 && !res_f32, "conv3d_tc: Cout>=32 writes the blocked bf16 output");
+        DMB_REQUIRE(y_hi && !y_f32 && !res_f32, "conv3d_tc: Cout>=32 writes the blocked 16-bit output");
     DMB_REQUIRE(!res_lo || res_hi, "conv3d_tc: res_lo without res_hi");
     if (!device_ok()) return fail(DMB_ERR_UNSUPPORTED, "conv3d_tc: needs an sm_100 device and a TMA-capable driver");
     const bool split = x_lo != nullptr;
@@ -489,14 +556,15 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
 
     const int IB = Cin / 32, OB = scalar_out ? 1 : Cout / 32;
     CUtensorMap map_hi, map_lo;
-    int rc = make_map(&map_hi, x_hi, B, Cin / 8, D, H, W);
+    int rc = make_map(&map_hi, x_hi, B, Cin / 8, D, H, W, fp16);
     if (rc) return rc;
-    rc = make_map(&map_lo, split ? x_lo : x_hi, B, Cin / 8, D, H, W);
+    rc = make_map(&map_lo, split ? x_lo : x_hi, B, Cin / 8, D, H, W, fp16);
     if (rc) return rc;
 
     Params p;
     p.B = B; p.D = D; p.H = H; p.W = W;
     p.n_valid_out = scalar_out ? 1 : 32;
+    p.acc_scale = 1.0f / w_scale;
     p.tiles_h = (int)cdiv(H, TH);
     p.tiles_w = (int)cdiv(W, TW);
     // depth segments: enough work items to balance 148 persistent CTAs, segments >= 6 planes
@@ -508,13 +576,7 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     p.nseg = (int)cdiv(D, p.seg_len);
     p.n_items = cols * p.nseg;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-
     const size_t blob = (size_t)TAPS * CB * (split ? 64 : 32) * 16;
-    const size_t smem = split ? Smem<true>::TOTAL : Smem<false>::TOTAL;
-    if (split)
-        DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-        DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int ob = 0; ob < OB; ++ob) {
         for (int ib = 0; ib < IB; ++ib) {
@@ -528,24 +590,23 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
             p.y_cb0 = ob * CB;
             p.y_cbs = scalar_out ? 0 : Cout / 8;
             p.y_f32 = y_f32;
-            if (first) {                       // external residual joins on the first pass
+            p.res_cb0 = ob * CB;
+            p.res_cbs = p.y_cbs;
+            if (first) {                       // the external residual joins on the first pass
                 p.res_hi = reinterpret_cast<const uint4*>(res_hi);
                 p.res_lo = reinterpret_cast<const uint4*>(res_lo);
-                p.res_cb0 = ob * CB;
-                p.res_cbs = p.y_cbs;
                 p.res_f32 = res_f32;
             } else {                           // later passes accumulate onto the output in place
                 p.res_hi = reinterpret_cast<const uint4*>(y_hi);
                 p.res_lo = reinterpret_cast<const uint4*>(y_lo);
-                p.res_cb0 = ob * CB;
-                p.res_cbs = p.y_cbs;
                 p.res_f32 = y_f32;
             }
             if (split)
-                conv3d_tc_kernel<true><<<grid, NTHREADS, smem, as_stream(stream)>>>(map_hi, map_lo, p);
+                rc = fp16 ? launch_pass<true, true>(map_hi, map_lo, p, grid, stream)
+                          : launch_pass<true, false>(map_hi, map_lo, p, grid, stream);
             else
-                conv3d_tc_kernel<false><<<grid, NTHREADS, smem, as_stream(stream)>>>(map_hi, map_lo, p);
-            rc = check_launch("conv3d_tc_kernel");
+                rc = fp16 ? launch_pass<false, true>(map_hi, map_lo, p, grid, stream)
+                          : launch_pass<false, false>(map_hi, map_lo, p, grid, stream);
             if (rc) return rc;
         }
     }

@@ -9,6 +9,8 @@
 // volume.  The row is staged ONCE per CTA in shared memory with a 1-D bulk async copy (TMA
 // engine, UBLKCP) and re-read from there for every disparity; the volume is written with
 // 16-byte streaming stores.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace dmb {
@@ -274,25 +276,39 @@ __global__ void __launch_bounds__(256) warp_volume_kernel(const float* __restric
 // ---------------------------------------------------------------------------------------
 // blocked channels-last bf16 (hi[,lo]) layout of the tensor-core trunk: [B][C/8][S][8], S = D*H*W
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
+__device__ __forceinline__ uint32_t pack2(float a, float b, int fp16) {
+    if (fp16) {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+__device__ __forceinline__ void unpack2(uint32_t u, int fp16, float& a, float& b) {
+    if (fp16) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u));
+        a = t.x;
+        b = t.y;
+    } else {
+        a = __uint_as_float(u << 16);
+        b = __uint_as_float(u & 0xFFFF0000u);
+    }
+}
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo, int fp16) {
     float h[8], l[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        h[e] = __bfloat162float(__float2bfloat16_rn(v[e]));
+        h[e] = fp16 ? __half2float(__float2half_rn(v[e])) : __bfloat162float(__float2bfloat16_rn(v[e]));
         l[e] = v[e] - h[e];
     }
-    hi = make_uint4(pack2(h[0], h[1]), pack2(h[2], h[3]), pack2(h[4], h[5]), pack2(h[6], h[7]));
-    lo = make_uint4(pack2(l[0], l[1]), pack2(l[2], l[3]), pack2(l[4], l[5]), pack2(l[6], l[7]));
+    hi = make_uint4(pack2(h[0], h[1], fp16), pack2(h[2], h[3], fp16), pack2(h[4], h[5], fp16), pack2(h[6], h[7], fp16));
+    lo = make_uint4(pack2(l[0], l[1], fp16), pack2(l[2], l[3], fp16), pack2(l[4], l[5], fp16), pack2(l[6], l[7], fp16));
 }
 
 // x: [B,C,S] fp32 -> hi/lo: [B][C/8][S][8] bf16.  One thread per (b, cb, s): 8 strided-by-S reads
 // (coalesced across s) and one 16-byte store per plane.
 __global__ void __launch_bounds__(256) ncs_to_blocked_kernel(const float* __restrict__ x, uint4* __restrict__ hi,
-                                                             uint4* __restrict__ lo, int C, size_t S, size_t total) {
+                                                             uint4* __restrict__ lo, int C, size_t S, size_t total, int fp16) {
     const int CBS = C / 8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t s = i % S;
@@ -304,14 +320,15 @@ __global__ void __launch_bounds__(256) ncs_to_blocked_kernel(const float* __rest
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e * S);
         uint4 h, l;
-        split8(v, h, l);
+        split8(v, h, l, fp16);
         hi[i] = h;
         if (lo) lo[i] = l;
     }
 }
 
 __global__ void __launch_bounds__(256) blocked_to_ncs_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo,
-                                                             float* __restrict__ y, int C, size_t S, size_t total) {
+                                                             float* __restrict__ y, int C, size_t S, size_t total,
+                                                             int fp16) {
     const int CBS = C / 8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const size_t s = i % S;
@@ -322,17 +339,16 @@ __global__ void __launch_bounds__(256) blocked_to_ncs_kernel(const uint4* __rest
         const uint32_t hu[4] = {h.x, h.y, h.z, h.w};
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[2 * k] = __uint_as_float(hu[k] << 16);
-            v[2 * k + 1] = __uint_as_float(hu[k] & 0xFFFF0000u);
-        }
+        for (int k = 0; k < 4; ++k) unpack2(hu[k], fp16, v[2 * k], v[2 * k + 1]);
         if (lo) {
             const uint4 l = __ldg(lo + i);
             const uint32_t lu[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                v[2 * k] += __uint_as_float(lu[k] << 16);
-                v[2 * k + 1] += __uint_as_float(lu[k] & 0xFFFF0000u);
+                float a, c2;
+                unpack2(lu[k], fp16, a, c2);
+                v[2 * k] += a;
+                v[2 * k + 1] += c2;
             }
         }
         float* dst = y + (b * C + (size_t)cb * 8) * S + s;
@@ -347,7 +363,7 @@ __global__ void __launch_bounds__(256) cat_volume_blocked_kernel(const float* __
                                                                  const float* __restrict__ right,
                                                                  uint4* __restrict__ o_hi, uint4* __restrict__ o_lo,
                                                                  int B, int C, int H, int W, int D, DispList dl,
-                                                                 size_t total) {
+                                                                 size_t total, int fp16) {
     const int CBS = 2 * C / 8, CB_L = C / 8;
     const size_t plane = (size_t)H * W;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -369,7 +385,7 @@ __global__ void __launch_bounds__(256) cat_volume_blocked_kernel(const float* __
             for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e * plane);
         }
         uint4 h, l;
-        split8(v, h, l);
+        split8(v, h, l, fp16);
         __stcs(o_hi + i, h);
         if (o_lo) __stcs(o_lo + i, l);
     }
@@ -447,28 +463,29 @@ static unsigned grid_for(size_t total) {
 }
 
 extern "C" int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W,
-                                         void* stream) {
+                                         int fp16, void* stream) {
     DMB_REQUIRE(x && y_hi, "ncdhw_to_blocked: null pointer");
     DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ncdhw_to_blocked: non-positive dimension");
     DMB_REQUIRE(C % 8 == 0, "ncdhw_to_blocked: C=%d must be a multiple of 8", C);
     const size_t S = (size_t)D * H * W, total = (size_t)B * (C / 8) * S;
-    ncs_to_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)y_hi, (uint4*)y_lo, C, S, total);
+    ncs_to_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)y_hi, (uint4*)y_lo, C, S, total, fp16 ? 1 : 0);
     return check_launch("ncs_to_blocked_kernel");
 }
 
 extern "C" int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W,
-                                         void* stream) {
+                                         int fp16, void* stream) {
     DMB_REQUIRE(x_hi && y, "blocked_to_ncdhw: null pointer");
     DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "blocked_to_ncdhw: non-positive dimension");
     DMB_REQUIRE(C % 8 == 0, "blocked_to_ncdhw: C=%d must be a multiple of 8", C);
     const size_t S = (size_t)D * H * W, total = (size_t)B * (C / 8) * S;
     blocked_to_ncs_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)x_hi, (const uint4*)x_lo, y, C, S,
-                                                                         total);
+                                                                         total, fp16 ? 1 : 0);
     return check_launch("blocked_to_ncs_kernel");
 }
 
 extern "C" int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out_hi, void* out_lo, int B,
-                                           int C, int H, int W, const int* disp_idx_host, int D, void* stream) {
+                                           int C, int H, int W, const int* disp_idx_host, int D, int fp16,
+                                           void* stream) {
     DMB_REQUIRE(left && right && out_hi && disp_idx_host, "cat_volume_blocked: null pointer");
     DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "cat_volume_blocked: non-positive dimension");
     DMB_REQUIRE(C % 8 == 0, "cat_volume_blocked: C=%d must be a multiple of 8", C);
@@ -480,6 +497,6 @@ extern "C" int dmb_b200_cat_volume_blocked(const float* left, const float* right
     }
     const size_t total = (size_t)B * (2 * C / 8) * D * H * W;
     cat_volume_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(left, right, (uint4*)out_hi, (uint4*)out_lo,
-                                                                             B, C, H, W, D, dl, total);
+                                                                             B, C, H, W, D, dl, total, fp16 ? 1 : 0);
     return check_launch("cat_volume_blocked_kernel");
 }

@@ -37,8 +37,8 @@ class PSMTrunk(nn.Module):
             ))
         # 'direct': fp32 SIMT kernels; 'tc': tcgen05 trunk (csrc/conv3d_tc.cu); 'auto': tc when available
         self.engine = "auto"
-        # tc engine arithmetic: 'bf16x3' (split-bf16, fp32-equivalent) or 'bf16'
-        self.precision = "bf16x3"
+        # tc engine arithmetic: 'fp16x3' (split fp16, fp32-equivalent), 'bf16x3', 'fp16', 'bf16'
+        self.precision = "fp16x3"
 
     def trunk(self, raw_cost):
         """raw [B,C,D,H,W] -> (cost1, cost2, cost3), each [B,1,D,H,W] (PSMNet.py:58-72)."""

@@ -150,7 +150,7 @@ int dmb_b200_lga(const float* x, const float* guidance, float* out,
 /* cat volume straight into the trunk's blocked layout: out_hi/out_lo [B][2C/8][D][H][W][8] bf16
  * from the float32 NCHW features (out_lo NULL => plain bf16, no split).  C % 8 == 0. */
 int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out_hi, void* out_lo,
-                                int B, int C, int H, int W, const int* disp_idx_host, int D, void* stream);
+                                int B, int C, int H, int W, const int* disp_idx_host, int D, int fp16, void* stream);
 
 /* 3x3x3 stride-1 pad-1 convolution on tcgen05, blocked channels-last activations.
  * x_hi/x_lo: [B][Cin/8][D][H][W][8] bf16 (x_lo NULL => plain bf16, else the (hi,lo) split pair).
@@ -161,20 +161,26 @@ int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out
  * Cout == 1     : y_f32 [B,1,D,H,W] float32 (+ optional res_f32 of the same shape) -- the 32->1
  *                 classifier heads (aggregators/PSMNet.py:41-52).
  * Cin % 32 == 0.  64-channel layers run as several 32->32 passes accumulating in place. */
-int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, const float* bias,
-                       const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
-                       float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu, void* stream);
+int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
+                       const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
+                       float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu, int fp16,
+                       void* stream);
 /* w_packed: [27][Cin][Cout] float32 (the conv3d_direct packing) -> w_blob (bf16), one
- * [27][4][32|64][8] block per (32 out, 32 in) channel pair; split=1 stores hi rows then lo rows. */
-int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split, void* stream);
+ * [27][4][32|64][8] block per (32 out, 32 in) channel pair; split=1 stores hi rows then lo rows.
+ * fp16: 0 = bfloat16 elements, 1 = IEEE half elements (all 16-bit tensors of one conv3d_tc call
+ * share the format).  `scale` (a power of two) pre-multiplies the weights so that the fp16 `lo`
+ * parts stay out of the subnormal range; pass the same value as `w_scale` to conv3d_tc, whose
+ * epilogue multiplies the accumulators by 1/w_scale (exact). */
+int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split, int fp16,
+                                    float scale, void* stream);
 /* bytes of the packed blob */
 int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split);
 /* 1 if this device/driver can run the tcgen05 path */
 int dmb_b200_conv3d_tc_available(void);
 
-/* layout helpers for the trunk boundary: [B,C,D,H,W] float32 <-> [B][C/8][D][H][W][8] bf16 (hi[,lo]) */
-int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, void* stream);
-int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W, void* stream);
+/* layout helpers for the trunk boundary: [B,C,D,H,W] float32 <-> [B][C/8][D][H][W][8] 16-bit (hi[,lo]) */
+int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, int fp16, void* stream);
+int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W, int fp16, void* stream);
 
 #ifdef __cplusplus
 }

@@ -384,14 +384,15 @@ def test_blocked_layout_roundtrip(P):
     tc = _tc_or_skip()
     g = torch.Generator().manual_seed(2)
     x = torch.randn(2, 16, 3, 5, 7, generator=g)
-    blk = tc.Blocked.from_ncdhw(x.to(DEV), True)
-    back = blk.to_ncdhw().cpu()
-    assert float((back - x).abs().max()) < 2e-5 * float(x.abs().max())          # hi+lo carries ~16 bits
-    hi = blk.hi.view(2, 2, 3, 5, 7, 8).float().cpu()
-    want = x.view(2, 2, 8, 3, 5, 7).permute(0, 1, 3, 4, 5, 2)
-    torch.testing.assert_close(hi, want.bfloat16().float())
-    plain = tc.Blocked.from_ncdhw(x.to(DEV), False)
-    torch.testing.assert_close(plain.to_ncdhw().cpu(), x.bfloat16().float())
+    for fp16, bits, dt in ((False, 16, torch.bfloat16), (True, 21, torch.float16)):
+        blk = tc.Blocked.from_ncdhw(x.to(DEV), True, fp16)
+        back = blk.to_ncdhw().cpu()
+        assert float((back - x).abs().max()) < 2.0 ** (1 - bits) * float(x.abs().max())
+        hi = blk.hi.view(2, 2, 3, 5, 7, 8).float().cpu()
+        want = x.view(2, 2, 8, 3, 5, 7).permute(0, 1, 3, 4, 5, 2)
+        torch.testing.assert_close(hi, want.to(dt).float())
+        plain = tc.Blocked.from_ncdhw(x.to(DEV), False, fp16)
+        torch.testing.assert_close(plain.to_ncdhw().cpu(), x.to(dt).float())
 
 
 TC_CASES = [
@@ -406,10 +407,12 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16x3", "fp16", "bf16"])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv3d_tc_vs_torch_cpu(P, case, split):
+def test_conv3d_tc_vs_torch_cpu(P, case, precision):
     tc = _tc_or_skip()
+    split, fp16 = tc.PRECISIONS[precision]
+    dt = torch.float16 if fp16 else torch.bfloat16
     cin, cout, dims, bias, residual, relu = case
     g = torch.Generator().manual_seed(cin + cout + dims[1])
     x = torch.randn(2, cin, *dims, generator=g)
@@ -421,9 +424,9 @@ def test_conv3d_tc_vs_torch_cpu(P, case, split):
     if bias:
         conv.bias.data.copy_(b)
     conv = conv.to(DEV)
-    if not split:   # plain bf16: compare against bf16-rounded operands with fp32 accumulation
-        xr, wr = x.bfloat16().float(), w.bfloat16().float()
-        rr = res.bfloat16().float() if (res is not None and cout > 1) else res
+    if not split:   # single plane: compare against operands rounded to the element type, fp32 accumulation
+        xr, wr = x.to(dt).float(), w.to(dt).float()
+        rr = res.to(dt).float() if (res is not None and cout > 1) else res
     else:
         xr, wr, rr = x, w, res
     ref = F.conv3d(xr, wr, b, padding=1)
@@ -431,19 +434,19 @@ def test_conv3d_tc_vs_torch_cpu(P, case, split):
         ref = ref + rr
     if relu:
         ref = F.relu(ref)
-    xb = tc.Blocked.from_ncdhw(x.to(DEV), split)
+    xb = tc.Blocked.from_ncdhw(x.to(DEV), split, fp16)
+    out_eps = {"fp16x3": 4e-6, "bf16x3": 3e-5, "fp16": 1.5e-3, "bf16": 1.2e-2}[precision]
     if cout == 1:
         got = tc.conv_tc(conv, xb, relu=relu, res_f32=res.to(DEV) if residual else None).cpu()
-        tol = 3e-5 if split else 2e-5
+        out_eps = min(out_eps, 3e-5)                  # fp32 output: no 16-bit output rounding
     else:
-        rb = tc.Blocked.from_ncdhw(res.to(DEV), split) if residual else None
+        rb = tc.Blocked.from_ncdhw(res.to(DEV), split, fp16) if residual else None
         got = tc.conv_tc(conv, xb, rb, relu=relu).to_ncdhw().cpu()
-        tol = 3e-5 if split else 1.2e-2       # plain: the OUTPUT is rounded to bf16 once more
     err = float((got - ref).abs().max())
-    assert err < tol * max(1.0, float(ref.abs().max())), err
+    assert err < out_eps * max(1.0, float(ref.abs().max())), err
 
 
-@pytest.mark.parametrize("precision,tol", [("bf16x3", 1e-3), ("bf16", 0.5)])
+@pytest.mark.parametrize("precision,tol", [("fp16x3", 1e-3), ("bf16x3", 2e-2), ("fp16", 0.5), ("bf16", 2.0)])
 def test_config1_tc_engine_vs_reference_golden(P, golden_dir, precision, tol):
     _tc_or_skip()
     rec = _load(golden_dir, "aggregators.pt")["PSMNet_sharp"]
