@@ -299,7 +299,8 @@ def run_ours(args, rank, world, local_rank):
     pk = peaks()
     macs = trunk_macs(B)
     agg_ms = seg[2]
-    passes = 3 if (args.precision == "bf16x3" and proc.aggregator._use_tc(torch.empty(B, 64, D4, H4, W4, device=device))) else 1
+    on_tc = proc.aggregator._use_tc(torch.empty(B, 64, D4, H4, W4, device=device))
+    passes = 3 if (on_tc and args.precision.endswith("x3")) else 1
     achieved_tflops = 2.0 * macs / (agg_ms * 1e-3) / 1e12
     cat_bytes = B * (2 * 32 * H4 * W4 + 64 * D4 * H4 * W4) * 4
     roofline = {"bound": "tensor", "kernel": "PSMAggregator trunk (25 conv launches + 3 upsample), timed as one span",
@@ -324,8 +325,8 @@ def run_ours(args, rank, world, local_rank):
         "metric": "disparity maps/sec (PSMNet, 960x540, D=192)", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": ("bf16x3 (split-bf16 tensor-core MMAs, fp32 accumulate)" if passes == 3 else
-                  ("bf16" if proc.aggregator._use_tc(torch.empty(B, 64, D4, H4, W4, device=device)) else "f32")),
+        "dtype": (("%s (split 16-bit tensor-core MMAs hi*hi+hi*lo+lo*hi, fp32 accumulate)" % args.precision)
+                  if passes == 3 else (args.precision if on_tc else "f32")),
         "data": "synthetic",
         "config": {"workload": "PSMNet full forward: backbone (torch/cuDNN, out of hot-path scope) + cat volume + "
                                "PSMAggregator + 3x FasterSoftArgmin; 960x540 top-padded to 544x960, D=192",
@@ -352,7 +353,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step")
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "direct"])
-    ap.add_argument("--precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "bf16x3", "fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 

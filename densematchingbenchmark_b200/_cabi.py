@@ -33,8 +33,8 @@ SIGNATURES = {
     "dmb_b200_sga": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dmb_b200_lga": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "dmb_b200_cat_volume_blocked": [_P, _P, _P, _P, _I, _I, _I, _I, _IP, _I, _I, _P],
-    "dmb_b200_conv3d_tc": [_P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P],
-    "dmb_b200_conv3d_tc_pack_weights": [_P, _P, _I, _I, _I, _I, _F, _P],
+    "dmb_b200_conv3d_tc": [_P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dmb_b200_conv3d_tc_pack_weights": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "dmb_b200_ncdhw_to_blocked": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_blocked_to_ncdhw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
 }
@@ -43,7 +43,7 @@ OTHER = {
     "dmb_b200_abi_version": ([], c_int),
     "dmb_b200_last_error": ([], c_char_p),
     "dmb_b200_launch_count": ([], c_int64),
-    "dmb_b200_conv3d_tc_weight_bytes": ([_I, _I, _I], c_int64),
+    "dmb_b200_conv3d_tc_weight_bytes": ([_I, _I, _I, _I], c_int64),
     "dmb_b200_conv3d_tc_available": ([], c_int),
 }
 

@@ -15,8 +15,13 @@
 // offset on the shared-memory descriptor.  Depth planes stream through a 4-deep ring (each plane
 // is read from L2 ~1.4x instead of 27x).
 //
-// One pass = 32 input channels -> 32 output channels (the trunk's 64-channel layers run as
-// several passes that accumulate in place).  Per output plane tile (16x8 voxels = M 128):
+// The hourglass' stride-2 convolutions (utils/hourglass.py:35-38,45-48) gather the four (h,w)
+// parity classes of each input plane with four strided tensor maps; its stride-2 transposed
+// convolutions (:53-60) run as 8 output-parity classes, each a 1..8-tap convolution over the input
+// grid, accumulated in separate TMEM columns.
+//
+// One pass = 32 (stride-2: 16) input channels -> 32 output channels (the trunk's 64-channel layers
+// run as several passes that accumulate in place).  Per output plane tile (16x8 voxels = M 128):
 //   plain : 27 taps x 2 K-steps  MMAs  M128 N32 K16
 //   split : per (tap, K-step)   A_hi x [W_hi | W_lo] (N64)  +  A_lo x W_hi (N32, own columns)
 // accumulating in TMEM (one short chain per depth tap, double buffered), epilogue = sum of the
@@ -32,28 +37,49 @@
 namespace dmb {
 namespace tc {
 
-constexpr int TH = 16, TW = 8;              // output tile (in-plane), M = TH*TW = 128
-constexpr int HH = TH + 2, HW = TW + 2;     // halo tile
-constexpr int CB = 4;                       // 8-channel blocks per pass (32 input channels)
+constexpr int TH = 16, TW = 8;              // M tile (in-plane) = 128 rows of the MMA
 constexpr int NB = 32;                      // output channels per pass
-constexpr int PLANE_BYTES = CB * HH * HW * 16;   // 11520
-constexpr uint32_t LBO_A = HH * HW * 16;    // byte distance between 8-channel blocks (K direction)
-constexpr uint32_t SBO_A = HW * 16;         // byte distance between groups of 8 rows (next h)
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 4;                   // depth-plane ring
 constexpr int TAPS = 27;
 constexpr int NTHREADS = 192;
 constexpr int TMEM_COLS = 512;
 
+// KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane
+// KIND 1: stride-2 conv (k3,p1)  M space = output grid; four (h,w)-parity sub-tiles per input plane
+// KIND 2: stride-2 transposed conv (k3,p1,op1)  M space = INPUT grid; 8 output parity classes,
+//         each a small conv over a 17x9 halo box
+template <int KIND> struct Geo;
+template <> struct Geo<0> {
+    static constexpr int CBK = 4;                                  // 8-channel blocks per pass (32 ch)
+    static constexpr int PLANE_BYTES = CBK * 18 * 10 * 16;         // 11520
+};
+template <> struct Geo<1> {
+    static constexpr int CBK = 2;                                  // 16 input channels per pass (smem budget)
+    // sub-tile (ph,pw): (16+ph) rows x (8+pw) cols, each padded to a multiple of 128 bytes
+    static constexpr int SUB_OFF0 = 0, SUB_OFF1 = 4096, SUB_OFF2 = 4096 + 4608, SUB_OFF3 = 4096 + 4608 + 4352;
+    static constexpr int PLANE_BYTES = 4096 + 4608 + 4352 + 4992;  // 18048
+};
+template <> struct Geo<2> {
+    static constexpr int CBK = 4;
+    static constexpr int PLANE_BYTES = 9856;                       // 4*17*9*16 = 9792, padded to 128
+};
+
+struct Maps {
+    CUtensorMap m[8];   // KIND 0/2: [0]=hi [1]=lo;  KIND 1: [(ph*2+pw)*2 + (0 hi | 1 lo)]
+};
+
 struct Params {
     const void* w_blob;        // this pass' packed weights
     const float* bias;         // [32] or null
-    const uint4* res_hi;       // residual (blocked) or null
+    const uint4* res_hi;       // residual (blocked, output geometry) or null
     const uint4* res_lo;
     uint4* y_hi;
     uint4* y_lo;
     float* y_f32;              // Cout==1 mode (NCDHW fp32), else null
     const float* res_f32;
-    int B, D, H, W;
+    int B;
+    int Dm, Hm, Wm;            // M-space grid the tiles / depth segments run over
+    int Do, Ho, Wo;            // output grid (indexing of y / residual)
     int in_cb0;                // first 8-channel block of the input tensor used by this pass
     int y_cb0, y_cbs;          // first block / total blocks of y
     int res_cb0, res_cbs;      // same for the residual tensor
@@ -142,11 +168,14 @@ __device__ __forceinline__ void unpack8(const uint4& q, float* f) {
     }
 }
 
-template <bool SPLIT>
+template <int KIND, bool SPLIT>
 struct Smem {
+    using G = Geo<KIND>;
+    static constexpr int CBK = G::CBK;
     static constexpr int ROWS = SPLIT ? 2 * NB : NB;               // B-operand rows per channel block
-    static constexpr int TAP_BYTES = CB * ROWS * 16;               // 2048 / 4096
-    static constexpr int W_BYTES = TAPS * TAP_BYTES;               // 55296 / 110592
+    static constexpr int TAP_BYTES = CBK * ROWS * 16;
+    static constexpr int W_BYTES = TAPS * TAP_BYTES;
+    static constexpr int PLANE_BYTES = G::PLANE_BYTES;
     static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;
     static constexpr int PLANES_OFF = W_BYTES;
     static constexpr int BAR_OFF = PLANES_OFF + NSTAGE * STAGE_BYTES;
@@ -155,17 +184,93 @@ struct Smem {
     static constexpr uint32_t SBO_B = 128;
     // The tensor core adds each K=16 partial product into the fp32 accumulator with truncation
     // (measured: error biased toward zero, growing with the chain length).  Accumulation chains are
-    // therefore kept short: one accumulator per depth tap kd (18 MMAs deep) and, in split mode, a
+    // therefore kept short.  KIND 0/1: one accumulator per depth tap kd and, in split mode, a
     // separate one for the small lo*hi term; the epilogue adds them with round-to-nearest.
     static constexpr int KD_COLS = SPLIT ? 64 : 32;                // [hi*Whi | hi*Wlo] of one kd
     static constexpr int LH_COL = 3 * KD_COLS;                     // lo*Whi (split only)
-    static constexpr int ACC_COLS = SPLIT ? 3 * 64 + 32 : 3 * 32;  // 224 / 96 columns per buffer
+    // KIND 2: one accumulator per output parity class (chains are <= 32 MMAs by construction)
+    static constexpr int CLS_COLS = SPLIT ? 64 : 32;
+    static constexpr int ACC_COLS = KIND == 2 ? 4 * CLS_COLS : (SPLIT ? 3 * 64 + 32 : 3 * 32);
+    static_assert(2 * ACC_COLS <= TMEM_COLS, "accumulators exceed TMEM");
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
 
-template <bool SPLIT, bool FP16>
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const Params p) {
-    using S = Smem<SPLIT>;
+struct Item {
+    int b, d0, d1, h0, w0;
+};
+__device__ __forceinline__ Item decode_item(const Params& p, int item) {
+    const int per_b = p.tiles_w * p.tiles_h * p.nseg;
+    Item it;
+    it.b = item / per_b;
+    int r = item - it.b * per_b;
+    const int seg = r / (p.tiles_w * p.tiles_h);
+    r -= seg * p.tiles_w * p.tiles_h;
+    const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
+    it.d0 = seg * p.seg_len;
+    it.d1 = min(p.Dm, it.d0 + p.seg_len);
+    it.h0 = th * TH;
+    it.w0 = tw * TW;
+    return it;
+}
+
+// bias + residual + ReLU + 16-bit (hi[,lo]) split + store of one output voxel's 32 channels
+template <bool FP16>
+__device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], const float (&bias)[NB], int b, int d, int h,
+                                            int w) {
+    const size_t plane_sz = (size_t)p.Ho * p.Wo;
+    const size_t vox = (size_t)d * plane_sz + (size_t)h * p.Wo + w;
+    if (p.y_f32) {
+        float o = v[0] + bias[0];
+        const size_t oi = (size_t)b * p.Do * plane_sz + vox;
+        if (p.res_f32) o += __ldg(p.res_f32 + oi);
+        if (p.relu) o = fmaxf(o, 0.f);
+        p.y_f32[oi] = o;
+        return;
+    }
+#pragma unroll
+    for (int c = 0; c < NB; ++c) v[c] += bias[c];
+    if (p.res_hi) {
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+            const size_t ri = ((size_t)(b * p.res_cbs + p.res_cb0 + cb) * p.Do) * plane_sz + vox;
+            float f[8];
+            unpack8<FP16>(__ldg(p.res_hi + ri), f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
+            if (p.res_lo) {
+                unpack8<FP16>(__ldg(p.res_lo + ri), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
+            }
+        }
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) v[c] = fmaxf(v[c], 0.f);
+    }
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+        const size_t yi = ((size_t)(b * p.y_cbs + p.y_cb0 + cb) * p.Do) * plane_sz + vox;
+        float hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float x = v[cb * 8 + e];
+            const float hv = round16<FP16>(x);
+            hi[e] = hv;
+            lo[e] = x - hv;
+        }
+        p.y_hi[yi] = make_uint4(pack2<FP16>(hi[0], hi[1]), pack2<FP16>(hi[2], hi[3]), pack2<FP16>(hi[4], hi[5]),
+                                pack2<FP16>(hi[6], hi[7]));
+        if (p.y_lo)
+            p.y_lo[yi] = make_uint4(pack2<FP16>(lo[0], lo[1]), pack2<FP16>(lo[2], lo[3]), pack2<FP16>(lo[4], lo[5]),
+                                    pack2<FP16>(lo[6], lo[7]));
+    }
+}
+
+template <int KIND, bool SPLIT, bool FP16>
+__global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+    using S = Smem<KIND, SPLIT>;
+    constexpr int CBK = S::CBK;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* w_smem = smem;
     unsigned char* planes = smem + S::PLANES_OFF;
@@ -202,34 +307,49 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int items_per_b = p.tiles_w * p.tiles_h * p.nseg;
-
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
-            // weights: packed in global exactly as they sit in shared memory
-            mbar_expect_tx(wbar, S::W_BYTES);
+            mbar_expect_tx(wbar, S::W_BYTES);      // weights: packed in global exactly as they sit in smem
             for (int t = 0; t < TAPS; ++t)
                 bulk_g2s(w_smem + t * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
                          S::TAP_BYTES, wbar);
             uint32_t n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const int b = item / items_per_b;
-                int r = item - b * items_per_b;
-                const int seg = r / (p.tiles_w * p.tiles_h);
-                r -= seg * p.tiles_w * p.tiles_h;
-                const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
-                const int d0 = seg * p.seg_len;
-                const int d1 = min(p.D, d0 + p.seg_len);
-                const int h0 = th * TH, w0 = tw * TW;
-                for (int pl = d0 - 1; pl <= d1; ++pl, ++n) {
+                const Item it = decode_item(p, item);
+                const int nout = it.d1 - it.d0;
+                const int nplanes = KIND == 0 ? nout + 2 : (KIND == 1 ? 2 * nout + 1 : nout + 1);
+                const int pl0 = KIND == 0 ? it.d0 - 1 : (KIND == 1 ? 2 * it.d0 - 1 : it.d0);
+                for (int j = 0; j < nplanes; ++j, ++n) {
+                    const int pl = pl0 + j;
                     const uint32_t slot = n % NSTAGE;
-                    const uint32_t ph = (n / NSTAGE) & 1;
-                    mbar_wait(&empty[slot], ph ^ 1);
-                    mbar_expect_tx(&full[slot], S::STAGE_BYTES);
+                    mbar_wait(&empty[slot], ((n / NSTAGE) & 1) ^ 1);
                     unsigned char* dst = planes + slot * S::STAGE_BYTES;
-                    tma_load_5d(dst, &map_hi, &full[slot], 8 * (w0 - 1), h0 - 1, pl, p.in_cb0, b);
-                    if (SPLIT) tma_load_5d(dst + PLANE_BYTES, &map_lo, &full[slot], 8 * (w0 - 1), h0 - 1, pl, p.in_cb0, b);
+                    if (KIND == 0) {
+                        mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 18 * 10 * 16);
+                        tma_load_5d(dst, &maps.m[0], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl, p.in_cb0, it.b);
+                        if (SPLIT)
+                            tma_load_5d(dst + S::PLANE_BYTES, &maps.m[1], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl,
+                                        p.in_cb0, it.b);
+                    } else if (KIND == 2) {
+                        mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 17 * 9 * 16);
+                        tma_load_5d(dst, &maps.m[0], &full[slot], 8 * it.w0, it.h0, pl, p.in_cb0, it.b);
+                        if (SPLIT)
+                            tma_load_5d(dst + S::PLANE_BYTES, &maps.m[1], &full[slot], 8 * it.w0, it.h0, pl, p.in_cb0, it.b);
+                    } else {
+                        // four parity sub-tiles; odd-parity ones start one index earlier (taps k=0)
+                        mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 16 * (16 * 8 + 16 * 9 + 17 * 8 + 17 * 9));
+                        constexpr int offs[4] = {Geo<1>::SUB_OFF0, Geo<1>::SUB_OFF1, Geo<1>::SUB_OFF2, Geo<1>::SUB_OFF3};
+#pragma unroll
+                        for (int sub = 0; sub < 4; ++sub) {
+                            const int ph = sub >> 1, pw = sub & 1;
+                            tma_load_5d(dst + offs[sub], &maps.m[sub * 2], &full[slot], 0, it.w0 - pw, it.h0 - ph, pl,
+                                        p.in_cb0);
+                            if (SPLIT)
+                                tma_load_5d(dst + S::PLANE_BYTES + offs[sub], &maps.m[sub * 2 + 1], &full[slot], 0,
+                                            it.w0 - pw, it.h0 - ph, pl, p.in_cb0);
+                        }
+                    }
                 }
             }
         }
@@ -242,29 +362,69 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
             mbar_wait(wbar, 0);
             const uint32_t w_addr = smem_u32(w_smem);
             const uint32_t planes_addr = smem_u32(planes);
-            uint32_t n_base = 0, t = 0;
+            auto bdesc = [&](int tap, int kk) {
+                return make_desc(w_addr + tap * S::TAP_BYTES + 2 * kk * S::LBO_B, S::LBO_B, S::SBO_B);
+            };
+            uint32_t n_base = 0, t_base = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int r = item % items_per_b;
-                const int seg = r / (p.tiles_w * p.tiles_h);
-                const int d0 = seg * p.seg_len;
-                const int d1 = min(p.D, d0 + p.seg_len);
-                const int nout = d1 - d0;
-                int waited = 0;
-                for (int od = 0; od < nout; ++od, ++t) {
-                    while (waited < od + 3) {
-                        const uint32_t n = n_base + waited;
-                        mbar_wait(&full[n % NSTAGE], (n / NSTAGE) & 1);
-                        ++waited;
-                    }
-                    const uint32_t buf = t & 1;
-                    mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
-                    tcgen05_fence_after();
-                    const uint32_t acc0 = tmem_base + buf * S::ACC_COLS;
-                    uint32_t first_lo = 1;
+                const Item it = decode_item(p, item);
+                const int nout = it.d1 - it.d0;
+                if (KIND == 0) {
+                    constexpr uint32_t LBO_A = 18 * 10 * 16, SBO_A = 10 * 16;
+                    int waited = 0;
+                    for (int od = 0; od < nout; ++od) {
+                        while (waited < od + 3) {
+                            const uint32_t n = n_base + waited;
+                            mbar_wait(&full[n % NSTAGE], (n / NSTAGE) & 1);
+                            ++waited;
+                        }
+                        const uint32_t t = t_base + od;
+                        const uint32_t buf = t & 1;
+                        mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
+                        tcgen05_fence_after();
+                        const uint32_t acc0 = tmem_base + buf * S::ACC_COLS;
+                        uint32_t first_lo = 1;
 #pragma unroll 1
-                    for (int kd = 0; kd < 3; ++kd) {
-                        const uint32_t slot = (n_base + od + kd) % NSTAGE;
-                        const uint32_t a_hi = planes_addr + slot * S::STAGE_BYTES;
+                        for (int kd = 0; kd < 3; ++kd) {
+                            const uint32_t a_hi = planes_addr + ((n_base + od + kd) % NSTAGE) * S::STAGE_BYTES;
+                            const uint32_t acc = acc0 + kd * S::KD_COLS;
+                            uint32_t first = 1;
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                                for (int kw = 0; kw < 3; ++kw) {
+                                    const int tap = (kd * 3 + kh) * 3 + kw;
+                                    const uint32_t a_off = (kh * 10 + kw) * 16;
+#pragma unroll
+                                    for (int kk = 0; kk < CBK / 2; ++kk) {
+                                        const uint64_t db = bdesc(tap, kk);
+                                        tcgen05_mma_bf16(acc, make_desc(a_hi + a_off + 2 * kk * LBO_A, LBO_A, SBO_A), db,
+                                                         idesc_main, first ? 0u : 1u);
+                                        first = 0;
+                                        if (SPLIT) {
+                                            tcgen05_mma_bf16(acc0 + S::LH_COL,
+                                                             make_desc(a_hi + S::PLANE_BYTES + a_off + 2 * kk * LBO_A, LBO_A, SBO_A),
+                                                             db, idesc_lo, first_lo ? 0u : 1u);
+                                            first_lo = 0;
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                        tcgen05_commit(&tfull[buf]);
+                        tcgen05_commit(&empty[(n_base + od) % NSTAGE]);          // plane d-1 is done
+                        if (od == nout - 1) {
+                            tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
+                            tcgen05_commit(&empty[(n_base + od + 2) % NSTAGE]);
+                        }
+                    }
+                    n_base += nout + 2;
+                    t_base += nout;
+                } else if (KIND == 1) {
+                    // plane-driven: input plane 2*od-1+kd feeds chain kd of output od
+                    const int nplanes = 2 * nout + 1;
+                    auto issue_kd = [&](uint32_t a_stage, uint32_t t, int kd) {
+                        const uint32_t acc0 = tmem_base + (t & 1) * S::ACC_COLS;
                         const uint32_t acc = acc0 + kd * S::KD_COLS;
                         uint32_t first = 1;
 #pragma unroll
@@ -272,30 +432,112 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 #pragma unroll
                             for (int kw = 0; kw < 3; ++kw) {
                                 const int tap = (kd * 3 + kh) * 3 + kw;
-                                const uint32_t a_off = (kh * HW + kw) * 16;
+                                const int ph = kh != 1, pw = kw != 1;
+                                const int nh = 16 + ph, nw = 8 + pw;
+                                const int sub_off = ph ? (pw ? Geo<1>::SUB_OFF3 : Geo<1>::SUB_OFF2)
+                                                       : (pw ? Geo<1>::SUB_OFF1 : Geo<1>::SUB_OFF0);
+                                const uint32_t lbo = nh * nw * 16, sbo = nw * 16;
+                                const uint32_t a = a_stage + sub_off + ((kh == 2 ? 1 : 0) * nw + (kw == 2 ? 1 : 0)) * 16;
+                                const uint64_t db = bdesc(tap, 0);
+                                tcgen05_mma_bf16(acc, make_desc(a, lbo, sbo), db, idesc_main, first ? 0u : 1u);
+                                if (SPLIT)
+                                    tcgen05_mma_bf16(acc0 + S::LH_COL, make_desc(a + S::PLANE_BYTES, lbo, sbo), db, idesc_lo,
+                                                     (kd == 0 && first) ? 0u : 1u);
+                                first = 0;
+                            }
+                        }
+                    };
+                    for (int j = 0; j < nplanes; ++j) {
+                        const uint32_t n = n_base + j;
+                        const uint32_t slot = n % NSTAGE;
+                        mbar_wait(&full[slot], (n / NSTAGE) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t a_stage = planes_addr + slot * S::STAGE_BYTES;
+                        if (j & 1) {
+                            issue_kd(a_stage, t_base + ((j - 1) >> 1), 1);
+                        } else {
+                            if (j >= 2) {
+                                const uint32_t t = t_base + (j >> 1) - 1;
+                                issue_kd(a_stage, t, 2);
+                                tcgen05_commit(&tfull[t & 1]);
+                            }
+                            if ((j >> 1) < nout) {
+                                const uint32_t t = t_base + (j >> 1);
+                                mbar_wait(&tempty[t & 1], ((t >> 1) & 1) ^ 1);
+                                tcgen05_fence_after();
+                                issue_kd(a_stage, t, 0);
+                            }
+                        }
+                        tcgen05_commit(&empty[slot]);
+                    }
+                    n_base += nplanes;
+                    t_base += nout;
+                } else {
+                    // transposed: per input depth qd two groups (output depth parity rd), 4 classes each
+                    constexpr uint32_t LBO_A = 17 * 9 * 16, SBO_A = 9 * 16;
+                    auto issue_group = [&](uint32_t a_same, uint32_t a_next, int rd) {
+                        const uint32_t accg = tmem_base + rd * S::ACC_COLS;
 #pragma unroll
-                                for (int kk = 0; kk < CB / 2; ++kk) {
-                                    const uint64_t db = make_desc(w_addr + tap * S::TAP_BYTES + 2 * kk * S::LBO_B, S::LBO_B, S::SBO_B);
-                                    const uint64_t da = make_desc(a_hi + a_off + 2 * kk * LBO_A, LBO_A, SBO_A);
-                                    tcgen05_mma_bf16(acc, da, db, idesc_main, first ? 0u : 1u);
-                                    first = 0;
-                                    if (SPLIT) {
-                                        const uint64_t dl = make_desc(a_hi + PLANE_BYTES + a_off + 2 * kk * LBO_A, LBO_A, SBO_A);
-                                        tcgen05_mma_bf16(acc0 + S::LH_COL, dl, db, idesc_lo, first_lo ? 0u : 1u);
-                                        first_lo = 0;
+                        for (int cls = 0; cls < 4; ++cls) {
+                            const int rh = cls >> 1, rw = cls & 1;
+                            const uint32_t acc = accg + cls * S::CLS_COLS;
+                            uint32_t first = 1;
+#pragma unroll
+                            for (int id = 0; id < 2; ++id) {
+                                if (id > rd) continue;
+                                // rd=0: (kd=1, this plane); rd=1: id0 = (kd=0, next plane), id1 = (kd=2, this plane)
+                                const int kd = rd == 0 ? 1 : (id == 0 ? 0 : 2);
+                                const uint32_t a_pl = (rd == 1 && id == 0) ? a_next : a_same;
+#pragma unroll
+                                for (int ih = 0; ih < 2; ++ih) {
+                                    if (ih > rh) continue;
+                                    const int kh = rh == 0 ? 1 : (ih == 0 ? 0 : 2);
+                                    const int offh = (rh == 1 && ih == 0) ? 1 : 0;
+#pragma unroll
+                                    for (int iw = 0; iw < 2; ++iw) {
+                                        if (iw > rw) continue;
+                                        const int kw = rw == 0 ? 1 : (iw == 0 ? 0 : 2);
+                                        const int offw = (rw == 1 && iw == 0) ? 1 : 0;
+                                        const int tap = (kd * 3 + kh) * 3 + kw;
+                                        const uint32_t a_off = (offh * 9 + offw) * 16;
+#pragma unroll
+                                        for (int kk = 0; kk < CBK / 2; ++kk) {
+                                            const uint64_t db = bdesc(tap, kk);
+                                            tcgen05_mma_bf16(acc, make_desc(a_pl + a_off + 2 * kk * LBO_A, LBO_A, SBO_A), db,
+                                                             idesc_main, first ? 0u : 1u);
+                                            first = 0;
+                                            if (SPLIT)
+                                                tcgen05_mma_bf16(acc, make_desc(a_pl + S::PLANE_BYTES + a_off + 2 * kk * LBO_A, LBO_A, SBO_A),
+                                                                 db, idesc_lo, 1u);
+                                        }
                                     }
                                 }
                             }
                         }
+                    };
+                    int waited = 0;
+                    for (int od = 0; od < nout; ++od) {
+                        while (waited < od + 2) {
+                            const uint32_t n = n_base + waited;
+                            mbar_wait(&full[n % NSTAGE], (n / NSTAGE) & 1);
+                            ++waited;
+                        }
+                        const uint32_t a_same = planes_addr + ((n_base + od) % NSTAGE) * S::STAGE_BYTES;
+                        const uint32_t a_next = planes_addr + ((n_base + od + 1) % NSTAGE) * S::STAGE_BYTES;
+#pragma unroll 1
+                        for (int rd = 0; rd < 2; ++rd) {
+                            const uint32_t t = t_base + 2 * od + rd;          // t_base is even: buffer == rd
+                            mbar_wait(&tempty[rd], ((t >> 1) & 1) ^ 1);
+                            tcgen05_fence_after();
+                            issue_group(a_same, a_next, rd);
+                            tcgen05_commit(&tfull[rd]);
+                        }
+                        tcgen05_commit(&empty[(n_base + od) % NSTAGE]);
+                        if (od == nout - 1) tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
                     }
-                    tcgen05_commit(&tfull[buf]);
-                    tcgen05_commit(&empty[(n_base + od) % NSTAGE]);          // plane d-1 is done
-                    if (od == nout - 1) {
-                        tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
-                        tcgen05_commit(&empty[(n_base + od + 2) % NSTAGE]);
-                    }
+                    n_base += nout + 1;
+                    t_base += 2 * nout;
                 }
-                n_base += nout + 2;
             }
         }
         __syncwarp();
@@ -307,109 +549,88 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
         float bias[NB];
 #pragma unroll
         for (int c = 0; c < NB; ++c) bias[c] = (p.bias && c < p.n_valid_out) ? __ldg(p.bias + c) : 0.f;
-        const size_t plane_sz = (size_t)p.H * p.W;
         uint32_t t = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const int b = item / items_per_b;
-            int r = item - b * items_per_b;
-            const int seg = r / (p.tiles_w * p.tiles_h);
-            r -= seg * p.tiles_w * p.tiles_h;
-            const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
-            const int d0 = seg * p.seg_len;
-            const int d1 = min(p.D, d0 + p.seg_len);
-            const int h = th * TH + hl, w = tw * TW + wl;
-            const bool valid = h < p.H && w < p.W;
-            for (int d = d0; d < d1; ++d, ++t) {
-                const uint32_t buf = t & 1;
-                mbar_wait(&tfull[buf], (t >> 1) & 1);
-                tcgen05_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
-                uint32_t r0[32], r1[32];
-                float v[NB];
-                if (SPLIT) {
-                    // small terms first: hi*Wlo of the three kd chains + lo*Whi, then the hi*Whi chains
-                    float sm[NB];
-                    tmem_ld32(taddr + 32, r0);
-                    tmem_ld32(taddr + 64 + 32, r1);
-                    tmem_ld_wait();
+            const Item it = decode_item(p, item);
+            const int h = it.h0 + hl, w = it.w0 + wl;
+            const bool valid = h < p.Hm && w < p.Wm;
+            for (int d = it.d0; d < it.d1; ++d) {
+                if (KIND != 2) {
+                    const uint32_t buf = t & 1;
+                    mbar_wait(&tfull[buf], (t >> 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
+                    uint32_t r0[32], r1[32];
+                    float v[NB];
+                    if (SPLIT) {
+                        // small terms first: hi*Wlo of the three kd chains + lo*Whi, then the hi*Whi chains
+                        float sm[NB];
+                        tmem_ld32(taddr + 32, r0);
+                        tmem_ld32(taddr + 64 + 32, r1);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) sm[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
-                    tmem_ld32(taddr + 128 + 32, r0);
-                    tmem_ld32(taddr + S::LH_COL, r1);
-                    tmem_ld_wait();
+                        for (int c = 0; c < NB; ++c) sm[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                        tmem_ld32(taddr + 128 + 32, r0);
+                        tmem_ld32(taddr + S::LH_COL, r1);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) sm[c] += __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
-                    tmem_ld32(taddr, r0);
-                    tmem_ld32(taddr + 64, r1);
-                    tmem_ld_wait();
+                        for (int c = 0; c < NB; ++c) sm[c] += __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                        tmem_ld32(taddr, r0);
+                        tmem_ld32(taddr + 64, r1);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
-                    tmem_ld32(taddr + 128, r0);
-                    tmem_ld_wait();
+                        for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                        tmem_ld32(taddr + 128, r0);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) v[c] = ((v[c] + __uint_as_float(r0[c])) + sm[c]) * p.acc_scale;
+                        for (int c = 0; c < NB; ++c) v[c] = ((v[c] + __uint_as_float(r0[c])) + sm[c]) * p.acc_scale;
+                    } else {
+                        tmem_ld32(taddr, r0);
+                        tmem_ld32(taddr + 32, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
+                        tmem_ld32(taddr + 64, r0);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) v[c] = (v[c] + __uint_as_float(r0[c])) * p.acc_scale;
+                    }
+                    // the accumulator buffer is free as soon as it sits in registers
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[buf]);
+                    ++t;
+                    if (valid) store_voxel<FP16>(p, v, bias, it.b, d, h, w);
                 } else {
-                    tmem_ld32(taddr, r0);
-                    tmem_ld32(taddr + 32, r1);
-                    tmem_ld_wait();
+#pragma unroll 1
+                    for (int rd = 0; rd < 2; ++rd, ++t) {
+                        mbar_wait(&tfull[rd], (t >> 1) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + rd * S::ACC_COLS;
+#pragma unroll 1
+                        for (int cls = 0; cls < 4; ++cls) {
+                            uint32_t r0[32];
+                            float v[NB];
+                            tmem_ld32(taddr + cls * S::CLS_COLS, r0);
+                            if (SPLIT) {
+                                uint32_t r1[32];
+                                tmem_ld32(taddr + cls * S::CLS_COLS + 32, r1);
+                                tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) + __uint_as_float(r1[c]);
-                    tmem_ld32(taddr + 64, r0);
-                    tmem_ld_wait();
+                                for (int c = 0; c < NB; ++c) v[c] = (__uint_as_float(r0[c]) + __uint_as_float(r1[c])) * p.acc_scale;
+                            } else {
+                                tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) v[c] = (v[c] + __uint_as_float(r0[c])) * p.acc_scale;
-                }
-                // the accumulator buffer is free as soon as it sits in registers
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
-                if (!valid) continue;
-                const size_t vox = (size_t)d * plane_sz + (size_t)h * p.W + w;
-                if (p.y_f32) {
-                    float o = v[0] + bias[0];
-                    const size_t oi = (size_t)b * p.D * plane_sz + vox;
-                    if (p.res_f32) o += __ldg(p.res_f32 + oi);
-                    if (p.relu) o = fmaxf(o, 0.f);
-                    p.y_f32[oi] = o;
-                    continue;
-                }
-#pragma unroll
-                for (int c = 0; c < NB; ++c) v[c] += bias[c];
-                if (p.res_hi) {
-#pragma unroll
-                    for (int cb = 0; cb < CB; ++cb) {
-                        const size_t ri = ((size_t)(b * p.res_cbs + p.res_cb0 + cb) * p.D) * plane_sz + vox;
-                        float f[8];
-                        unpack8<FP16>(__ldg(p.res_hi + ri), f);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
-                        if (p.res_lo) {
-                            unpack8<FP16>(__ldg(p.res_lo + ri), f);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[cb * 8 + e] += f[e];
+                                for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) * p.acc_scale;
+                            }
+                            if (cls == 3) {
+                                tcgen05_fence_before();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&tempty[rd]);
+                            }
+                            if (valid) store_voxel<FP16>(p, v, bias, it.b, 2 * d + rd, 2 * h + (cls >> 1), 2 * w + (cls & 1));
                         }
                     }
-                }
-                if (p.relu) {
-#pragma unroll
-                    for (int c = 0; c < NB; ++c) v[c] = fmaxf(v[c], 0.f);
-                }
-#pragma unroll
-                for (int cb = 0; cb < CB; ++cb) {
-                    const size_t yi = ((size_t)(b * p.y_cbs + p.y_cb0 + cb) * p.D) * plane_sz + vox;
-                    float hi[8], lo[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float x = v[cb * 8 + e];
-                        const float hv = round16<FP16>(x);
-                        hi[e] = hv;
-                        lo[e] = x - hv;
-                    }
-                    p.y_hi[yi] = make_uint4(pack2<FP16>(hi[0], hi[1]), pack2<FP16>(hi[2], hi[3]), pack2<FP16>(hi[4], hi[5]),
-                                            pack2<FP16>(hi[6], hi[7]));
-                    if (p.y_lo)
-                        p.y_lo[yi] = make_uint4(pack2<FP16>(lo[0], lo[1]), pack2<FP16>(lo[2], lo[3]),
-                                                pack2<FP16>(lo[4], lo[5]), pack2<FP16>(lo[6], lo[7]));
                 }
             }
         }
@@ -424,23 +645,24 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_consta
 }
 
 // ---- weight packing ---------------------------------------------------------------------------
-// w: [27][Cin][Cout] fp32  ->  blobs[(ob*IB + ib)] = [27][CB][ROWS][8] bf16, ROWS = 32 (plain) or 64 (hi rows, lo rows)
-__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cin, int Cout,
+// w: [27][Cin][Cout] fp32 -> blobs[(ob*IB + ib)] = [27][cbk][ROWS][8] 16-bit, ROWS = 32 (plain) or 64 (hi rows, lo
+// rows); one blob covers 8*cbk input channels x 32 output channels
+__global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cin, int Cout, int cbk,
                                     int split, int fp16, float scale) {
     const int rows = split ? 2 * NB : NB;
-    const int IB = Cin / 32, OB = (Cout + 31) / 32;
-    const size_t blob = (size_t)TAPS * CB * rows * 8;
+    const int IB = Cin / (8 * cbk), OB = (Cout + 31) / 32;
+    const size_t blob = (size_t)TAPS * cbk * rows * 8;
     const size_t total = blob * IB * OB;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
         const int e = r % 8; r /= 8;
         const int row = r % rows; r /= rows;
-        const int cb = r % CB; r /= CB;
+        const int cb = r % cbk; r /= cbk;
         const int tap = r % TAPS; r /= TAPS;
         const int ib = r % IB;
         const int ob = r / IB;
         const int co = ob * 32 + (row % NB);
-        const int ci = ib * 32 + cb * 8 + e;
+        const int ci = (ib * cbk + cb) * 8 + e;
         const float v = (co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] * scale : 0.f;
         if (fp16) {
             const __half hi = __float2half_rn(v);
@@ -473,19 +695,37 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W, int fp16) {
+static int encode(CUtensorMap* map, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                  const cuuint32_t* box, int fp16) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return fail(DMB_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled entry point unavailable");
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DMB_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return DMB_OK;
+}
+
+// dense map over [B][CBS][D][H][W][8]: dims (w*8, h, d, cb, b), box (bw*8, bh, 1, cbk, 1)
+static int make_dense_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W, int bh, int bw, int cbk,
+                          int fp16) {
     const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CBS, (cuuint64_t)B};
     const cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
                                    (cuuint64_t)CBS * D * H * W * 16};
-    const cuuint32_t box[5] = {HW * 8, HH, 1, CB, 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(DMB_ERR_CUDA, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
-    return DMB_OK;
+    const cuuint32_t box[5] = {(cuuint32_t)bw * 8, (cuuint32_t)bh, 1, (cuuint32_t)cbk, 1};
+    return encode(map, base, dims, strides, box, fp16);
+}
+
+// parity map (ph,pw) over one batch element: dims (8, W/2, H/2, D, cb), element (c8, w2, h2, d, cb) lives at
+// base + ((cb*D + d)*H + 2*h2+ph)*W*16 + (2*w2+pw)*16
+static int make_parity_map(CUtensorMap* map, const void* base_b, int CBS, int D, int H, int W, int ph, int pw, int cbk,
+                           int fp16) {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(base_b) + ((size_t)ph * W + pw) * 16;
+    const cuuint64_t dims[5] = {8, (cuuint64_t)W / 2, (cuuint64_t)H / 2, (cuuint64_t)D, (cuuint64_t)CBS};
+    const cuuint64_t strides[4] = {32, (cuuint64_t)2 * W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)(8 + pw), (cuuint32_t)(16 + ph), 1, (cuuint32_t)cbk};
+    return encode(map, base, dims, strides, box, fp16);
 }
 
 static int device_ok() {
@@ -501,6 +741,23 @@ static int device_ok() {
     return cached;
 }
 
+template <int KIND, bool SPLIT, bool FP16>
+static int launch_pass(const Maps& maps, const Params& p, int grid, void* stream) {
+    const size_t smem = Smem<KIND, SPLIT>::TOTAL;
+    DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KIND, SPLIT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_tc_kernel<KIND, SPLIT, FP16><<<grid, NTHREADS, smem, as_stream(stream)>>>(maps, p);
+    return check_launch("conv3d_tc_kernel");
+}
+
+template <int KIND>
+static int launch_kind(const Maps& maps, const Params& p, int grid, bool split, int fp16, void* stream) {
+    if (split)
+        return fp16 ? launch_pass<KIND, true, true>(maps, p, grid, stream) : launch_pass<KIND, true, false>(maps, p, grid, stream);
+    return fp16 ? launch_pass<KIND, false, true>(maps, p, grid, stream) : launch_pass<KIND, false, false>(maps, p, grid, stream);
+}
+
+static int cbk_of(int kind) { return kind == 1 ? Geo<1>::CBK : 4; }
+
 }  // namespace tc
 }  // namespace dmb
 
@@ -509,38 +766,33 @@ using namespace dmb::tc;
 
 extern "C" int dmb_b200_conv3d_tc_available(void) { return device_ok(); }
 
-extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split) {
-    if (Cin <= 0 || Cout <= 0 || Cin % 32) return 0;
-    const int64_t blob = (int64_t)TAPS * CB * (split ? 64 : 32) * 16;
-    return blob * (Cin / 32) * ((Cout + 31) / 32);
+extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split, int kind) {
+    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 2) return 0;
+    const int cbk = cbk_of(kind);
+    const int64_t blob = (int64_t)TAPS * cbk * (split ? 64 : 32) * 16;
+    return blob * (Cin / (8 * cbk)) * ((Cout + 31) / 32);
 }
 
 extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split,
-                                               int fp16, float scale, void* stream) {
+                                               int fp16, float scale, int kind, void* stream) {
     DMB_REQUIRE(w_packed && w_blob, "conv3d_tc_pack_weights: null pointer");
+    DMB_REQUIRE(kind >= 0 && kind <= 2, "conv3d_tc_pack_weights: kind must be 0, 1 or 2");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc_pack_weights: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(Cout > 0 && (Cout % 32 == 0 || Cout < 32), "conv3d_tc_pack_weights: Cout=%d must be <32 or a multiple of 32", Cout);
     DMB_REQUIRE(scale > 0.f, "conv3d_tc_pack_weights: scale must be positive");
-    const int64_t n = dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, split) / 2;
+    const int64_t n = dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, split, kind) / 2;
     pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w_packed, (uint16_t*)w_blob, Cin, Cout,
-                                                                                split ? 1 : 0, fp16 ? 1 : 0, scale);
+                                                                                cbk_of(kind), split ? 1 : 0, fp16 ? 1 : 0, scale);
     return check_launch("pack_weights_kernel");
-}
-
-template <bool SPLIT, bool FP16>
-static int launch_pass(const CUtensorMap& map_hi, const CUtensorMap& map_lo, const Params& p, int grid, void* stream) {
-    const size_t smem = Smem<SPLIT>::TOTAL;
-    DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<SPLIT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3d_tc_kernel<SPLIT, FP16><<<grid, NTHREADS, smem, as_stream(stream)>>>(map_hi, map_lo, p);
-    return check_launch("conv3d_tc_kernel");
 }
 
 extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
                                   const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
-                                  int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu,
-                                  int fp16, void* stream) {
+                                  int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind,
+                                  int relu, int fp16, void* stream) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
+    DMB_REQUIRE(kind >= 0 && kind <= 2, "conv3d_tc: kind must be 0 (stride 1), 1 (stride 2) or 2 (transposed stride 2)");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(w_scale > 0.f, "conv3d_tc: w_scale must be positive");
     const bool scalar_out = (Cout == 1);
@@ -550,64 +802,90 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     else
         DMB_REQUIRE(y_hi && !y_f32 && !res_f32, "conv3d_tc: Cout>=32 writes the blocked 16-bit output");
     DMB_REQUIRE(!res_lo || res_hi, "conv3d_tc: res_lo without res_hi");
+    if (kind == 1) DMB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "conv3d_tc: stride-2 needs even input extents");
     if (!device_ok()) return fail(DMB_ERR_UNSUPPORTED, "conv3d_tc: needs an sm_100 device and a TMA-capable driver");
     const bool split = x_lo != nullptr;
     DMB_REQUIRE(scalar_out || split == (y_lo != nullptr), "conv3d_tc: x_lo and y_lo must both be given or both be NULL");
 
-    const int IB = Cin / 32, OB = scalar_out ? 1 : Cout / 32;
-    CUtensorMap map_hi, map_lo;
-    int rc = make_map(&map_hi, x_hi, B, Cin / 8, D, H, W, fp16);
-    if (rc) return rc;
-    rc = make_map(&map_lo, split ? x_lo : x_hi, B, Cin / 8, D, H, W, fp16);
-    if (rc) return rc;
+    const int cbk = cbk_of(kind);
+    const int IB = Cin / (8 * cbk), OB = scalar_out ? 1 : Cout / 32;
+    const int CBS = Cin / 8;
 
     Params p;
-    p.B = B; p.D = D; p.H = H; p.W = W;
+    p.B = (kind == 1) ? 1 : B;
+    p.Dm = kind == 1 ? D / 2 : D; p.Hm = kind == 1 ? H / 2 : H; p.Wm = kind == 1 ? W / 2 : W;
+    p.Do = kind == 0 ? D : (kind == 1 ? D / 2 : 2 * D);
+    p.Ho = kind == 0 ? H : (kind == 1 ? H / 2 : 2 * H);
+    p.Wo = kind == 0 ? W : (kind == 1 ? W / 2 : 2 * W);
     p.n_valid_out = scalar_out ? 1 : 32;
     p.acc_scale = 1.0f / w_scale;
-    p.tiles_h = (int)cdiv(H, TH);
-    p.tiles_w = (int)cdiv(W, TW);
-    // depth segments: enough work items to balance 148 persistent CTAs, segments >= 6 planes
-    const int cols = p.tiles_h * p.tiles_w * B;
+    p.tiles_h = (int)cdiv(p.Hm, TH);
+    p.tiles_w = (int)cdiv(p.Wm, TW);
+    // depth segments: enough work items to balance the persistent CTAs, segments >= 6 planes where possible
+    const int cols = p.tiles_h * p.tiles_w * p.B;
     int nseg = (int)cdiv((int64_t)sm_count() * 8, cols);
-    if (nseg > D / 6) nseg = D / 6;
+    if (nseg > p.Dm / 6) nseg = p.Dm / 6;
     if (nseg < 1) nseg = 1;
-    p.seg_len = (int)cdiv(D, nseg);
-    p.nseg = (int)cdiv(D, p.seg_len);
+    p.seg_len = (int)cdiv(p.Dm, nseg);
+    p.nseg = (int)cdiv(p.Dm, p.seg_len);
     p.n_items = cols * p.nseg;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    const size_t blob = (size_t)TAPS * CB * (split ? 64 : 32) * 16;
+    const size_t blob = (size_t)TAPS * cbk * (split ? 64 : 32) * 16;
+    const size_t in_batch_bytes = (size_t)CBS * D * H * W * 16;
+    const size_t out_cbs = scalar_out ? 0 : Cout / 8;
 
-    for (int ob = 0; ob < OB; ++ob) {
-        for (int ib = 0; ib < IB; ++ib) {
-            const bool first = ib == 0, last = ib == IB - 1;
-            p.w_blob = reinterpret_cast<const unsigned char*>(w_blob) + (size_t)(ob * IB + ib) * blob;
-            p.bias = (first && bias) ? bias + ob * 32 : nullptr;
-            p.in_cb0 = ib * CB;
-            p.relu = (last && relu) ? 1 : 0;
-            p.y_hi = reinterpret_cast<uint4*>(y_hi);
-            p.y_lo = reinterpret_cast<uint4*>(y_lo);
-            p.y_cb0 = ob * CB;
-            p.y_cbs = scalar_out ? 0 : Cout / 8;
-            p.y_f32 = y_f32;
-            p.res_cb0 = ob * CB;
-            p.res_cbs = p.y_cbs;
-            if (first) {                       // the external residual joins on the first pass
-                p.res_hi = reinterpret_cast<const uint4*>(res_hi);
-                p.res_lo = reinterpret_cast<const uint4*>(res_lo);
-                p.res_f32 = res_f32;
-            } else {                           // later passes accumulate onto the output in place
-                p.res_hi = reinterpret_cast<const uint4*>(y_hi);
-                p.res_lo = reinterpret_cast<const uint4*>(y_lo);
-                p.res_f32 = y_f32;
+    const int nb_outer = (kind == 1) ? B : 1;       // the parity maps cover one batch element each
+    for (int bo = 0; bo < nb_outer; ++bo) {
+        Maps maps;
+        int rc;
+        const unsigned char* xh = reinterpret_cast<const unsigned char*>(x_hi) + bo * in_batch_bytes;
+        const unsigned char* xl = split ? reinterpret_cast<const unsigned char*>(x_lo) + bo * in_batch_bytes : xh;
+        if (kind == 1) {
+            for (int sub = 0; sub < 4; ++sub) {
+                rc = make_parity_map(&maps.m[sub * 2], xh, CBS, D, H, W, sub >> 1, sub & 1, cbk, fp16);
+                if (rc) return rc;
+                rc = make_parity_map(&maps.m[sub * 2 + 1], xl, CBS, D, H, W, sub >> 1, sub & 1, cbk, fp16);
+                if (rc) return rc;
             }
-            if (split)
-                rc = fp16 ? launch_pass<true, true>(map_hi, map_lo, p, grid, stream)
-                          : launch_pass<true, false>(map_hi, map_lo, p, grid, stream);
-            else
-                rc = fp16 ? launch_pass<false, true>(map_hi, map_lo, p, grid, stream)
-                          : launch_pass<false, false>(map_hi, map_lo, p, grid, stream);
+        } else {
+            const int bh = kind == 0 ? 18 : 17, bw = kind == 0 ? 10 : 9;
+            rc = make_dense_map(&maps.m[0], xh, B, CBS, D, H, W, bh, bw, cbk, fp16);
             if (rc) return rc;
+            rc = make_dense_map(&maps.m[1], xl, B, CBS, D, H, W, bh, bw, cbk, fp16);
+            if (rc) return rc;
+            for (int i = 2; i < 8; ++i) maps.m[i] = maps.m[0];
+        }
+        // per-batch output base offsets when the kernel sees a single batch element
+        const size_t out_plane = (size_t)p.Do * p.Ho * p.Wo;
+        const size_t yb = (size_t)bo * out_cbs * out_plane;      // in uint4 units (16-byte voxel-block)
+        for (int ob = 0; ob < OB; ++ob) {
+            for (int ib = 0; ib < IB; ++ib) {
+                const bool first = ib == 0, last = ib == IB - 1;
+                p.w_blob = reinterpret_cast<const unsigned char*>(w_blob) + (size_t)(ob * IB + ib) * blob;
+                p.bias = (first && bias) ? bias + ob * 32 : nullptr;
+                p.in_cb0 = ib * cbk;
+                p.relu = (last && relu) ? 1 : 0;
+                p.y_hi = y_hi ? reinterpret_cast<uint4*>(y_hi) + yb : nullptr;
+                p.y_lo = y_lo ? reinterpret_cast<uint4*>(y_lo) + yb : nullptr;
+                p.y_cb0 = ob * 4;
+                p.y_cbs = (int)out_cbs;
+                p.y_f32 = y_f32 ? y_f32 + (size_t)bo * out_plane : nullptr;
+                p.res_cb0 = ob * 4;
+                p.res_cbs = p.y_cbs;
+                if (first) {                       // the external residual joins on the first pass
+                    p.res_hi = res_hi ? reinterpret_cast<const uint4*>(res_hi) + yb : nullptr;
+                    p.res_lo = res_lo ? reinterpret_cast<const uint4*>(res_lo) + yb : nullptr;
+                    p.res_f32 = res_f32 ? res_f32 + (size_t)bo * out_plane : nullptr;
+                } else {                           // later passes accumulate onto the output in place
+                    p.res_hi = p.y_hi;
+                    p.res_lo = p.y_lo;
+                    p.res_f32 = p.y_f32;
+                }
+                if (kind == 0) rc = launch_kind<0>(maps, p, grid, split, fp16, stream);
+                else if (kind == 1) rc = launch_kind<1>(maps, p, grid, split, fp16, stream);
+                else rc = launch_kind<2>(maps, p, grid, split, fp16, stream);
+                if (rc) return rc;
+            }
         }
     }
     return DMB_OK;

@@ -76,9 +76,25 @@ def tc_supported(trunk, raw_cost):
     return D % 4 == 0 and H % 4 == 0 and W % 4 == 0
 
 
+def _kind_of(layer):
+    """0: stride-1 conv, 1: stride-2 conv, 2: stride-2 transposed conv (k3, p1, op1)."""
+    conv = layer.conv if isinstance(layer, FusedConvUnit) else layer
+    if tuple(conv.kernel_size) != (3, 3, 3) or tuple(conv.padding) != (1, 1, 1) or tuple(conv.dilation) != (1, 1, 1):
+        raise NotImplementedError("the tcgen05 path implements 3x3x3, padding 1, dilation 1 only")
+    if isinstance(conv, torch.nn.ConvTranspose3d):
+        if tuple(conv.stride) != (2, 2, 2) or tuple(conv.output_padding) != (1, 1, 1):
+            raise NotImplementedError("transposed conv on tcgen05: stride 2, output_padding 1 only")
+        return 2
+    if tuple(conv.stride) == (1, 1, 1):
+        return 0
+    if tuple(conv.stride) == (2, 2, 2):
+        return 1
+    raise NotImplementedError("stride %s is not supported on tcgen05" % (tuple(conv.stride),))
+
+
 def _blob(layer, split, fp16):
-    """(packed tcgen05 weight blob, folded bias, Cin, Cout, scale) of a FusedConvUnit or a bare
-    nn.Conv3d, cached until the layer's parameters change."""
+    """(packed tcgen05 weight blob, folded bias, Cin, Cout, scale, kind) of a FusedConvUnit or a
+    bare nn.Conv3d, cached until the layer's parameters change."""
     cache = layer.__dict__.setdefault("_dmb_b200_tc_cache", {})
     mode = (split, fp16)
     if isinstance(layer, FusedConvUnit):
@@ -91,12 +107,11 @@ def _blob(layer, split, fp16):
     hit = cache.get(mode)
     if hit is not None and hit[0] == key:
         return hit[1]
+    kind = _kind_of(layer)
     if w is None:
-        w = F_.pack_conv_weight(layer.weight.detach(), False)
+        w = F_.pack_conv_weight(layer.weight.detach(), isinstance(layer, torch.nn.ConvTranspose3d))
         b = layer.bias.detach().float().contiguous() if layer.bias is not None else None
     K3, Cin, Cout = w.shape
-    if K3 != 27:
-        raise NotImplementedError("the tcgen05 path implements 3x3x3 kernels only")
     scale = 1.0
     if fp16:
         # power-of-two pre-scale: largest |w| lands in [4, 8) so that the `lo` halves stay normal
@@ -104,33 +119,40 @@ def _blob(layer, split, fp16):
         if wmax > 0:
             import math
             scale = 2.0 ** max(-14, min(14, math.floor(math.log2(8.0 / wmax))))
-    nbytes = C.load().dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, 1 if split else 0)
+    nbytes = C.load().dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, 1 if split else 0, kind)
     blob = torch.empty(nbytes // 2, dtype=torch.float16 if fp16 else torch.bfloat16, device=w.device)
     C.call("dmb_b200_conv3d_tc_pack_weights", C.ptr(w), C.ptr(blob), Cin, Cout, 1 if split else 0,
-           1 if fp16 else 0, float(scale), C.stream(w.device))
-    val = (blob, b, Cin, Cout, scale, w)      # `w` is kept alive so that id(w) stays unique
+           1 if fp16 else 0, float(scale), kind, C.stream(w.device))
+    val = (blob, b, Cin, Cout, scale, kind, w)      # `w` is kept alive so that id(w) stays unique
     cache[mode] = (key, val)
     return val
 
 
 def conv_tc(layer, x, residual=None, relu=False, res_f32=None):
     """x: Blocked.  Returns Blocked (Cout % 32 == 0) or a float32 [B,1,D,H,W] tensor (Cout == 1)."""
-    blob, bias, Cin, Cout, scale, _ = _blob(layer, x.split, x.fp16)
+    blob, bias, Cin, Cout, scale, kind, _ = _blob(layer, x.split, x.fp16)
     if Cin != x.C:
         raise ValueError("layer expects %d input channels, activation has %d" % (Cin, x.C))
     D, H, W = x.dims
+    if kind == 1 and (D % 2 or H % 2 or W % 2):
+        raise ValueError("stride-2 convolution on tcgen05 needs even extents, got %s" % (x.dims,))
+    odims = x.dims if kind == 0 else (tuple(n // 2 for n in x.dims) if kind == 1 else tuple(2 * n for n in x.dims))
     dev = x.hi.device
     fp16 = 1 if x.fp16 else 0
     if Cout == 1:
-        y = torch.empty(x.B, 1, D, H, W, dtype=torch.float32, device=dev)
+        y = torch.empty(x.B, 1, *odims, dtype=torch.float32, device=dev)
         C.call("dmb_b200_conv3d_tc", C.ptr(x.hi), C.ptr(x.lo), Cin, C.ptr(blob), float(scale), C.ptr(bias),
-               None, None, None, None, 1, C.ptr(y), C.ptr(res_f32), x.B, D, H, W, 1 if relu else 0, fp16, C.stream(dev))
+               None, None, None, None, 1, C.ptr(y), C.ptr(res_f32), x.B, D, H, W, kind, 1 if relu else 0, fp16,
+               C.stream(dev))
         return y
-    y = Blocked.empty(x.B, Cout, x.dims, x.split, x.fp16, dev)
+    if residual is not None and (residual.dims != odims or residual.C != Cout):
+        raise ValueError("residual geometry %s x%d does not match the output %s x%d"
+                         % (residual.dims, residual.C, odims, Cout))
+    y = Blocked.empty(x.B, Cout, odims, x.split, x.fp16, dev)
     C.call("dmb_b200_conv3d_tc", C.ptr(x.hi), C.ptr(x.lo), Cin, C.ptr(blob), float(scale), C.ptr(bias),
            C.ptr(residual.hi) if residual is not None else None,
            C.ptr(residual.lo) if residual is not None else None,
-           C.ptr(y.hi), C.ptr(y.lo), Cout, None, None, x.B, D, H, W, 1 if relu else 0, fp16, C.stream(dev))
+           C.ptr(y.hi), C.ptr(y.lo), Cout, None, None, x.B, D, H, W, kind, 1 if relu else 0, fp16, C.stream(dev))
     return y
 
 
@@ -141,11 +163,15 @@ def _unit(layer, x, residual=None, relu_after=False):
     return conv_tc(layer, x, residual, relu=layer._has_relu or relu_after)
 
 
-def _hourglass_direct(hg, x_blk, presqu, postsqu, out_residual_blk):
-    """Interim: stride-2 / transposed layers of the hourglass run on the fp32 direct kernels."""
-    x = x_blk.to_ncdhw()
-    out, pre, post = hg(x, presqu, postsqu, out_residual=out_residual_blk.to_ncdhw())
-    return Blocked.from_ncdhw(out, x_blk.split, x_blk.fp16), pre, post
+def _hourglass(hg, x, presqu, postsqu, out_residual):
+    """Hourglass.forward (utils/hourglass.py:62-86) entirely on tcgen05, Blocked in / Blocked out."""
+    out = _unit(hg.conv1, x)                                               # stride 2
+    pre = _unit(hg.conv2, out, residual=postsqu, relu_after=True)
+    out = _unit(hg.conv3, pre)                                             # stride 2
+    out = _unit(hg.conv4, out)
+    post = _unit(hg.conv5, out, residual=presqu if presqu is not None else pre, relu_after=True)   # transposed
+    out = _unit(hg.conv6, post, residual=out_residual)                     # transposed
+    return out, pre, post
 
 
 def run_trunk_tc(trunk, raw_cost):
@@ -154,9 +180,9 @@ def run_trunk_tc(trunk, raw_cost):
     x = Blocked.from_ncdhw(raw_cost, split, fp16)
     c0 = _unit(trunk.dres0[1], _unit(trunk.dres0[0], x))
     cost0 = _unit(trunk.dres1[1], _unit(trunk.dres1[0], c0), residual=c0)
-    out1, pre1, post1 = _hourglass_direct(trunk.dres2, cost0, None, None, cost0)
-    out2, pre2, post2 = _hourglass_direct(trunk.dres3, out1, pre1, post1, cost0)
-    out3, pre3, post3 = _hourglass_direct(trunk.dres4, out2, pre2, post2, cost0)
+    out1, pre1, post1 = _hourglass(trunk.dres2, cost0, None, None, cost0)
+    out2, pre2, post2 = _hourglass(trunk.dres3, out1, pre1, post1, cost0)
+    out3, pre3, post3 = _hourglass(trunk.dres4, out2, pre2, post2, cost0)
     cost1 = conv_tc(trunk.classif1[1], _unit(trunk.classif1[0], out1))
     cost2 = conv_tc(trunk.classif2[1], _unit(trunk.classif2[0], out2), res_f32=cost1)
     cost3 = conv_tc(trunk.classif3[1], _unit(trunk.classif3[0], out3), res_f32=cost2)

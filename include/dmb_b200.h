@@ -152,29 +152,33 @@ int dmb_b200_lga(const float* x, const float* guidance, float* out,
 int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out_hi, void* out_lo,
                                 int B, int C, int H, int W, const int* disp_idx_host, int D, int fp16, void* stream);
 
-/* 3x3x3 stride-1 pad-1 convolution on tcgen05, blocked channels-last activations.
- * x_hi/x_lo: [B][Cin/8][D][H][W][8] bf16 (x_lo NULL => plain bf16, else the (hi,lo) split pair).
- * w_blob: packed by dmb_b200_conv3d_tc_pack_weights with the same `split`.
- * bias [Cout] f32 or NULL (BatchNorm folded by the caller, as for conv3d_direct).
- * Cout % 32 == 0: y_hi/y_lo [B][Cout/8][D][H][W][8] bf16 (+ optional residual res_hi/res_lo of the
+/* 3x3x3 convolutions of the trunk on tcgen05, blocked channels-last 16-bit activations.
+ *   kind 0: stride 1, pad 1                      (conv3d_bn[_relu], basic_layers.py:68-177)
+ *   kind 1: stride 2, pad 1 (even input extents)  (Hourglass conv1/conv3, utils/hourglass.py:35-48)
+ *   kind 2: transposed, stride 2, pad 1, output_padding 1 (Hourglass conv5/conv6, :53-60)
+ * x_hi/x_lo: [B][Cin/8][D][H][W][8] (x_lo NULL => single plane, else the (hi,lo) split pair);
+ * B,D,H,W are the INPUT extents; the output grid is the same / halved / doubled.
+ * w_blob: packed by dmb_b200_conv3d_tc_pack_weights with the same split / fp16 / kind; w_scale its
+ * `scale`.  bias [Cout] f32 or NULL (BatchNorm folded by the caller, as for conv3d_direct).
+ * Cout % 32 == 0: y_hi/y_lo [B][Cout/8][Do][Ho][Wo][8] (+ optional residual res_hi/res_lo of the
  *                 same geometry, added before the ReLU);
- * Cout == 1     : y_f32 [B,1,D,H,W] float32 (+ optional res_f32 of the same shape) -- the 32->1
+ * Cout == 1     : y_f32 [B,1,Do,Ho,Wo] float32 (+ optional res_f32 of the same shape) -- the 32->1
  *                 classifier heads (aggregators/PSMNet.py:41-52).
- * Cin % 32 == 0.  64-channel layers run as several 32->32 passes accumulating in place. */
+ * Cin % 32 == 0.  Wider layers run as several passes accumulating in place.
+ * fp16: 0 = bfloat16 elements, 1 = IEEE half elements (all 16-bit tensors of a call share it). */
 int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
                        const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
-                       float* y_f32, const float* res_f32, int B, int D, int H, int W, int relu, int fp16,
+                       float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind, int relu, int fp16,
                        void* stream);
-/* w_packed: [27][Cin][Cout] float32 (the conv3d_direct packing) -> w_blob (bf16), one
- * [27][4][32|64][8] block per (32 out, 32 in) channel pair; split=1 stores hi rows then lo rows.
- * fp16: 0 = bfloat16 elements, 1 = IEEE half elements (all 16-bit tensors of one conv3d_tc call
- * share the format).  `scale` (a power of two) pre-multiplies the weights so that the fp16 `lo`
- * parts stay out of the subnormal range; pass the same value as `w_scale` to conv3d_tc, whose
- * epilogue multiplies the accumulators by 1/w_scale (exact). */
+/* w_packed: [27][Cin][Cout] float32 (the conv3d_direct packing; for kind 2 the ConvTranspose3d
+ * weight packed the same way, un-flipped) -> w_blob (16-bit), one [27][cbk][32|64][8] block per
+ * (32 out, 8*cbk in) channel pair; split=1 stores hi rows then lo rows.  `scale` (a power of two)
+ * pre-multiplies the weights so that the fp16 `lo` parts stay out of the subnormal range; the
+ * kernel's epilogue multiplies the accumulators by 1/w_scale (exact). */
 int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split, int fp16,
-                                    float scale, void* stream);
+                                    float scale, int kind, void* stream);
 /* bytes of the packed blob */
-int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split);
+int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split, int kind);
 /* 1 if this device/driver can run the tcgen05 path */
 int dmb_b200_conv3d_tc_available(void);
 

@@ -446,6 +446,56 @@ def test_conv3d_tc_vs_torch_cpu(P, case, precision):
     assert err < out_eps * max(1.0, float(ref.abs().max())), err
 
 
+TC_STRIDED_CASES = [
+    # kind ('s2' | 'tr'), Cin, Cout, input dims, bias, residual, relu
+    ("s2", 32, 64, (4, 32, 16), False, False, True),          # one tile per output plane
+    ("s2", 32, 32, (6, 38, 22), True, False, False),          # ragged tiles
+    ("s2", 64, 64, (8, 36, 36), True, False, True),           # several input / output passes
+    ("tr", 32, 32, (3, 16, 8), False, False, False),          # one tile
+    ("tr", 64, 32, (4, 19, 11), True, True, False),           # ragged, residual at output resolution
+    ("tr", 64, 64, (5, 17, 18), False, True, True),
+]
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16"])
+@pytest.mark.parametrize("case", TC_STRIDED_CASES)
+def test_conv3d_tc_strided_vs_torch_cpu(P, case, precision):
+    tc = _tc_or_skip()
+    split, fp16 = tc.PRECISIONS[precision]
+    dt = torch.float16 if fp16 else torch.bfloat16
+    kind, cin, cout, dims, bias, residual, relu = case
+    g = torch.Generator().manual_seed(cin + cout + dims[1])
+    x = torch.randn(2, cin, *dims, generator=g)
+    if kind == "s2":
+        conv = torch.nn.Conv3d(cin, cout, 3, 2, 1, bias=bias)
+    else:
+        conv = torch.nn.ConvTranspose3d(cin, cout, 3, 2, 1, output_padding=1, bias=bias)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * (2.0 / (cin * 27)) ** 0.5)
+        if bias:
+            conv.bias.copy_(torch.randn(cout, generator=g) * 0.1)
+    w, b = conv.weight.detach().clone(), (conv.bias.detach().clone() if bias else None)
+    xr, wr = (x, w) if split else (x.to(dt).float(), w.to(dt).float())
+    if kind == "s2":
+        ref = F.conv3d(xr, wr, b, stride=2, padding=1)
+    else:
+        ref = F.conv_transpose3d(xr, wr, b, stride=2, padding=1, output_padding=1)
+    res = torch.randn(ref.shape, generator=g) if residual else None
+    if res is not None:
+        ref = ref + (res if split else res.to(dt).float())
+    if relu:
+        ref = F.relu(ref)
+    conv = conv.to(DEV)
+    xb = tc.Blocked.from_ncdhw(x.to(DEV), split, fp16)
+    rb = tc.Blocked.from_ncdhw(res.to(DEV), split, fp16) if residual else None
+    got = tc.conv_tc(conv, xb, rb, relu=relu)
+    assert got.dims == tuple(ref.shape[2:])
+    got = got.to_ncdhw().cpu()
+    eps = {"fp16x3": 4e-6, "bf16": 1.2e-2}[precision]
+    err = float((got - ref).abs().max())
+    assert err < eps * max(1.0, float(ref.abs().max())), err
+
+
 @pytest.mark.parametrize("precision,tol", [("fp16x3", 1e-3), ("bf16x3", 2e-2), ("fp16", 0.5), ("bf16", 2.0)])
 def test_config1_tc_engine_vs_reference_golden(P, golden_dir, precision, tol):
     _tc_or_skip()
