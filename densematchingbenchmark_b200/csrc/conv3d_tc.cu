@@ -100,15 +100,19 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// The MMA warp runs its loops with all 32 lanes (warp-uniform control flow and operands, so the
+// descriptor arithmetic lives in the uniform datapath); one elected lane issues the instruction.
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+        : "memory");
 }
 __device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                                  uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -132,6 +136,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo, 
     return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
            (1ull << 46);
 }
+// low word for (address, LBO); adding (byte_offset >> 4) moves the start address (no carry: < 2^14)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo) {
+    return ((smem_addr & 0x3FFFF) >> 4) | ((lbo >> 4) << 16);
+}
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, M=128
 // fmt: 0 = F16, 1 = BF16 (UMMA::F16F32Format)
 __host__ __device__ constexpr uint32_t make_idesc(int n, uint32_t fmt) {
@@ -356,14 +366,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        {
             constexpr uint32_t idesc_main = make_idesc(S::ROWS, FP16 ? 0u : 1u);
             constexpr uint32_t idesc_lo = make_idesc(NB, FP16 ? 0u : 1u);
             mbar_wait(wbar, 0);
             const uint32_t w_addr = smem_u32(w_smem);
             const uint32_t planes_addr = smem_u32(planes);
+            const uint32_t b_lo0 = desc_lo(w_addr, S::LBO_B);
+            constexpr uint32_t b_hi = desc_hi(S::SBO_B);
             auto bdesc = [&](int tap, int kk) {
-                return make_desc(w_addr + tap * S::TAP_BYTES + 2 * kk * S::LBO_B, S::LBO_B, S::SBO_B);
+                return desc_of(b_lo0 + ((tap * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
             };
             uint32_t n_base = 0, t_base = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -388,28 +400,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
                         for (int kd = 0; kd < 3; ++kd) {
                             const uint32_t a_hi = planes_addr + ((n_base + od + kd) % NSTAGE) * S::STAGE_BYTES;
                             const uint32_t acc = acc0 + kd * S::KD_COLS;
-                            uint32_t first = 1;
+                            const uint32_t a_lo0 = desc_lo(a_hi, LBO_A);
+                            const uint32_t b_lo_kd = b_lo0 + ((kd * 9 * S::TAP_BYTES) >> 4);
+                            constexpr uint32_t a_hiw = desc_hi(SBO_A);
 #pragma unroll
                             for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
                                 for (int kw = 0; kw < 3; ++kw) {
-                                    const int tap = (kd * 3 + kh) * 3 + kw;
                                     const uint32_t a_off = (kh * 10 + kw) * 16;
 #pragma unroll
                                     for (int kk = 0; kk < CBK / 2; ++kk) {
-                                        const uint64_t db = bdesc(tap, kk);
-                                        tcgen05_mma_bf16(acc, make_desc(a_hi + a_off + 2 * kk * LBO_A, LBO_A, SBO_A), db,
+                                        const bool first = (kh == 0 && kw == 0 && kk == 0);
+                                        const uint64_t db = desc_of(b_lo_kd + (((kh * 3 + kw) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
+                                        tcgen05_mma_bf16(acc, desc_of(a_lo0 + ((a_off + 2 * kk * LBO_A) >> 4), a_hiw), db,
                                                          idesc_main, first ? 0u : 1u);
-                                        first = 0;
                                         if (SPLIT) {
                                             tcgen05_mma_bf16(acc0 + S::LH_COL,
-                                                             make_desc(a_hi + S::PLANE_BYTES + a_off + 2 * kk * LBO_A, LBO_A, SBO_A),
-                                                             db, idesc_lo, first_lo ? 0u : 1u);
-                                            first_lo = 0;
+                                                             desc_of(a_lo0 + ((S::PLANE_BYTES + a_off + 2 * kk * LBO_A) >> 4), a_hiw),
+                                                             db, idesc_lo, (first && first_lo) ? 0u : 1u);
                                         }
                                     }
                                 }
                             }
+                            first_lo = 0;
                         }
                         tcgen05_commit(&tfull[buf]);
                         tcgen05_commit(&empty[(n_base + od) % NSTAGE]);          // plane d-1 is done
@@ -426,24 +439,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
                     auto issue_kd = [&](uint32_t a_stage, uint32_t t, int kd) {
                         const uint32_t acc0 = tmem_base + (t & 1) * S::ACC_COLS;
                         const uint32_t acc = acc0 + kd * S::KD_COLS;
-                        uint32_t first = 1;
+                        const uint32_t a_base = (a_stage & 0x3FFFF) >> 4;
+                        const uint32_t b_lo_kd = b_lo0 + ((kd * 9 * S::TAP_BYTES) >> 4);
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
                             for (int kw = 0; kw < 3; ++kw) {
-                                const int tap = (kd * 3 + kh) * 3 + kw;
+                                const bool first = (kh == 0 && kw == 0);
                                 const int ph = kh != 1, pw = kw != 1;
                                 const int nh = 16 + ph, nw = 8 + pw;
                                 const int sub_off = ph ? (pw ? Geo<1>::SUB_OFF3 : Geo<1>::SUB_OFF2)
                                                        : (pw ? Geo<1>::SUB_OFF1 : Geo<1>::SUB_OFF0);
                                 const uint32_t lbo = nh * nw * 16, sbo = nw * 16;
-                                const uint32_t a = a_stage + sub_off + ((kh == 2 ? 1 : 0) * nw + (kw == 2 ? 1 : 0)) * 16;
-                                const uint64_t db = bdesc(tap, 0);
-                                tcgen05_mma_bf16(acc, make_desc(a, lbo, sbo), db, idesc_main, first ? 0u : 1u);
+                                const uint32_t off = sub_off + ((kh == 2 ? 1 : 0) * nw + (kw == 2 ? 1 : 0)) * 16;
+                                const uint32_t lo = (a_base + (off >> 4)) | ((lbo >> 4) << 16);
+                                const uint64_t db = desc_of(b_lo_kd + (((kh * 3 + kw) * S::TAP_BYTES) >> 4), b_hi);
+                                tcgen05_mma_bf16(acc, desc_of(lo, desc_hi(sbo)), db, idesc_main, first ? 0u : 1u);
                                 if (SPLIT)
-                                    tcgen05_mma_bf16(acc0 + S::LH_COL, make_desc(a + S::PLANE_BYTES, lbo, sbo), db, idesc_lo,
-                                                     (kd == 0 && first) ? 0u : 1u);
-                                first = 0;
+                                    tcgen05_mma_bf16(acc0 + S::LH_COL, desc_of(lo + (S::PLANE_BYTES >> 4), desc_hi(sbo)), db,
+                                                     idesc_lo, (kd == 0 && first) ? 0u : 1u);
                             }
                         }
                     };
@@ -481,13 +495,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
                         for (int cls = 0; cls < 4; ++cls) {
                             const int rh = cls >> 1, rw = cls & 1;
                             const uint32_t acc = accg + cls * S::CLS_COLS;
-                            uint32_t first = 1;
+                            bool first = true;
 #pragma unroll
                             for (int id = 0; id < 2; ++id) {
                                 if (id > rd) continue;
                                 // rd=0: (kd=1, this plane); rd=1: id0 = (kd=0, next plane), id1 = (kd=2, this plane)
                                 const int kd = rd == 0 ? 1 : (id == 0 ? 0 : 2);
                                 const uint32_t a_pl = (rd == 1 && id == 0) ? a_next : a_same;
+                                const uint32_t a_lo0 = desc_lo(a_pl, LBO_A);
 #pragma unroll
                                 for (int ih = 0; ih < 2; ++ih) {
                                     if (ih > rh) continue;
@@ -503,11 +518,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
 #pragma unroll
                                         for (int kk = 0; kk < CBK / 2; ++kk) {
                                             const uint64_t db = bdesc(tap, kk);
-                                            tcgen05_mma_bf16(acc, make_desc(a_pl + a_off + 2 * kk * LBO_A, LBO_A, SBO_A), db,
+                                            tcgen05_mma_bf16(acc, desc_of(a_lo0 + ((a_off + 2 * kk * LBO_A) >> 4), desc_hi(SBO_A)), db,
                                                              idesc_main, first ? 0u : 1u);
-                                            first = 0;
+                                            first = false;
                                             if (SPLIT)
-                                                tcgen05_mma_bf16(acc, make_desc(a_pl + S::PLANE_BYTES + a_off + 2 * kk * LBO_A, LBO_A, SBO_A),
+                                                tcgen05_mma_bf16(acc, desc_of(a_lo0 + ((S::PLANE_BYTES + a_off + 2 * kk * LBO_A) >> 4), desc_hi(SBO_A)),
                                                                  db, idesc_lo, 1u);
                                         }
                                     }
@@ -821,10 +836,11 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     p.acc_scale = 1.0f / w_scale;
     p.tiles_h = (int)cdiv(p.Hm, TH);
     p.tiles_w = (int)cdiv(p.Wm, TW);
-    // depth segments: enough work items to balance the persistent CTAs, segments >= 6 planes where possible
+    // depth segments: ~4 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
+    // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
     const int cols = p.tiles_h * p.tiles_w * p.B;
-    int nseg = (int)cdiv((int64_t)sm_count() * 8, cols);
-    if (nseg > p.Dm / 6) nseg = p.Dm / 6;
+    int nseg = (int)cdiv((int64_t)sm_count() * 4, cols);
+    if (nseg > p.Dm / 2) nseg = p.Dm / 2;
     if (nseg < 1) nseg = 1;
     p.seg_len = (int)cdiv(p.Dm, nseg);
     p.nseg = (int)cdiv(p.Dm, p.seg_len);

@@ -17,7 +17,7 @@ class AcfAggregator(PSMTrunk):
         self.defer_upsample = True
 
     def forward(self, raw_cost):
-        B, C, D, H, W = raw_cost.shape
+        D, H, W = raw_cost.dims if hasattr(raw_cost, "dims") else raw_cost.shape[2:]
         cost1, cost2, cost3 = self.trunk(raw_cost)
         size = (self.max_disp, H * 4, W * 4)
         if size[0] != 4 * D:

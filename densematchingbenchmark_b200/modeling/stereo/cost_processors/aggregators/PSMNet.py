@@ -55,6 +55,19 @@ class PSMTrunk(nn.Module):
         cost3 = fused_plain_conv3d(self.classif3[1], self.classif3[0](out3), residual=cost2)
         return cost1, cost2, cost3
 
+    def blocked_cat_volume(self, ref_fms, tgt_fms, max_disp=192, start_disp=0, dilation=1):
+        """Fast path used by CatCostProcessor: when the trunk will run on tcgen05, build the
+        concatenation volume directly in the trunk's blocked 16-bit layout.  Returns None when
+        the trunk is not going to use the tensor-core engine for this shape."""
+        if self.engine == "direct" or self.training or not ref_fms.is_cuda:
+            return None
+        from . import tc_engine
+        D = (max_disp + dilation - 1) // dilation
+        dhw = (D, ref_fms.shape[2], ref_fms.shape[3])
+        if ref_fms.shape[1] % 8 or not tc_engine.tc_shape_ok(self, 2 * ref_fms.shape[1], dhw):
+            return None
+        return tc_engine.cat_volume_blocked(ref_fms, tgt_fms, max_disp, start_disp, dilation, self.precision)
+
     def _use_tc(self, raw_cost):
         if self.engine == "direct":
             return False
@@ -74,7 +87,7 @@ class PSMAggregator(PSMTrunk):
         self.defer_upsample = True
 
     def forward(self, raw_cost):
-        B, C, D, H, W = raw_cost.shape
+        D, H, W = raw_cost.dims if hasattr(raw_cost, "dims") else raw_cost.shape[2:]
         cost1, cost2, cost3 = self.trunk(raw_cost)
         size = (self.max_disp, H * 4, W * 4)
         if self.defer_upsample and not self.training:

@@ -68,12 +68,17 @@ def tc_available():
 
 
 def tc_supported(trunk, raw_cost):
+    if isinstance(raw_cost, Blocked):
+        return True
     if not raw_cost.is_cuda or raw_cost.dim() != 5:
         return False
-    if trunk.in_planes % 32 != 0 or not tc_available():
+    return tc_shape_ok(trunk, raw_cost.shape[1], tuple(raw_cost.shape[2:]))
+
+
+def tc_shape_ok(trunk, channels, dhw):
+    if trunk.in_planes % 32 != 0 or channels != trunk.in_planes or not tc_available():
         return False
-    B, Cc, D, H, W = raw_cost.shape
-    return D % 4 == 0 and H % 4 == 0 and W % 4 == 0
+    return all(n % 4 == 0 for n in dhw)
 
 
 def _kind_of(layer):
@@ -174,10 +179,24 @@ def _hourglass(hg, x, presqu, postsqu, out_residual):
     return out, pre, post
 
 
+def cat_volume_blocked(reference_fm, target_fm, max_disp, start_disp, dilation, precision):
+    """cat_fms (cat_fms.py:7-48) written straight into the trunk's blocked 16-bit layout: the fp32
+    NCDHW volume (401 MB at 544x960) and its conversion pass are never materialised."""
+    split, fp16 = PRECISIONS[precision]
+    l, r = C.f32(reference_fm), C.f32(target_fm)
+    B, Cc, H, W = l.shape
+    idx = F_.disp_indices(max_disp, start_disp, dilation)
+    out = Blocked.empty(B, 2 * Cc, (len(idx), H, W), split, fp16, l.device)
+    C.call("dmb_b200_cat_volume_blocked", C.ptr(l), C.ptr(r), C.ptr(out.hi), C.ptr(out.lo), B, Cc, H, W,
+           C.int_array(idx), len(idx), 1 if fp16 else 0, C.stream(l.device))
+    return out
+
+
 def run_trunk_tc(trunk, raw_cost):
-    """PSMTrunk.trunk() on tcgen05: returns (cost1, cost2, cost3) float32 [B,1,D,H,W]."""
+    """PSMTrunk.trunk() on tcgen05: returns (cost1, cost2, cost3) float32 [B,1,D,H,W].
+    `raw_cost` is the NCDHW float32 volume or an already Blocked one."""
     split, fp16 = PRECISIONS[trunk.precision]
-    x = Blocked.from_ncdhw(raw_cost, split, fp16)
+    x = raw_cost if isinstance(raw_cost, Blocked) else Blocked.from_ncdhw(raw_cost, split, fp16)
     c0 = _unit(trunk.dres0[1], _unit(trunk.dres0[0], x))
     cost0 = _unit(trunk.dres1[1], _unit(trunk.dres1[0], c0), residual=c0)
     out1, pre1, post1 = _hourglass(trunk.dres2, cost0, None, None, cost0)

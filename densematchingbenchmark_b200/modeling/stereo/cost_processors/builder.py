@@ -38,6 +38,15 @@ class CatCostProcessor(_VolumeThenAggregate):
     def cat_func(self):
         return self.func
 
+    def forward(self, ref_fms, tgt_fms, disp_sample=None):
+        # fused route: default cat volume feeding a tensor-core trunk is written once, in the trunk's own
+        # layout (the reference materialises 401 MB of fp32 and the aggregator re-reads it)
+        if self.func is CAT_FUNCS['default'] and hasattr(self.aggregator, "blocked_cat_volume"):
+            blk = self.aggregator.blocked_cat_volume(ref_fms, tgt_fms, **self.default_args)
+            if blk is not None:
+                return self.aggregator(blk)
+        return super(CatCostProcessor, self).forward(ref_fms, tgt_fms, disp_sample)
+
 
 class DifCostProcessor(_VolumeThenAggregate):
     table = DIF_FUNCS

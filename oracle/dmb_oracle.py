@@ -383,7 +383,8 @@ def spn_scan_backward(X, G1, G2, G3, Hout, grad_out, horizontal, reverse):
     Gs = [g.clone().requires_grad_(True) for g in (G1, G2, G3)]
     out = _spn_autograd(Xr, Gs[0], Gs[1], Gs[2], horizontal, reverse)
     out.backward(grad_out)
-    return Xr.grad, Gs[0].grad, Gs[1].grad, Gs[2].grad
+    # a scan of length 1 never touches the gates: autograd leaves their .grad unset (= zero)
+    return tuple(t.grad if t.grad is not None else torch.zeros_like(t) for t in [Xr] + Gs)
 
 
 def _spn_autograd(X, G1, G2, G3, horizontal, reverse):
@@ -490,10 +491,16 @@ def epe(est, gt, lb=0, ub=192):
 # --------------------------------------------------------------------------------------
 # whole hot path (used by bench.py's cpu_baseline / --impl reference)
 # --------------------------------------------------------------------------------------
-def psm_hot_path(sd, left_fm, right_fm, max_disp=192, prefix="cost_processor.aggregator."):
+def psm_hot_path(sd, left_fm, right_fm, max_disp=192, prefix="cost_processor.aggregator.", dtype=torch.float32):
     """CatCostProcessor.forward + FasterSoftArgmin per cost (cost_processors/builder.py:33-40,
-    models/general_stereo_model.py:51-54) for the PSMNet scene_flow config."""
+    models/general_stereo_model.py:51-54) for the PSMNet scene_flow config.  `dtype=torch.float64`
+    evaluates the same arithmetic in double precision: the "truth" that two float32 implementations
+    (the reference's and ours) are both compared with at sizes where float32 rounding noise in the
+    disparity exceeds the 1e-3 px tolerance."""
     raw = cat_volume(left_fm, right_fm, max_disp // 4, 0, 1)
+    if dtype != torch.float32:
+        raw = raw.to(dtype)
+        sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     costs = psm_aggregator(sd, raw, max_disp, prefix)
     disps = [soft_argmin(c, max_disp) for c in costs]
     return costs, disps

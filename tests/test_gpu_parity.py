@@ -297,23 +297,41 @@ def test_training_mode_fails_loudly(P):
         proc(l.to(DEV), r.to(DEV))
 
 
-def test_medium_size_psm_hot_path_vs_oracle(P):
-    """A quarter of BASELINE config 2 (272x480 image, D=192): CUDA path vs the CPU oracle on the
-    same seeded weights (sharpened) and a structured stereo pair."""
+@pytest.mark.parametrize("engine,precision", [("direct", "fp16x3"), ("auto", "fp16x3"), ("auto", "bf16x3")])
+@pytest.mark.parametrize("sharpen", [1.0, 4.0])
+def test_medium_size_psm_hot_path_vs_oracle(P, engine, precision, sharpen):
+    """A quarter of BASELINE config 2 (272x480 image, D=192, cost volume 48x68x120).
+
+    At D=192 the float32 rounding noise of the REFERENCE ITSELF exceeds 1e-3 px at the worst pixels
+    (measured in the build container, reference vs float64 arithmetic: max 1.35e-3 at sharpen=1,
+    5.5e-3 at sharpen=4; reference vs the float32 oracle: 2.9e-4 / 1.5e-3).  The per-pixel check is
+    therefore made against the float64 evaluation of the same arithmetic: our error must not exceed
+    the float32 CPU oracle's own error by more than a small factor, and EPE / mean deviations must
+    stay far below 1e-3."""
     cfg = _cfg(P, "PSMNet", feat_disp=48, max_disp=192)
     proc = P.build_cost_processor(cfg)
     pred = P.build_disp_predictor(cfg)
-    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=3, sharpen=4.0)
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=3, sharpen=sharpen)
     proc.aggregator.load_state_dict(sd)
     proc = proc.to(DEV).eval(); pred = pred.to(DEV).eval()
-    proc.aggregator.engine = "direct"
+    proc.aggregator.engine = engine
+    proc.aggregator.precision = precision
     l, r = seeded.feature_pair(1, 32, 68, 120, seed=21, scale=0.5, shift=9)
     disps = [pred(c).cpu() for c in proc(l.to(DEV), r.to(DEV))]
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
-    _, want = O.psm_hot_path(sd, l, r, 192, prefix="")
-    for got, w in zip(disps, want):
-        assert float((got - w).abs().max()) < 1e-3
-        assert abs(O.epe(got, w + 1.0, 0, 1e9) - 1.0) < 1e-3   # |dEPE| against a shifted pseudo-GT
+    torch.set_num_threads(min(32, max(1, os.cpu_count() or 1)))
+    _, f32 = O.psm_hot_path(sd, l, r, 192, prefix="")
+    _, f64 = O.psm_hot_path(sd, l, r, 192, prefix="", dtype=torch.float64)
+    slack = 1.5 if precision != "bf16x3" else 12.0            # bf16x3 carries ~16 bits, fp16x3 ~21
+    for got, w32, w64 in zip(disps, f32, f64):
+        ours = float((got.double() - w64).abs().max())
+        theirs = float((w32.double() - w64).abs().max())
+        mean = float((got.double() - w64).abs().mean())
+        print("%s/%s sharpen %.0f: ours-vs-f64 max %.2e mean %.2e | f32 oracle-vs-f64 max %.2e | ours-vs-f32 oracle max %.2e"
+              % (engine, precision, sharpen, ours, mean, theirs, float((got - w32).abs().max())))
+        assert ours < slack * theirs + 2e-4
+        assert mean < (1e-4 if precision != "bf16x3" else 1e-3) * sharpen
+        gt = w64.float() + 1.0                                  # pseudo ground truth
+        assert abs(O.epe(got, gt, 0, 1e9) - O.epe(w32, gt, 0, 1e9)) < 1e-3      # |dEPE| vs the float32 oracle
 
 
 # ------------------------------------------------------------------------------- scans
@@ -514,3 +532,17 @@ def test_config1_tc_engine_vs_reference_golden(P, golden_dir, precision, tol):
     mean = max(float((d - w).abs().mean()) for d, w in zip(disps, rec["disps"]))
     print("tc engine %s: max |d_disp| %.3e mean %.3e" % (precision, worst, mean))
     assert worst < tol
+
+
+def test_cat_volume_blocked_matches_oracle(P):
+    tc = _tc_or_skip()
+    l, r = seeded.feature_pair(2, 16, 6, 20, seed=8)
+    want = O.cat_volume(l, r, 7, -2, 1)                      # [2,32,7,6,20]
+    for prec in ("fp16x3", "bf16"):
+        blk = tc.cat_volume_blocked(l.to(DEV), r.to(DEV), 7, -2, 1, prec)
+        assert blk.C == 32 and blk.dims == (7, 6, 20)
+        got = blk.to_ncdhw().cpu()
+        if prec == "bf16":
+            assert torch.equal(got, want.bfloat16().float())
+        else:
+            assert float((got - want).abs().max()) < 2.0 ** -20 * float(want.abs().max())
