@@ -44,7 +44,8 @@ constexpr int TAPS = 27;
 constexpr int NTHREADS = 192;
 constexpr int TMEM_COLS = 512;
 
-// KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane
+// KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane (reference kernel)
+// KIND 3: stride-1 conv, kw taps merged into N (the production kernel for stride-1 layers)
 // KIND 1: stride-2 conv (k3,p1)  M space = output grid; four (h,w)-parity sub-tiles per input plane
 // KIND 2: stride-2 transposed conv (k3,p1,op1)  M space = INPUT grid; 8 output parity classes,
 //         each a small conv over a 17x9 halo box
@@ -63,6 +64,16 @@ template <> struct Geo<2> {
     static constexpr int CBK = 4;
     static constexpr int PLANE_BYTES = 9856;                       // 4*17*9*16 = 9792, padded to 128
 };
+// KIND 3: stride-1 conv with the three kw taps merged into the MMA's N dimension.  The 8 tile columns
+// are w0-1 .. w0+6; every MMA multiplies the UNSHIFTED column block with [W(kw=0)|W(kw=1)|W(kw=2)], the
+// epilogue adds the three partial results of neighbouring columns (warp shuffles).  6 of 8 columns
+// produce outputs, but the A tile is streamed from shared memory 3x less often -- the operand
+// bandwidth, not the tensor pipe, bounds these N<=64 MMAs (profiles/README.md).
+template <> struct Geo<3> {
+    static constexpr int CBK = 4;
+    static constexpr int PLANE_BYTES = 4 * 18 * 8 * 16;            // 9216
+};
+constexpr int TWV = 6;                      // valid output columns per tile row in KIND 3
 
 struct Maps {
     CUtensorMap m[8];   // KIND 0/2: [0]=hi [1]=lo;  KIND 1: [(ph*2+pw)*2 + (0 hi | 1 lo)]
@@ -182,9 +193,10 @@ template <int KIND, bool SPLIT>
 struct Smem {
     using G = Geo<KIND>;
     static constexpr int CBK = G::CBK;
-    static constexpr int ROWS = SPLIT ? 2 * NB : NB;               // B-operand rows per channel block
-    static constexpr int TAP_BYTES = CBK * ROWS * 16;
-    static constexpr int W_BYTES = TAPS * TAP_BYTES;
+    static constexpr int NKW = KIND == 3 ? 3 : 1;                  // kw taps merged into one B block
+    static constexpr int ROWS = (SPLIT ? 2 * NB : NB) * NKW;       // B-operand rows per channel block
+    static constexpr int TAP_BYTES = CBK * ROWS * 16;              // one B block (a tap, or a (kd,kh) tap row)
+    static constexpr int W_BYTES = (TAPS / NKW) * TAP_BYTES;
     static constexpr int PLANE_BYTES = G::PLANE_BYTES;
     static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;
     static constexpr int PLANES_OFF = W_BYTES;
@@ -200,7 +212,7 @@ struct Smem {
     static constexpr int LH_COL = 3 * KD_COLS;                     // lo*Whi (split only)
     // KIND 2: one accumulator per output parity class (chains are <= 32 MMAs by construction)
     static constexpr int CLS_COLS = SPLIT ? 64 : 32;
-    static constexpr int ACC_COLS = KIND == 2 ? 4 * CLS_COLS : (SPLIT ? 3 * 64 + 32 : 3 * 32);
+    static constexpr int ACC_COLS = KIND == 2 ? 4 * CLS_COLS : (KIND == 3 ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32));
     static_assert(2 * ACC_COLS <= TMEM_COLS, "accumulators exceed TMEM");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -208,6 +220,7 @@ struct Smem {
 struct Item {
     int b, d0, d1, h0, w0;
 };
+template <int TWSTEP>
 __device__ __forceinline__ Item decode_item(const Params& p, int item) {
     const int per_b = p.tiles_w * p.tiles_h * p.nseg;
     Item it;
@@ -219,7 +232,7 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
     it.d0 = seg * p.seg_len;
     it.d1 = min(p.Dm, it.d0 + p.seg_len);
     it.h0 = th * TH;
-    it.w0 = tw * TW;
+    it.w0 = tw * TWSTEP;
     return it;
 }
 
@@ -321,15 +334,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
         // ================================ TMA producer ================================
         if (lane == 0) {
             mbar_expect_tx(wbar, S::W_BYTES);      // weights: packed in global exactly as they sit in smem
-            for (int t = 0; t < TAPS; ++t)
+            for (int t = 0; t < TAPS / S::NKW; ++t)
                 bulk_g2s(w_smem + t * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
                          S::TAP_BYTES, wbar);
             uint32_t n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+                const Item it = decode_item<(KIND == 3 ? TWV : TW)>(p, item);
                 const int nout = it.d1 - it.d0;
-                const int nplanes = KIND == 0 ? nout + 2 : (KIND == 1 ? 2 * nout + 1 : nout + 1);
-                const int pl0 = KIND == 0 ? it.d0 - 1 : (KIND == 1 ? 2 * it.d0 - 1 : it.d0);
+                const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : (KIND == 1 ? 2 * nout + 1 : nout + 1);
+                const int pl0 = (KIND == 0 || KIND == 3) ? it.d0 - 1 : (KIND == 1 ? 2 * it.d0 - 1 : it.d0);
                 for (int j = 0; j < nplanes; ++j, ++n) {
                     const int pl = pl0 + j;
                     const uint32_t slot = n % NSTAGE;
@@ -337,6 +350,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
                     unsigned char* dst = planes + slot * S::STAGE_BYTES;
                     if (KIND == 0) {
                         mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 18 * 10 * 16);
+                        tma_load_5d(dst, &maps.m[0], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl, p.in_cb0, it.b);
+                        if (SPLIT)
+                            tma_load_5d(dst + S::PLANE_BYTES, &maps.m[1], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl,
+                                        p.in_cb0, it.b);
+                    } else if (KIND == 3) {
+                        mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * S::PLANE_BYTES);
                         tma_load_5d(dst, &maps.m[0], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl, p.in_cb0, it.b);
                         if (SPLIT)
                             tma_load_5d(dst + S::PLANE_BYTES, &maps.m[1], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl,
@@ -379,7 +398,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
             };
             uint32_t n_base = 0, t_base = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item(p, item);
+                const Item it = decode_item<(KIND == 3 ? TWV : TW)>(p, item);
                 const int nout = it.d1 - it.d0;
                 if (KIND == 0) {
                     constexpr uint32_t LBO_A = 18 * 10 * 16, SBO_A = 10 * 16;
@@ -426,6 +445,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
                         }
                         tcgen05_commit(&tfull[buf]);
                         tcgen05_commit(&empty[(n_base + od) % NSTAGE]);          // plane d-1 is done
+                        if (od == nout - 1) {
+                            tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
+                            tcgen05_commit(&empty[(n_base + od + 2) % NSTAGE]);
+                        }
+                    }
+                    n_base += nout + 2;
+                    t_base += nout;
+                } else if (KIND == 3) {
+                    constexpr uint32_t LBO_A = 18 * 8 * 16, SBO_A = 8 * 16;
+                    constexpr uint32_t idesc_hi3 = make_idesc(3 * NB, FP16 ? 0u : 1u);     // A_lo x [Whi kw0..2]
+                    constexpr uint32_t a_hiw = desc_hi(SBO_A);
+                    int waited = 0;
+                    for (int od = 0; od < nout; ++od) {
+                        while (waited < od + 3) {
+                            const uint32_t n = n_base + waited;
+                            mbar_wait(&full[n % NSTAGE], (n / NSTAGE) & 1);
+                            ++waited;
+                        }
+                        const uint32_t t = t_base + od;
+                        const uint32_t buf = t & 1;
+                        mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
+                        tcgen05_fence_after();
+                        const uint32_t acc = tmem_base + buf * S::ACC_COLS;
+#pragma unroll
+                        for (int kd = 0; kd < 3; ++kd) {
+                            const uint32_t a_hi = planes_addr + ((n_base + od + kd) % NSTAGE) * S::STAGE_BYTES;
+                            const uint32_t a_lo0 = desc_lo(a_hi, LBO_A);
+#pragma unroll
+                            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                                for (int kk = 0; kk < CBK / 2; ++kk) {
+                                    const bool first = (kd == 0 && kh == 0 && kk == 0);
+                                    const uint64_t db = desc_of(b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
+                                    const uint32_t a_off = kh * SBO_A + 2 * kk * LBO_A;
+                                    tcgen05_mma_bf16(acc, desc_of(a_lo0 + (a_off >> 4), a_hiw), db, idesc_main, first ? 0u : 1u);
+                                    if (SPLIT)   // lo*Whi of the three kw lands on the (small) hi*Wlo columns
+                                        tcgen05_mma_bf16(acc + 3 * NB, desc_of(a_lo0 + ((S::PLANE_BYTES + a_off) >> 4), a_hiw), db,
+                                                         idesc_hi3, 1u);
+                                }
+                            }
+                        }
+                        tcgen05_commit(&tfull[buf]);
+                        tcgen05_commit(&empty[(n_base + od) % NSTAGE]);
                         if (od == nout - 1) {
                             tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
                             tcgen05_commit(&empty[(n_base + od + 2) % NSTAGE]);
@@ -566,11 +628,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
         for (int c = 0; c < NB; ++c) bias[c] = (p.bias && c < p.n_valid_out) ? __ldg(p.bias + c) : 0.f;
         uint32_t t = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const Item it = decode_item(p, item);
-            const int h = it.h0 + hl, w = it.w0 + wl;
-            const bool valid = h < p.Hm && w < p.Wm;
+            const Item it = decode_item<(KIND == 3 ? TWV : TW)>(p, item);
+            const int h = it.h0 + hl, w = KIND == 3 ? it.w0 - 1 + wl : it.w0 + wl;
+            const bool valid = KIND == 3 ? (h < p.Hm && wl >= 1 && wl <= TWV && w < p.Wm) : (h < p.Hm && w < p.Wm);
             for (int d = it.d0; d < it.d1; ++d) {
-                if (KIND != 2) {
+                if (KIND == 3) {
+                    const uint32_t buf = t & 1;
+                    mbar_wait(&tfull[buf], (t >> 1) & 1);
+                    tcgen05_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
+                    uint32_t r0[32], r1[32];
+                    float v[NB];
+                    // out(w) = D'[w-1][kw=0] + D'[w][kw=1] + D'[w+1][kw=2]; lanes of one tile row are adjacent
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        tmem_ld32(taddr + kw * NB, r0);
+                        if (SPLIT) tmem_ld32(taddr + 3 * NB + kw * NB, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int c = 0; c < NB; ++c) {
+                            float sv = __uint_as_float(r0[c]);
+                            if (SPLIT) sv += __uint_as_float(r1[c]);
+                            if (kw == 0) v[c] = __shfl_up_sync(0xffffffffu, sv, 1);
+                            else if (kw == 1) v[c] += sv;
+                            else v[c] = (v[c] + __shfl_down_sync(0xffffffffu, sv, 1)) * p.acc_scale;
+                        }
+                    }
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[buf]);
+                    ++t;
+                    if (valid) store_voxel<FP16>(p, v, bias, it.b, d, h, w);
+                } else if (KIND != 2) {
                     const uint32_t buf = t & 1;
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
                     tcgen05_fence_after();
@@ -662,31 +751,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
 // ---- weight packing ---------------------------------------------------------------------------
 // w: [27][Cin][Cout] fp32 -> blobs[(ob*IB + ib)] = [27][cbk][ROWS][8] 16-bit, ROWS = 32 (plain) or 64 (hi rows, lo
 // rows); one blob covers 8*cbk input channels x 32 output channels
+// nkw = 3 (KIND 3): a block covers one (kd,kh) tap row, rows = [hi kw0|hi kw1|hi kw2|lo kw0|lo kw1|lo kw2]
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cin, int Cout, int cbk,
-                                    int split, int fp16, float scale) {
-    const int rows = split ? 2 * NB : NB;
+                                    int nkw, int split, int fp16, float scale) {
+    const int hi_rows = NB * nkw;
+    const int rows = split ? 2 * hi_rows : hi_rows;
+    const int nblk = TAPS / nkw;
     const int IB = Cin / (8 * cbk), OB = (Cout + 31) / 32;
-    const size_t blob = (size_t)TAPS * cbk * rows * 8;
+    const size_t blob = (size_t)nblk * cbk * rows * 8;
     const size_t total = blob * IB * OB;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = i;
         const int e = r % 8; r /= 8;
         const int row = r % rows; r /= rows;
         const int cb = r % cbk; r /= cbk;
-        const int tap = r % TAPS; r /= TAPS;
+        const int blk = r % nblk; r /= nblk;
         const int ib = r % IB;
         const int ob = r / IB;
-        const int co = ob * 32 + (row % NB);
+        const bool is_lo = row >= hi_rows;
+        const int rr = row % hi_rows;
+        const int tap = blk * nkw + rr / NB;
+        const int co = ob * 32 + (rr % NB);
         const int ci = (ib * cbk + cb) * 8 + e;
         const float v = (co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] * scale : 0.f;
         if (fp16) {
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
-            out[i] = (row < NB) ? __half_as_ushort(hi) : __half_as_ushort(lo);
+            out[i] = is_lo ? __half_as_ushort(lo) : __half_as_ushort(hi);
         } else {
             __nv_bfloat16 hi, lo;
             split_bf16(v, hi, lo);
-            out[i] = (row < NB) ? __bfloat16_as_ushort(hi) : __bfloat16_as_ushort(lo);
+            out[i] = is_lo ? __bfloat16_as_ushort(lo) : __bfloat16_as_ushort(hi);
         }
     }
 }
@@ -772,6 +867,7 @@ static int launch_kind(const Maps& maps, const Params& p, int grid, bool split, 
 }
 
 static int cbk_of(int kind) { return kind == 1 ? Geo<1>::CBK : 4; }
+static int nkw_of(int kind) { return kind == 3 ? 3 : 1; }
 
 }  // namespace tc
 }  // namespace dmb
@@ -782,7 +878,7 @@ using namespace dmb::tc;
 extern "C" int dmb_b200_conv3d_tc_available(void) { return device_ok(); }
 
 extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split, int kind) {
-    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 2) return 0;
+    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 3) return 0;
     const int cbk = cbk_of(kind);
     const int64_t blob = (int64_t)TAPS * cbk * (split ? 64 : 32) * 16;
     return blob * (Cin / (8 * cbk)) * ((Cout + 31) / 32);
@@ -791,13 +887,13 @@ extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split,
 extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split,
                                                int fp16, float scale, int kind, void* stream) {
     DMB_REQUIRE(w_packed && w_blob, "conv3d_tc_pack_weights: null pointer");
-    DMB_REQUIRE(kind >= 0 && kind <= 2, "conv3d_tc_pack_weights: kind must be 0, 1 or 2");
+    DMB_REQUIRE(kind >= 0 && kind <= 3, "conv3d_tc_pack_weights: kind must be 0..3");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc_pack_weights: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(Cout > 0 && (Cout % 32 == 0 || Cout < 32), "conv3d_tc_pack_weights: Cout=%d must be <32 or a multiple of 32", Cout);
     DMB_REQUIRE(scale > 0.f, "conv3d_tc_pack_weights: scale must be positive");
     const int64_t n = dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, split, kind) / 2;
     pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w_packed, (uint16_t*)w_blob, Cin, Cout,
-                                                                                cbk_of(kind), split ? 1 : 0, fp16 ? 1 : 0, scale);
+                                                                                cbk_of(kind), nkw_of(kind), split ? 1 : 0, fp16 ? 1 : 0, scale);
     return check_launch("pack_weights_kernel");
 }
 
@@ -807,7 +903,7 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                                   int relu, int fp16, void* stream) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
-    DMB_REQUIRE(kind >= 0 && kind <= 2, "conv3d_tc: kind must be 0 (stride 1), 1 (stride 2) or 2 (transposed stride 2)");
+    DMB_REQUIRE(kind >= 0 && kind <= 3, "conv3d_tc: kind must be 0/3 (stride 1), 1 (stride 2) or 2 (transposed stride 2)");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(w_scale > 0.f, "conv3d_tc: w_scale must be positive");
     const bool scalar_out = (Cout == 1);
@@ -829,13 +925,14 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     Params p;
     p.B = (kind == 1) ? 1 : B;
     p.Dm = kind == 1 ? D / 2 : D; p.Hm = kind == 1 ? H / 2 : H; p.Wm = kind == 1 ? W / 2 : W;
-    p.Do = kind == 0 ? D : (kind == 1 ? D / 2 : 2 * D);
-    p.Ho = kind == 0 ? H : (kind == 1 ? H / 2 : 2 * H);
-    p.Wo = kind == 0 ? W : (kind == 1 ? W / 2 : 2 * W);
+    const bool same = (kind == 0 || kind == 3);
+    p.Do = same ? D : (kind == 1 ? D / 2 : 2 * D);
+    p.Ho = same ? H : (kind == 1 ? H / 2 : 2 * H);
+    p.Wo = same ? W : (kind == 1 ? W / 2 : 2 * W);
     p.n_valid_out = scalar_out ? 1 : 32;
     p.acc_scale = 1.0f / w_scale;
     p.tiles_h = (int)cdiv(p.Hm, TH);
-    p.tiles_w = (int)cdiv(p.Wm, TW);
+    p.tiles_w = (int)cdiv(p.Wm, kind == 3 ? TWV : TW);
     // depth segments: ~4 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
     // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
     const int cols = p.tiles_h * p.tiles_w * p.B;
@@ -864,7 +961,7 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                 if (rc) return rc;
             }
         } else {
-            const int bh = kind == 0 ? 18 : 17, bw = kind == 0 ? 10 : 9;
+            const int bh = kind == 2 ? 17 : 18, bw = kind == 0 ? 10 : (kind == 3 ? 8 : 9);
             rc = make_dense_map(&maps.m[0], xh, B, CBS, D, H, W, bh, bw, cbk, fp16);
             if (rc) return rc;
             rc = make_dense_map(&maps.m[1], xl, B, CBS, D, H, W, bh, bw, cbk, fp16);
@@ -899,7 +996,8 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                 }
                 if (kind == 0) rc = launch_kind<0>(maps, p, grid, split, fp16, stream);
                 else if (kind == 1) rc = launch_kind<1>(maps, p, grid, split, fp16, stream);
-                else rc = launch_kind<2>(maps, p, grid, split, fp16, stream);
+                else if (kind == 2) rc = launch_kind<2>(maps, p, grid, split, fp16, stream);
+                else rc = launch_kind<3>(maps, p, grid, split, fp16, stream);
                 if (rc) return rc;
             }
         }

@@ -9,12 +9,18 @@ Activations stay in the blocked channels-last 16-bit layout [B][C/8][D][H][W][8]
   'fp16' / 'bf16' : single 16-bit plane, 1 MMA per product (fastest, 11 / 8 significant bits)
 BatchNorm is folded (eval mode) exactly as on the direct path; packed weight blobs are cached per
 layer until a parameter changes."""
+import os
+
 import torch
 
 from ..... import _cabi as C
 from .....ops import functional as F_
 from ...layers.basic_layers import FusedConvUnit
 
+
+# stride-1 layers: kind 3 (kw taps merged into the MMA N dimension, the fast kernel) or kind 0 (one
+# MMA per tap; kept as the simpler reference implementation, DMB_B200_TC_KW_MERGE=0 selects it)
+KW_MERGE = os.environ.get("DMB_B200_TC_KW_MERGE", "1") != "0"
 
 PRECISIONS = {          # name -> (split, fp16)
     "fp16x3": (True, True),
@@ -91,7 +97,7 @@ def _kind_of(layer):
             raise NotImplementedError("transposed conv on tcgen05: stride 2, output_padding 1 only")
         return 2
     if tuple(conv.stride) == (1, 1, 1):
-        return 0
+        return 3 if KW_MERGE else 0
     if tuple(conv.stride) == (2, 2, 2):
         return 1
     raise NotImplementedError("stride %s is not supported on tcgen05" % (tuple(conv.stride),))
@@ -141,7 +147,7 @@ def conv_tc(layer, x, residual=None, relu=False, res_f32=None):
     D, H, W = x.dims
     if kind == 1 and (D % 2 or H % 2 or W % 2):
         raise ValueError("stride-2 convolution on tcgen05 needs even extents, got %s" % (x.dims,))
-    odims = x.dims if kind == 0 else (tuple(n // 2 for n in x.dims) if kind == 1 else tuple(2 * n for n in x.dims))
+    odims = x.dims if kind in (0, 3) else (tuple(n // 2 for n in x.dims) if kind == 1 else tuple(2 * n for n in x.dims))
     dev = x.hi.device
     fp16 = 1 if x.fp16 else 0
     if Cout == 1:

@@ -153,7 +153,9 @@ int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out
                                 int B, int C, int H, int W, const int* disp_idx_host, int D, int fp16, void* stream);
 
 /* 3x3x3 convolutions of the trunk on tcgen05, blocked channels-last 16-bit activations.
- *   kind 0: stride 1, pad 1                      (conv3d_bn[_relu], basic_layers.py:68-177)
+ *   kind 0: stride 1, pad 1, one MMA per tap     (conv3d_bn[_relu], basic_layers.py:68-177)
+ *   kind 3: stride 1, pad 1, the three kw taps merged into the MMA N dimension (same result,
+ *           3x fewer A-operand reads; the production kernel for stride-1 layers)
  *   kind 1: stride 2, pad 1 (even input extents)  (Hourglass conv1/conv3, utils/hourglass.py:35-48)
  *   kind 2: transposed, stride 2, pad 1, output_padding 1 (Hourglass conv5/conv6, :53-60)
  * x_hi/x_lo: [B][Cin/8][D][H][W][8] (x_lo NULL => single plane, else the (hi,lo) split pair);
