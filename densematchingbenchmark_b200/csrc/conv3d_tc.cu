@@ -39,9 +39,13 @@ namespace tc {
 
 constexpr int TH = 16, TW = 8;              // M tile (in-plane) = 128 rows of the MMA
 constexpr int NB = 32;                      // output channels per pass
-constexpr int NSTAGE = 4;                   // depth-plane ring
 constexpr int TAPS = 27;
-constexpr int NTHREADS = 192;
+// threads: warp 0 = TMA producer, warp 1 = MMA issuer, then 4 epilogue warps (8 for the transposed
+// kernel, whose tiles carry 8 output parity classes = 8x the epilogue work per MMA tile)
+__host__ __device__ constexpr int nthreads_of(int kind) { return kind == 2 ? 320 : 192; }
+// depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
+// work-item boundaries)
+__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 6 : 4; }
 constexpr int TMEM_COLS = 512;
 
 // KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane (reference kernel)
@@ -199,8 +203,9 @@ struct Smem {
     static constexpr int W_BYTES = (TAPS / NKW) * TAP_BYTES;
     static constexpr int PLANE_BYTES = G::PLANE_BYTES;
     static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;
+    static constexpr int NST = nstage_of(KIND);
     static constexpr int PLANES_OFF = W_BYTES;
-    static constexpr int BAR_OFF = PLANES_OFF + NSTAGE * STAGE_BYTES;
+    static constexpr int BAR_OFF = PLANES_OFF + NST * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256;
     static constexpr uint32_t LBO_B = ROWS * 16;
     static constexpr uint32_t SBO_B = 128;
@@ -291,9 +296,12 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
 }
 
 template <int KIND, bool SPLIT, bool FP16>
-__global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+__global__ void __launch_bounds__(nthreads_of(KIND), 1)
+conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     using S = Smem<KIND, SPLIT>;
     constexpr int CBK = S::CBK;
+    constexpr int NSTAGE = S::NST;
+    constexpr int EPI_WARPS = nthreads_of(KIND) / 32 - 2;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* w_smem = smem;
     unsigned char* planes = smem + S::PLANES_OFF;
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], 4);
+            mbar_init(&tempty[i], EPI_WARPS);
         }
         mbar_init(wbar, 1);
         fence_mbar_init();
@@ -711,8 +719,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
                         mbar_wait(&tfull[rd], (t >> 1) & 1);
                         tcgen05_fence_after();
                         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + rd * S::ACC_COLS;
+                        const int cls0 = (warp - 2) >> 2;          // warps 2..5: classes 0,2; warps 6..9: classes 1,3
 #pragma unroll 1
-                        for (int cls = 0; cls < 4; ++cls) {
+                        for (int cls = cls0; cls < 4; cls += 2) {
                             uint32_t r0[32];
                             float v[NB];
                             tmem_ld32(taddr + cls * S::CLS_COLS, r0);
@@ -727,7 +736,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv3d_tc_kernel(const __grid_con
 #pragma unroll
                                 for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) * p.acc_scale;
                             }
-                            if (cls == 3) {
+                            if (cls >= 2) {
                                 tcgen05_fence_before();
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&tempty[rd]);
@@ -855,7 +864,7 @@ template <int KIND, bool SPLIT, bool FP16>
 static int launch_pass(const Maps& maps, const Params& p, int grid, void* stream) {
     const size_t smem = Smem<KIND, SPLIT>::TOTAL;
     DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KIND, SPLIT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3d_tc_kernel<KIND, SPLIT, FP16><<<grid, NTHREADS, smem, as_stream(stream)>>>(maps, p);
+    conv3d_tc_kernel<KIND, SPLIT, FP16><<<grid, nthreads_of(KIND), smem, as_stream(stream)>>>(maps, p);
     return check_launch("conv3d_tc_kernel");
 }
 

@@ -15,32 +15,37 @@
 namespace dmb {
 
 // running softmax-expectation state: m = running max, s = sum e^(c-m), t = sum e^(c-m) * disp
+// e^x for x <= 0 as exp2f(x * log2(e)): the subtraction (c - m) is done first, so the product's rounding
+// error is relative to the SHIFTED argument (|x| < ~20 for every term that matters) -- 2-ulp exp2f keeps
+// the softmax weights within ~1e-6 relative of expf at a third of its instruction count.
+__device__ __forceinline__ float exp_neg(float x) { return exp2f(x * 1.4426950408889634f); }
+
 struct SoftState {
     float m, s, t;
     __device__ __forceinline__ void init() { m = -INFINITY; s = 0.f; t = 0.f; }
     __device__ __forceinline__ void push4(const float c[4], const float dv[4]) {
         const float cm = fmaxf(fmaxf(c[0], c[1]), fmaxf(c[2], c[3]));
         if (cm > m) {
-            const float f = expf(m - cm);   // m = -inf on the first chunk: f = 0, s = t = 0
+            const float f = exp_neg(m - cm);   // m = -inf on the first chunk: f = 0, s = t = 0
             s *= f;
             t *= f;
             m = cm;
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float e = expf(c[j] - m);
+            const float e = exp_neg(c[j] - m);
             s += e;
             t = fmaf(e, dv[j], t);
         }
     }
     __device__ __forceinline__ void push1(float c, float dv) {
         if (c > m) {
-            const float f = expf(m - c);
+            const float f = exp_neg(m - c);
             s *= f;
             t *= f;
             m = c;
         }
-        const float e = expf(c - m);
+        const float e = exp_neg(c - m);
         s += e;
         t = fmaf(e, dv, t);
     }
@@ -198,6 +203,80 @@ __global__ void __launch_bounds__(256) upsample_regress_kernel(const float* __re
     if (REGRESS) disp_out[(size_t)b * oplane + (size_t)y * p.W + x] = p.normalize ? st.result() : lin;
 }
 
+// Trilinear variant with the thread's 2-D-interpolated source column a[0..Dl) staged in shared memory
+// ([Dl][256], each thread touches only its own column: no barrier, no bank conflicts); the depth
+// march then costs two shared loads and a blend per output value.
+template <bool WRITE_COST, bool REGRESS>
+__global__ void __launch_bounds__(256) upsample_trilinear_kernel(const float* __restrict__ low,
+                                                                 float* __restrict__ cost_out,
+                                                                 float* __restrict__ disp_out,
+                                                                 const float* __restrict__ dvals, RegressParams p) {
+    extern __shared__ float sa[];
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    if (x >= p.W || y >= p.H) return;
+    const size_t lplane = (size_t)p.Hl * p.Wl;
+    const float* lb = low + (size_t)b * p.Dl * lplane;
+    const size_t oplane = (size_t)p.H * p.W;
+    float* co = WRITE_COST ? cost_out + (size_t)b * p.D * oplane + (size_t)y * p.W + x : nullptr;
+    float* col = sa + threadIdx.x;
+
+    const float sy = p.H > 1 ? (float)(p.Hl - 1) / (float)(p.H - 1) : 0.f;
+    const float sx = p.W > 1 ? (float)(p.Wl - 1) / (float)(p.W - 1) : 0.f;
+    const float sd = p.D > 1 ? (float)(p.Dl - 1) / (float)(p.D - 1) : 0.f;
+    {
+        const float fy = sy * (float)y, fx = sx * (float)x;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < p.Hl - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wl - 1 ? 1 : 0);
+        const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+        const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+        const float* q00 = lb + y0 * p.Wl + x0;
+        const float* q01 = lb + y0 * p.Wl + x1;
+        const float* q10 = lb + y1 * p.Wl + x0;
+        const float* q11 = lb + y1 * p.Wl + x1;
+#pragma unroll 4
+        for (int dl = 0; dl < p.Dl; ++dl) {
+            const size_t o = (size_t)dl * lplane;
+            col[dl * 256] = ly0 * (lx0 * __ldg(q00 + o) + lx1 * __ldg(q01 + o)) +
+                            ly1 * (lx0 * __ldg(q10 + o) + lx1 * __ldg(q11 + o));
+        }
+    }
+    SoftState st;
+    st.init();
+    float lin = 0.f;
+    for (int d0 = 0; d0 < p.D; d0 += 4) {
+        float c[4], dv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int d = d0 + j;
+            if (d < p.D) {
+                const float fd = sd * (float)d;
+                const int i0 = (int)fd;
+                const int i1 = i0 + (i0 < p.Dl - 1 ? 1 : 0);
+                const float l1 = fd - (float)i0, l0 = 1.f - l1;
+                const float v = l0 * col[i0 * 256] + l1 * col[i1 * 256];
+                if (WRITE_COST) st_cs_f(co + (size_t)d * oplane, v);
+                c[j] = v * p.alpha;
+                dv[j] = REGRESS ? disp_value(dvals, p, d) : 0.f;
+            } else {
+                c[j] = -INFINITY;
+                dv[j] = 0.f;
+            }
+        }
+        if (REGRESS) {
+            if (p.normalize) {
+                st.push4(c, dv);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (d0 + j < p.D) lin = fmaf(c[j], dv[j], lin);
+            }
+        }
+    }
+    if (REGRESS) disp_out[(size_t)b * oplane + (size_t)y * p.W + x] = p.normalize ? st.result() : lin;
+}
+
 // stand-alone soft-argmin over a materialised cost [B,D,H,W]; one thread per pixel, 8 loads in
 // flight per thread, coalesced across x.
 template <bool PER_PIXEL>
@@ -304,6 +383,21 @@ extern "C" int dmb_b200_upsample_regress(const float* cost_low, const float* up_
     cudaStream_t s = as_stream(stream);
 #define DMB_LAUNCH_UP(M, WC, RG) \
     upsample_regress_kernel<M, WC, RG><<<grid, 256, 0, s>>>(cost_low, up_weight, cost_out, disp_out, disp_values, p)
+    const size_t tri_smem = (size_t)Dl * 256 * sizeof(float);
+    if (mode == 0 && tri_smem <= 160 * 1024) {
+#define DMB_LAUNCH_TRI(WC, RG)                                                                                          \
+    do {                                                                                                                \
+        if (tri_smem > 48 * 1024)                                                                                       \
+            DMB_CUDA(cudaFuncSetAttribute(upsample_trilinear_kernel<WC, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)tri_smem));                                                              \
+        upsample_trilinear_kernel<WC, RG><<<grid, 256, tri_smem, s>>>(cost_low, cost_out, disp_out, disp_values, p);    \
+    } while (0)
+        if (cost_out && disp_out) DMB_LAUNCH_TRI(true, true);
+        else if (cost_out) DMB_LAUNCH_TRI(true, false);
+        else DMB_LAUNCH_TRI(false, true);
+#undef DMB_LAUNCH_TRI
+        return check_launch("upsample_trilinear_kernel");
+    }
     if (mode == 0) {
         if (cost_out && disp_out) DMB_LAUNCH_UP(0, true, true);
         else if (cost_out) DMB_LAUNCH_UP(0, true, false);
