@@ -179,6 +179,224 @@ __global__ void __launch_bounds__(1024) sga_dir_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------
+// SGA, tiled kernels (coalesced HBM access in both scan orientations).
+//
+// Vertical scans (dir 2 top->bottom, 3 bottom->top): a CTA owns 32 adjacent columns of one (b,c);
+// lane = column, warp = group of DPT consecutive disparities held in registers.  Neighbouring
+// disparities and the max over d cross warps through a tiny double-buffered shared array
+// (one barrier per step).  Every global access is a 128-byte row segment.
+// ---------------------------------------------------------------------------------------
+template <int DPT>
+__global__ void __launch_bounds__(256) sga_vertical_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                           float* __restrict__ out, int C, int D, int H, int W, int dir,
+                                                           int first) {
+    __shared__ float lo_s[2][8][32], hi_s[2][8][32], mx_s[2][8][32];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + lane;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const bool colok = col < W;
+    const int dbase = grp * DPT;
+    const size_t plane = (size_t)H * W;
+    const float* xb = x + ((size_t)(b * C + c) * D + dbase) * plane + (colok ? col : 0);
+    float* ob = out + ((size_t)(b * C + c) * D + dbase) * plane + (colok ? col : 0);
+    const float* gb = guid + (((size_t)(b * 4 + dir) * 5) * C + c) * plane + (colok ? col : 0);
+    const size_t gk = (size_t)C * plane;
+    const bool rev = dir == 3;
+    float prev[DPT];
+#pragma unroll
+    for (int j = 0; j < DPT; ++j) prev[j] = 0.f;
+    // software pipeline: the loads of step s+1 are issued before step s is computed
+    float xn[DPT], on[DPT], wn[5];
+    auto fetch = [&](int step) {
+        const int y = rev ? H - 1 - step : step;
+        const size_t row = (size_t)y * W;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) wn[k] = colok ? __ldg(gb + k * gk + row) : 0.f;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const bool ok = colok && dbase + j < D;
+            xn[j] = ok ? __ldg(xb + (size_t)j * plane + row) : 0.f;
+            on[j] = (ok && !first) ? ob[(size_t)j * plane + row] : -INFINITY;
+        }
+    };
+    fetch(0);
+    for (int step = 0; step < H; ++step) {
+        const int y = rev ? H - 1 - step : step;
+        const size_t row = (size_t)y * W;
+        float xv[DPT], ov[DPT], w[5];
+        float nrm = 0.f;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            w[k] = wn[k];
+            nrm += fabsf(w[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            xv[j] = xn[j];
+            ov[j] = on[j];
+        }
+        if (step + 1 < H) fetch(step + 1);
+        const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k] *= inv;
+        float below = 0.f, above = 0.f, mx = 0.f;
+        if (step > 0) {
+            const int pb = (step - 1) & 1;
+            below = grp > 0 ? hi_s[pb][grp - 1][lane] : 0.f;                  // A(p-r, dbase-1)
+            above = grp < 7 ? lo_s[pb][grp + 1][lane] : 0.f;                  // A(p-r, dbase+DPT)
+            mx = mx_s[pb][0][lane];
+#pragma unroll
+            for (int g = 1; g < 8; ++g) mx = fmaxf(mx, mx_s[pb][g][lane]);
+        }
+        float cur[DPT];
+        float gmax = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            const int d = dbase + j;
+            float v = 0.f;
+            if (d < D) {
+                v = w[0] * xv[j];
+                if (step > 0) {
+                    const float dm = j > 0 ? prev[j - 1] : below;
+                    // the value one above the last valid disparity is outside the volume: 0
+                    const float dp = (d + 1 < D) ? (j < DPT - 1 ? prev[j + 1] : above) : 0.f;
+                    v += w[1] * prev[j] + w[2] * dm + w[3] * dp + w[4] * mx;
+                }
+                gmax = fmaxf(gmax, v);
+                if (colok) ob[(size_t)j * plane + row] = fmaxf(ov[j], v);   // ov = -inf for the first direction
+            }
+            cur[j] = v;
+        }
+        const int cb = step & 1;
+        lo_s[cb][grp][lane] = cur[0];
+        hi_s[cb][grp][lane] = cur[DPT - 1];
+        mx_s[cb][grp][lane] = gmax;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) prev[j] = cur[j];
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Horizontal scans (dir 0 left->right, 1 right->left): a CTA owns YT=8 rows of one (b,c); warp = row
+// (an independent scan line), lane l holds disparities l, l+32, l+64, ... so that d-1 / d+1 are
+// lane-neighbours (warp shuffles) and the max over d is a warp reduction: no barrier inside a tile.
+// x / out / guidance travel through shared-memory tiles of TT scan steps, loaded and stored as 128-byte
+// row segments and transposed on the way in ([y][t][d], odd pitch).
+// ---------------------------------------------------------------------------------------
+template <int NJ>   // NJ = ceil(D / 32) disparities per lane
+__global__ void __launch_bounds__(128) sga_horizontal_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                             float* __restrict__ out, int C, int D, int H, int W, int dir,
+                                                             int first, int TT) {
+    extern __shared__ float sh[];
+    constexpr int YT = 4;                                   // rows (= warps) per CTA
+    const int Dp = D | 1;                                   // odd pitch: conflict-free transposing stores
+    float* xt = sh;                                         // [YT][TT][Dp]
+    float* ot = xt + (size_t)YT * TT * Dp;                  // [YT][TT][Dp]
+    float* gt = ot + (size_t)YT * TT * Dp;                  // [5][YT][TT]
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+    const int y0 = blockIdx.x * YT;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const size_t plane = (size_t)H * W;
+    const float* xb = x + ((size_t)(b * C + c) * D) * plane;
+    float* ob = out + ((size_t)(b * C + c) * D) * plane;
+    const float* gb = guid + (((size_t)(b * 4 + dir) * 5) * C + c) * plane;
+    const size_t gk = (size_t)C * plane;
+    const bool rev = dir == 1;
+    const int ntiles = (W + TT - 1) / TT;
+    // tile transfers: a warp moves one (d, row) segment of TT values per iteration; lanes run along t
+    const int tpl = TT < 32 ? TT : 32;                      // active lanes along t (TT is a power of two <= 32)
+    const int rows_per_iter = (32 / tpl) * YT;              // (d,row) segments handled per CTA iteration
+    const int seg_in_warp = lane / tpl;                     // which of the warp's segments this lane serves
+    const int tl = lane % tpl;
+    float prev[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) prev[j] = 0.f;
+    bool started = false;
+    for (int ti = 0; ti < ntiles; ++ti) {
+        const int tile = rev ? ntiles - 1 - ti : ti;
+        const int t0 = tile * TT;
+        const int tx = t0 + tl;
+        for (int r = wy * (32 / tpl) + seg_in_warp; r < D * YT; r += rows_per_iter) {
+            const int yy = r % YT, d = r / YT;
+            const int y = y0 + yy;
+            float v = 0.f, o = -INFINITY;
+            if (y < H && tx < W) {
+                const size_t a = (size_t)d * plane + (size_t)y * W + tx;
+                v = __ldg(xb + a);
+                if (!first) o = ob[a];
+            }
+            const size_t si = ((size_t)yy * TT + tl) * Dp + d;
+            xt[si] = v;
+            ot[si] = o;
+        }
+        for (int r = wy * (32 / tpl) + seg_in_warp; r < 5 * YT; r += rows_per_iter) {
+            const int yy = r % YT, k = r / YT;
+            const int y = y0 + yy;
+            gt[(k * YT + yy) * TT + tl] = (y < H && tx < W) ? __ldg(gb + k * gk + (size_t)y * W + tx) : 0.f;
+        }
+        __syncthreads();
+        // ---- scan the TT steps of this warp's row ----
+        if (y0 + wy < H) {
+            const int nst = min(TT, W - t0);
+            for (int s2 = 0; s2 < nst; ++s2) {
+                const int t = rev ? nst - 1 - s2 : s2;
+                float w[5], nrm = 0.f;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    w[k] = gt[(k * YT + wy) * TT + t];
+                    nrm += fabsf(w[k]);
+                }
+                const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) w[k] *= inv;
+                float mx = -INFINITY;
+                if (started) {
+#pragma unroll
+                    for (int j = 0; j < NJ; ++j)
+                        if (j * 32 + lane < D) mx = fmaxf(mx, prev[j]);
+                    mx = warp_max(mx);
+                }
+                const float* xrow = xt + ((size_t)wy * TT + t) * Dp;
+                float* orow = ot + ((size_t)wy * TT + t) * Dp;
+                float cur[NJ];
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    const int d = j * 32 + lane;
+                    // neighbours in d: lane-1 / lane+1 of the same j, wrapping to j-1 / j+1 at the warp edge
+                    float dm = __shfl_up_sync(0xffffffffu, prev[j], 1);
+                    const float wrap_dn = __shfl_sync(0xffffffffu, j > 0 ? prev[j > 0 ? j - 1 : 0] : 0.f, 31);
+                    if (lane == 0) dm = wrap_dn;
+                    float dp = __shfl_down_sync(0xffffffffu, prev[j], 1);
+                    const float wrap_up = __shfl_sync(0xffffffffu, j < NJ - 1 ? prev[j < NJ - 1 ? j + 1 : j] : 0.f, 0);
+                    if (lane == 31) dp = wrap_up;
+                    if (d + 1 >= D) dp = 0.f;
+                    float v = 0.f;
+                    if (d < D) {
+                        v = w[0] * xrow[d];
+                        if (started) v += w[1] * prev[j] + w[2] * dm + w[3] * dp + w[4] * mx;
+                        orow[d] = fmaxf(orow[d], v);      // -inf for the first direction
+                    }
+                    cur[j] = v;
+                }
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) prev[j] = cur[j];
+                started = true;
+            }
+        } else {
+            started = true;
+        }
+        __syncthreads();
+        for (int r = wy * (32 / tpl) + seg_in_warp; r < D * YT; r += rows_per_iter) {
+            const int yy = r % YT, d = r / YT;
+            const int y = y0 + yy;
+            if (y < H && tx < W) ob[(size_t)d * plane + (size_t)y * W + tx] = ot[((size_t)yy * TT + tl) * Dp + d];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // LGA, radius 2 (5x5 window, 75 weights per pixel held in registers).  One thread per pixel,
 // marching over d with the three d-planes of the 5x5 neighbourhood kept in registers, so each
 // step loads 25 new values and issues 75 FMAs.
@@ -238,6 +456,109 @@ __global__ void __launch_bounds__(128) lga_r2_kernel(const float* __restrict__ x
             vm[i] = v0[i];
             v0[i] = vp[i];
         }
+    }
+}
+
+// Tiled variant: a 32x8 pixel tile per CTA; the NEW depth plane (d+1) of the tile + halo is staged in
+// shared memory once per step (double buffered, one barrier per step, the global loads of plane d+2
+// are in flight while plane d is computed); the planes d-1, d, d+1 of each thread's 5x5 neighbourhood
+// rotate through three register arrays (loop unrolled by 3, no moves).  25 shared loads + 75 FMAs per
+// output value.
+__global__ void __launch_bounds__(256, 1) lga_r2_tiled_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                              float* __restrict__ out, int D, int H, int W) {
+    constexpr int TX = 32, TY = 8, PW = TX + 4, PH = TY + 4, NE = PH * PW;   // 432 tile elements
+    __shared__ float tile[2][NE];
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int px = x0 + tx, py = y0 + ty;
+    const int b = blockIdx.z;
+    const bool inside = px < W && py < H;
+    const size_t plane = (size_t)H * W;
+    float w[75];
+    {
+        const float* gb = guid + (size_t)b * 75 * plane + (size_t)(inside ? py : 0) * W + (inside ? px : 0);
+        float nrm = 0.f;
+#pragma unroll
+        for (int i = 0; i < 75; ++i) {
+            w[i] = __ldg(gb + (size_t)i * plane);
+            nrm += fabsf(w[i]);
+        }
+        nrm = fmaxf(nrm, 1e-12f);
+#pragma unroll
+        for (int i = 0; i < 75; ++i) w[i] = w[i] / nrm;
+    }
+    const float* xb = x + (size_t)b * D * plane;
+    float* ob = out + (size_t)b * D * plane + (size_t)py * W + px;
+    // this thread stages tile elements e0 = tid and e1 = tid + 256 (if < NE); offsets are loop invariant
+    int goff[2];
+    bool gok[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int e = tid + k * 256;
+        const int r = e / PW, c = e - r * PW;
+        const int yy = y0 + r - 2, xx = x0 + c - 2;
+        gok[k] = e < NE && yy >= 0 && yy < H && xx >= 0 && xx < W;
+        goff[k] = gok[k] ? yy * W + xx : 0;
+    }
+    auto fetch = [&](int d, float (&r)[2]) {
+        const bool dok = d < D;
+        const float* q = xb + (size_t)(dok ? d : 0) * plane;
+        r[0] = (dok && gok[0]) ? __ldg(q + goff[0]) : 0.f;
+        r[1] = (dok && gok[1]) ? __ldg(q + goff[1]) : 0.f;
+    };
+    auto stage = [&](int slot, const float (&r)[2]) {
+        tile[slot][tid] = r[0];
+        if (tid + 256 < NE) tile[slot][tid + 256] = r[1];
+    };
+    const float* tbase0 = &tile[0][ty * PW + tx];
+    const float* tbase1 = &tile[1][ty * PW + tx];
+    float A[25], Bv[25], Cv[25];
+    float pre[2];
+    // prologue: plane 0 -> Bv (centre of d=0), A = 0 (plane -1); plane 1 staged in slot 1; plane 2 in flight
+    fetch(0, pre);
+    stage(0, pre);
+    fetch(1, pre);
+    __syncthreads();
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+            A[ky * 5 + kx] = 0.f;
+            Bv[ky * 5 + kx] = tbase0[ky * PW + kx];
+        }
+    stage(1, pre);
+    fetch(2, pre);
+    __syncthreads();
+    // step(d, M, Cn, Pl): plane d+1 (slot (d+1)&1) -> Pl; out(d) = w0.Cn + w1.M + w2.Pl; stage plane d+2, prefetch d+3
+    auto step = [&](int d, float (&M)[25], float (&Cn)[25], float (&Pl)[25]) {
+        const float* tb = ((d + 1) & 1) ? tbase1 : tbase0;
+        float acc = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const int i = ky * 5 + kx;
+                Pl[i] = tb[ky * PW + kx];
+                acc = fmaf(w[i], Cn[i], acc);
+                acc = fmaf(w[25 + i], M[i], acc);
+                acc = fmaf(w[50 + i], Pl[i], acc);
+            }
+        if (inside) st_cs_f(ob + (size_t)d * plane, acc);
+        // slot d&1 held plane d (already consumed into registers one step ago): refill it with plane d+2
+        stage(d & 1, pre);
+        fetch(d + 3, pre);
+        __syncthreads();
+    };
+    int d = 0;
+    for (; d + 3 <= D; d += 3) {
+        step(d, A, Bv, Cv);
+        step(d + 1, Bv, Cv, A);
+        step(d + 2, Cv, A, Bv);
+    }
+    if (d < D) {
+        step(d, A, Bv, Cv);
+        if (d + 1 < D) step(d + 1, Bv, Cv, A);
     }
 }
 
@@ -304,14 +625,70 @@ extern "C" int dmb_b200_spn_backward(const float* X, const float* G1, const floa
     return check_launch("spn_backward_kernel");
 }
 
+template <int DPT>
+static void launch_sga_v(const float* x, const float* g, float* out, int B, int C, int D, int H, int W, int dir, int first,
+                         cudaStream_t s) {
+    dim3 grid((unsigned)cdiv(W, 32), C, B);
+    sga_vertical_kernel<DPT><<<grid, 256, 0, s>>>(x, g, out, C, D, H, W, dir, first);
+}
+template <int NJ>
+static int launch_sga_h(const float* x, const float* g, float* out, int B, int C, int D, int H, int W, int dir, int first,
+                        cudaStream_t s) {
+    const int Dp = D | 1;
+    int TT = 32;
+    auto bytes = [&](int tt) { return ((size_t)2 * 4 * tt * Dp + 5 * 4 * tt) * sizeof(float); };
+    while (TT > 4 && bytes(TT) > 72 * 1024) TT >>= 1;         // <= 72 KB per CTA: three CTAs per SM
+    const size_t smem = bytes(TT);
+    if (smem > 200 * 1024) return 1;
+    if (smem > 48 * 1024)
+        DMB_CUDA(cudaFuncSetAttribute(sga_horizontal_kernel<NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)cdiv(H, 4), C, B);
+    sga_horizontal_kernel<NJ><<<grid, 128, smem, s>>>(x, g, out, C, D, H, W, dir, first, TT);
+    return 0;
+}
+
 extern "C" int dmb_b200_sga(const float* x, const float* guidance, float* out, int B, int C, int D, int H, int W,
                             void* stream) {
     DMB_REQUIRE(x && guidance && out, "sga: null pointer");
     DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "sga: non-positive dimension");
     DMB_REQUIRE(D <= 1024, "sga: D=%d exceeds 1024", D);
+    DMB_REQUIRE(C <= 65535 && B <= 65535, "sga: grid dimension too large");
+    cudaStream_t s = as_stream(stream);
+    const bool tiled = D <= 256;
     for (int dir = 0; dir < 4; ++dir) {
+        const int first = dir == 0 ? 1 : 0;
+        if (tiled && dir < 2) {
+            const int nj = (D + 31) / 32;
+            int rc = 0;
+            switch (nj) {
+                case 1: rc = launch_sga_h<1>(x, guidance, out, B, C, D, H, W, dir, first, s); break;
+                case 2: rc = launch_sga_h<2>(x, guidance, out, B, C, D, H, W, dir, first, s); break;
+                case 3: rc = launch_sga_h<3>(x, guidance, out, B, C, D, H, W, dir, first, s); break;
+                case 4: rc = launch_sga_h<4>(x, guidance, out, B, C, D, H, W, dir, first, s); break;
+                case 5: case 6: rc = launch_sga_h<6>(x, guidance, out, B, C, D, H, W, dir, first, s); break;
+                default: rc = launch_sga_h<8>(x, guidance, out, B, C, D, H, W, dir, first, s); break;
+            }
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                rc = check_launch("sga_horizontal_kernel");
+                if (rc) return rc;
+                continue;
+            }
+        } else if (tiled) {
+            const int dpt = (D + 7) / 8;
+            if (dpt <= 4) launch_sga_v<4>(x, guidance, out, B, C, D, H, W, dir, first, s);
+            else if (dpt <= 6) launch_sga_v<6>(x, guidance, out, B, C, D, H, W, dir, first, s);
+            else if (dpt <= 8) launch_sga_v<8>(x, guidance, out, B, C, D, H, W, dir, first, s);
+            else if (dpt <= 12) launch_sga_v<12>(x, guidance, out, B, C, D, H, W, dir, first, s);
+            else if (dpt <= 16) launch_sga_v<16>(x, guidance, out, B, C, D, H, W, dir, first, s);
+            else if (dpt <= 24) launch_sga_v<24>(x, guidance, out, B, C, D, H, W, dir, first, s);
+            else launch_sga_v<32>(x, guidance, out, B, C, D, H, W, dir, first, s);
+            int rc = check_launch("sga_vertical_kernel");
+            if (rc) return rc;
+            continue;
+        }
+        // generic fallback (very large D): one CTA per scan line
         const bool horiz = dir < 2;
-        // vertical scans: 8 adjacent columns per CTA so that every 32-byte sector is fully used
         int lpb = horiz ? 1 : 8;
         while (lpb > 1 && D * lpb > 1024) lpb >>= 1;
         const int nlines = horiz ? H : W;
@@ -320,8 +697,6 @@ extern "C" int dmb_b200_sga(const float* x, const float* guidance, float* out, i
         const int nwarps = threads / 32;
         const size_t smem = ((size_t)2 * (D + 2) * lpb + (size_t)nwarps * lpb) * 4;
         const unsigned grid = (unsigned)((size_t)B * C * groups);
-        const int first = dir == 0 ? 1 : 0;
-        cudaStream_t s = as_stream(stream);
         switch (lpb) {
             case 1: sga_dir_kernel<1><<<grid, threads, smem, s>>>(x, guidance, out, C, D, H, W, dir, first); break;
             case 2: sga_dir_kernel<2><<<grid, threads, smem, s>>>(x, guidance, out, C, D, H, W, dir, first); break;
@@ -340,10 +715,10 @@ extern "C" int dmb_b200_lga(const float* x, const float* guidance, float* out, i
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0 && radius >= 0, "lga: bad dimension");
     DMB_REQUIRE(B <= 65535, "lga: batch too large");
     if (radius == 2) {
-        dim3 grid((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 4), B);
+        dim3 grid((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
         DMB_REQUIRE(grid.y <= 65535, "lga: image too tall");
-        lga_r2_kernel<<<grid, 128, 0, as_stream(stream)>>>(x, guidance, out, D, H, W);
-        return check_launch("lga_r2_kernel");
+        lga_r2_tiled_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, guidance, out, D, H, W);
+        return check_launch("lga_r2_tiled_kernel");
     }
     dim3 grid((unsigned)cdiv((size_t)H * W, 256), B);
     lga_generic_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, guidance, out, D, H, W, radius);

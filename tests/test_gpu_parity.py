@@ -356,7 +356,7 @@ def test_spn_forward_backward_vs_oracle(P, shape):
                 torch.testing.assert_close(got.cpu(), w, atol=1e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 6, 5, 7), (2, 3, 16, 9, 12), (1, 2, 70, 6, 10)])
+@pytest.mark.parametrize("shape", [(1, 2, 6, 5, 7), (2, 3, 16, 9, 12), (1, 2, 70, 6, 10), (1, 1, 64, 19, 45), (1, 1, 300, 4, 6)])
 def test_sga_vs_oracle(P, shape):
     from densematchingbenchmark_b200.ops import SGA
     B, C, D, H, W = shape
