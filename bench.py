@@ -54,6 +54,21 @@ def trunk_macs(B=1, d=D4, h=H4, w=W4):
     return B * macs
 
 
+def max_over_ranks(values, device, world):
+    """Element-wise MAX of a list of floats over all ranks (every multi-GPU time is the max over ranks)."""
+    if world <= 1:
+        return [float(v) for v in values]
+    import torch.distributed as dist
+    t = torch.tensor([float(v) for v in values], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t]
+
+
+def aggregate_throughput(pairs_per_rank, world, ms_per_step):
+    """Whole-job pairs/s: every rank processes `pairs_per_rank` independent pairs per step (weak scaling)."""
+    return pairs_per_rank * world / (ms_per_step * 1e-3)
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -381,10 +396,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
 
-    if world > 1:
-        t = torch.tensor([ms, e2e_ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms = max_over_ranks([ms, e2e_ms], device, world)
     if rank != 0:
         return
 
@@ -399,7 +411,10 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "tensor", "kernel": "PSMAggregator trunk (89 tcgen05 conv launches), timed as one span with CUDA events in the eager pass",
                 "achieved": achieved_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tflops / pk["tflops_sustained"], "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
-                "algorithmic_flops_per_step": 2.0 * macs, "mma_passes": passes, "traffic": None}
+                "algorithmic_flops_per_step": 2.0 * macs, "mma_passes": passes,
+                # dram__bytes_read+write of ONE launch of the dominant kernel (32->32 layer at 48x136x240, ncu --set
+                # full, profiles/r1_ncu_full_conv3d_tc_kwmerge_n4_32to32_fp16x3.txt) against 401 MB algorithmic
+                "traffic": 376.4e6, "traffic_scope": "one launch of conv3d_tc_kernel<3> (32->32 @ 48x136x240)"}
     roofline_cat = {"bound": "hbm", "kernel": "cat_volume (blocked 16-bit hi/lo)" if on_tc else "cat_volume (fp32 NCDHW)", "achieved": cat_bytes / (seg[1] * 1e-3) / 1e9,
                     "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": cat_bytes / (seg[1] * 1e-3) / 1e9 / pk["hbm_gbs"],
                     "algorithmic_bytes_per_step": cat_bytes, "traffic": None}
@@ -415,7 +430,7 @@ def run_ours(args, rank, world, local_rank):
 
     pairs = B * world
     line = {
-        "metric": "disparity maps/sec (PSMNet, 960x540, D=192)", "value": pairs / (ms * 1e-3), "unit": "pairs/s",
+        "metric": "disparity maps/sec (PSMNet, 960x540, D=192)", "value": aggregate_throughput(B, world, ms), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": (("%s (split 16-bit tensor-core MMAs hi*hi+hi*lo+lo*hi, fp32 accumulate)" % args.precision)

@@ -565,3 +565,56 @@ def test_acfnet_tc_engine_vs_reference_golden(P, golden_dir):
     disps = [pred(c).cpu() for c in proc(l.to(DEV), r.to(DEV))]
     for d, w in zip(disps, rec["disps"]):
         assert float((d - w).abs().max()) < 1e-3
+
+
+# ------------------------------------------------------------------------------- BASELINE config sizes
+def test_config2_full_size_psm_hot_path(P):
+    """BASELINE config 2 at FULL size (features [1,32,136,240], D=192 -> 3x [1,1,544,960]) on the
+    tensor-core engine against the float32 CPU oracle.  Per-pixel agreement is bounded by the float32
+    noise floor measured at medium size (see test_medium_size...); the mean deviation and the EPE
+    difference must be far below 1e-3 px."""
+    _tc_or_skip()
+    cfg = _cfg(P, "PSMNet", feat_disp=48, max_disp=192)
+    proc = P.build_cost_processor(cfg)
+    pred = P.build_disp_predictor(cfg)
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=0, sharpen=1.0)
+    proc.aggregator.load_state_dict(sd)
+    proc = proc.to(DEV).eval(); pred = pred.to(DEV).eval()
+    l, r = seeded.feature_pair(1, 32, 136, 240, seed=5, scale=0.5, shift=6)
+    disps = [pred(c).cpu() for c in proc(l.to(DEV), r.to(DEV))]
+    assert all(tuple(d.shape) == (1, 1, 544, 960) for d in disps)
+    torch.set_num_threads(min(32, max(1, os.cpu_count() or 1)))
+    _, want = O.psm_hot_path(sd, l, r, 192, prefix="")
+    for got, w in zip(disps, want):
+        diff = (got - w).abs()
+        print("config 2 full size: max |d_disp| %.2e mean %.2e" % (float(diff.max()), float(diff.mean())))
+        assert float(diff.max()) < 5e-3 and float(diff.mean()) < 1e-4
+        gt = w + 1.0
+        assert abs(O.epe(got, gt, 0, 1e9) - 1.0) < 1e-3
+
+
+def test_config3_gwc_full_size_properties(P):
+    """BASELINE config 3: 320-channel features, 40 groups, D4=48 at 136x240."""
+    l, r = seeded.feature_pair(1, 320, 136, 240, seed=9)
+    lg, rg = l.to(DEV), r.to(DEV)
+    vol = P.GWC_FUNCS["default"](lg, rg, max_disp=48, num_groups=40)
+    assert tuple(vol.shape) == (1, 40, 48, 136, 240)
+    for d in (0, 3, 47):
+        want = (lg[0, :, :, d:] * rg[0, :, :, :240 - d]).view(40, 8, 136, 240 - d).mean(1)
+        torch.testing.assert_close(vol[0, :, d, :, d:], want, atol=1e-5, rtol=1e-5)
+        assert float(vol[0, :, d, :, :d].abs().sum()) == 0.0
+    # linearity in the left features
+    vol2 = P.GWC_FUNCS["default"](2.0 * lg, rg, max_disp=48, num_groups=40)
+    torch.testing.assert_close(vol2, 2.0 * vol, atol=1e-5, rtol=1e-5)
+
+
+def test_config4_ganet_full_size_properties(P):
+    """BASELINE config 4 sizes (1248x384 padded from 1242x375): identity guidance reproduces the input."""
+    from densematchingbenchmark_b200.ops import SGA, LGA
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 8, 64, 128, 416, generator=g).to(DEV)          # 8 of the 32 channels (memory of the test box)
+    gd = torch.zeros(1, 4, 5, 8, 128, 416, device=DEV); gd[:, :, 0] = 1.7
+    torch.testing.assert_close(SGA()(x, gd.view(1, 160, 128, 416)), x)
+    c = torch.randn(1, 192, 384, 1248, generator=g).to(DEV)
+    gl = torch.zeros(1, 3, 5, 5, 384, 1248, device=DEV); gl[:, 0, 2, 2] = 0.3
+    torch.testing.assert_close(LGA(2)(c, gl.view(1, 75, 384, 1248)), c)
