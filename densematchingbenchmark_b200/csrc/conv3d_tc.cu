@@ -45,7 +45,7 @@ constexpr int TAPS = 27;
 __host__ __device__ constexpr int nthreads_of(int kind) { return kind == 2 ? 320 : 192; }
 // depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
 // work-item boundaries)
-__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 6 : 4; }
+__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 5 : 4; }
 constexpr int TMEM_COLS = 512;
 
 // KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane (reference kernel)
@@ -73,11 +73,14 @@ template <> struct Geo<2> {
 // epilogue adds the three partial results of neighbouring columns (warp shuffles).  6 of 8 columns
 // produce outputs, but the A tile is streamed from shared memory 3x less often -- the operand
 // bandwidth, not the tensor pipe, bounds these N<=64 MMAs (profiles/README.md).
+// Its M tile is 8 rows x 16 columns (two 8-voxel core-matrix groups per row, still a uniform 128-byte
+// group pitch because no w halo is stored): 14 of 16 columns carry outputs.
 template <> struct Geo<3> {
     static constexpr int CBK = 4;
-    static constexpr int PLANE_BYTES = 4 * 18 * 8 * 16;            // 9216
+    static constexpr int PLANE_BYTES = 4 * 10 * 16 * 16;           // 10240: (8+2) rows x 16 columns x 32 channels
 };
-constexpr int TWV = 6;                      // valid output columns per tile row in KIND 3
+constexpr int TH3 = 8, TW3 = 16;            // KIND 3 tile
+constexpr int TWV = 14;                     // valid output columns per tile row in KIND 3
 
 struct Maps {
     CUtensorMap m[8];   // KIND 0/2: [0]=hi [1]=lo;  KIND 1: [(ph*2+pw)*2 + (0 hi | 1 lo)]
@@ -225,7 +228,7 @@ struct Smem {
 struct Item {
     int b, d0, d1, h0, w0;
 };
-template <int TWSTEP>
+template <int THSTEP, int TWSTEP>
 __device__ __forceinline__ Item decode_item(const Params& p, int item) {
     const int per_b = p.tiles_w * p.tiles_h * p.nseg;
     Item it;
@@ -236,7 +239,7 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
     const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
     it.d0 = seg * p.seg_len;
     it.d1 = min(p.Dm, it.d0 + p.seg_len);
-    it.h0 = th * TH;
+    it.h0 = th * THSTEP;
     it.w0 = tw * TWSTEP;
     return it;
 }
@@ -347,7 +350,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                          S::TAP_BYTES, wbar);
             uint32_t n = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<(KIND == 3 ? TWV : TW)>(p, item);
+                const Item it = decode_item<(KIND == 3 ? TH3 : TH), (KIND == 3 ? TWV : TW)>(p, item);
                 const int nout = it.d1 - it.d0;
                 const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : (KIND == 1 ? 2 * nout + 1 : nout + 1);
                 const int pl0 = (KIND == 0 || KIND == 3) ? it.d0 - 1 : (KIND == 1 ? 2 * it.d0 - 1 : it.d0);
@@ -406,7 +409,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             };
             uint32_t n_base = 0, t_base = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<(KIND == 3 ? TWV : TW)>(p, item);
+                const Item it = decode_item<(KIND == 3 ? TH3 : TH), (KIND == 3 ? TWV : TW)>(p, item);
                 const int nout = it.d1 - it.d0;
                 if (KIND == 0) {
                     constexpr uint32_t LBO_A = 18 * 10 * 16, SBO_A = 10 * 16;
@@ -461,7 +464,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     n_base += nout + 2;
                     t_base += nout;
                 } else if (KIND == 3) {
-                    constexpr uint32_t LBO_A = 18 * 8 * 16, SBO_A = 8 * 16;
+                    constexpr uint32_t LBO_A = 10 * 16 * 16, SBO_A = 8 * 16;   // 10 rows of 256 bytes per channel block
                     constexpr uint32_t idesc_hi3 = make_idesc(3 * NB, FP16 ? 0u : 1u);     // A_lo x [Whi kw0..2]
                     constexpr uint32_t a_hiw = desc_hi(SBO_A);
                     int waited = 0;
@@ -486,7 +489,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                                 for (int kk = 0; kk < CBK / 2; ++kk) {
                                     const bool first = (kd == 0 && kh == 0 && kk == 0);
                                     const uint64_t db = desc_of(b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
-                                    const uint32_t a_off = kh * SBO_A + 2 * kk * LBO_A;
+                                    const uint32_t a_off = kh * (TW3 * 16) + 2 * kk * LBO_A;
                                     tcgen05_mma_bf16(acc, desc_of(a_lo0 + (a_off >> 4), a_hiw), db, idesc_main, first ? 0u : 1u);
                                     if (SPLIT)   // lo*Whi of the three kw lands on the (small) hi*Wlo columns
                                         tcgen05_mma_bf16(acc + 3 * NB, desc_of(a_lo0 + ((S::PLANE_BYTES + a_off) >> 4), a_hiw), db,
@@ -630,13 +633,13 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         // ================================ epilogue =====================================
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
-        const int hl = m >> 3, wl = m & 7;
+        const int hl = KIND == 3 ? (m >> 4) : (m >> 3), wl = KIND == 3 ? (m & 15) : (m & 7);
         float bias[NB];
 #pragma unroll
         for (int c = 0; c < NB; ++c) bias[c] = (p.bias && c < p.n_valid_out) ? __ldg(p.bias + c) : 0.f;
         uint32_t t = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const Item it = decode_item<(KIND == 3 ? TWV : TW)>(p, item);
+            const Item it = decode_item<(KIND == 3 ? TH3 : TH), (KIND == 3 ? TWV : TW)>(p, item);
             const int h = it.h0 + hl, w = KIND == 3 ? it.w0 - 1 + wl : it.w0 + wl;
             const bool valid = KIND == 3 ? (h < p.Hm && wl >= 1 && wl <= TWV && w < p.Wm) : (h < p.Hm && w < p.Wm);
             for (int d = it.d0; d < it.d1; ++d) {
@@ -940,7 +943,7 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     p.Wo = same ? W : (kind == 1 ? W / 2 : 2 * W);
     p.n_valid_out = scalar_out ? 1 : 32;
     p.acc_scale = 1.0f / w_scale;
-    p.tiles_h = (int)cdiv(p.Hm, TH);
+    p.tiles_h = (int)cdiv(p.Hm, kind == 3 ? TH3 : TH);
     p.tiles_w = (int)cdiv(p.Wm, kind == 3 ? TWV : TW);
     // depth segments: ~4 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
     // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
@@ -970,7 +973,7 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                 if (rc) return rc;
             }
         } else {
-            const int bh = kind == 2 ? 17 : 18, bw = kind == 0 ? 10 : (kind == 3 ? 8 : 9);
+            const int bh = kind == 2 ? 17 : (kind == 3 ? TH3 + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? TW3 : 9);
             rc = make_dense_map(&maps.m[0], xh, B, CBS, D, H, W, bh, bw, cbk, fp16);
             if (rc) return rc;
             rc = make_dense_map(&maps.m[1], xl, B, CBS, D, H, W, bh, bw, cbk, fp16);
