@@ -30,6 +30,7 @@
 // Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (warp 1 also
 // owns the TMEM allocation), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -945,10 +946,16 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     p.acc_scale = 1.0f / w_scale;
     p.tiles_h = (int)cdiv(p.Hm, kind == 3 ? TH3 : TH);
     p.tiles_w = (int)cdiv(p.Wm, kind == 3 ? TWV : TW);
-    // depth segments: ~4 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
+    // depth segments: ~8 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
     // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
     const int cols = p.tiles_h * p.tiles_w * p.B;
-    int nseg = (int)cdiv((int64_t)sm_count() * 4, cols);
+    static int items_per_sm = 0;      // tuning knob (DMB_B200_TC_ITEMS_PER_SM); 8 measured best (2: 5.37 ms, 4: 4.83, 8: 4.60, 12: 4.58)
+    if (items_per_sm == 0) {
+        const char* e = getenv("DMB_B200_TC_ITEMS_PER_SM");
+        items_per_sm = e ? atoi(e) : 8;
+        if (items_per_sm < 1 || items_per_sm > 64) items_per_sm = 8;
+    }
+    int nseg = (int)cdiv((int64_t)sm_count() * items_per_sm, cols);
     if (nseg > p.Dm / 2) nseg = p.Dm / 2;
     if (nseg < 1) nseg = 1;
     p.seg_len = (int)cdiv(p.Dm, nseg);
