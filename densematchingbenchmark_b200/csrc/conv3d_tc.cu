@@ -46,7 +46,7 @@ constexpr int TAPS = 27;
 __host__ __device__ constexpr int nthreads_of(int kind) { return kind == 2 ? 320 : 192; }
 // depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
 // work-item boundaries)
-__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 5 : 4; }
+__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 5 : (kind == 4 ? 3 : 4); }
 constexpr int TMEM_COLS = 512;
 
 // KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane (reference kernel)
@@ -80,7 +80,18 @@ template <> struct Geo<3> {
     static constexpr int CBK = 4;
     static constexpr int PLANE_BYTES = 4 * 10 * 16 * 16;           // 10240: (8+2) rows x 16 columns x 32 channels
 };
-constexpr int TH3 = 8, TW3 = 16;            // KIND 3 tile
+// KIND 4: stride-2 conv on the kw-merged scheme.  The depth and height strides are taken by the loads
+// (plane index 2*od+kd-1; two row-parity boxes per plane through tensor maps with a doubled row pitch --
+// full 256-byte rows, unlike KIND 1's 16-byte gathers); along W every input column is computed and the
+// epilogue keeps the even centres.  The MMA work doubles, but these layers are small and the 16-byte TMA
+// elements of KIND 1 were the bottleneck (measured: 55 us per pass against a 15 us HBM floor).
+template <> struct Geo<4> {
+    static constexpr int CBK = 4;
+    static constexpr int EVEN_BYTES = 4 * 8 * 16 * 16;             // 8192: rows 2*oh
+    static constexpr int ODD_BYTES = 4 * 9 * 16 * 16;              // 9216: rows 2*oh-1 .. 2*oh+15
+    static constexpr int PLANE_BYTES = EVEN_BYTES + ODD_BYTES;     // 17408
+};
+constexpr int TH3 = 8, TW3 = 16;            // KIND 3 / 4 tile
 constexpr int TWV = 14;                     // valid output columns per tile row in KIND 3
 
 struct Maps {
@@ -201,7 +212,7 @@ template <int KIND, bool SPLIT>
 struct Smem {
     using G = Geo<KIND>;
     static constexpr int CBK = G::CBK;
-    static constexpr int NKW = KIND == 3 ? 3 : 1;                  // kw taps merged into one B block
+    static constexpr int NKW = (KIND == 3 || KIND == 4) ? 3 : 1;   // kw taps merged into one B block
     static constexpr int ROWS = (SPLIT ? 2 * NB : NB) * NKW;       // B-operand rows per channel block
     static constexpr int TAP_BYTES = CBK * ROWS * 16;              // one B block (a tap, or a (kd,kh) tap row)
     static constexpr int W_BYTES = (TAPS / NKW) * TAP_BYTES;
@@ -221,7 +232,8 @@ struct Smem {
     static constexpr int LH_COL = 3 * KD_COLS;                     // lo*Whi (split only)
     // KIND 2: one accumulator per output parity class (chains are <= 32 MMAs by construction)
     static constexpr int CLS_COLS = SPLIT ? 64 : 32;
-    static constexpr int ACC_COLS = KIND == 2 ? 4 * CLS_COLS : (KIND == 3 ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32));
+    static constexpr int ACC_COLS =
+        KIND == 2 ? 4 * CLS_COLS : ((KIND == 3 || KIND == 4) ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32));
     static_assert(2 * ACC_COLS <= TMEM_COLS, "accumulators exceed TMEM");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -350,11 +362,12 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 bulk_g2s(w_smem + t * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
                          S::TAP_BYTES, wbar);
             uint32_t n = 0;
+            const int in_cb0_k4 = p.in_cb0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<(KIND == 3 ? TH3 : TH), (KIND == 3 ? TWV : TW)>(p, item);
+                const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
                 const int nout = it.d1 - it.d0;
-                const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : (KIND == 1 ? 2 * nout + 1 : nout + 1);
-                const int pl0 = (KIND == 0 || KIND == 3) ? it.d0 - 1 : (KIND == 1 ? 2 * it.d0 - 1 : it.d0);
+                const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : ((KIND == 1 || KIND == 4) ? 2 * nout + 1 : nout + 1);
+                const int pl0 = (KIND == 0 || KIND == 3) ? it.d0 - 1 : ((KIND == 1 || KIND == 4) ? 2 * it.d0 - 1 : it.d0);
                 for (int j = 0; j < nplanes; ++j, ++n) {
                     const int pl = pl0 + j;
                     const uint32_t slot = n % NSTAGE;
@@ -372,6 +385,16 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                         if (SPLIT)
                             tma_load_5d(dst + S::PLANE_BYTES, &maps.m[1], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl,
                                         p.in_cb0, it.b);
+                    } else if (KIND == 4) {
+                        // m[0]/m[1]: even input rows (hi/lo), m[2]/m[3]: odd input rows; row index = ih >> 1
+                        mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * S::PLANE_BYTES);
+                        tma_load_5d(dst, &maps.m[0], &full[slot], 8 * (it.w0 - 1), it.h0, pl, in_cb0_k4, it.b);
+                        tma_load_5d(dst + Geo<4>::EVEN_BYTES, &maps.m[2], &full[slot], 8 * (it.w0 - 1), it.h0 - 1, pl, in_cb0_k4, it.b);
+                        if (SPLIT) {
+                            tma_load_5d(dst + S::PLANE_BYTES, &maps.m[1], &full[slot], 8 * (it.w0 - 1), it.h0, pl, in_cb0_k4, it.b);
+                            tma_load_5d(dst + S::PLANE_BYTES + Geo<4>::EVEN_BYTES, &maps.m[3], &full[slot], 8 * (it.w0 - 1),
+                                        it.h0 - 1, pl, in_cb0_k4, it.b);
+                        }
                     } else if (KIND == 2) {
                         mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 17 * 9 * 16);
                         tma_load_5d(dst, &maps.m[0], &full[slot], 8 * it.w0, it.h0, pl, p.in_cb0, it.b);
@@ -410,7 +433,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             };
             uint32_t n_base = 0, t_base = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<(KIND == 3 ? TH3 : TH), (KIND == 3 ? TWV : TW)>(p, item);
+                const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
                 const int nout = it.d1 - it.d0;
                 if (KIND == 0) {
                     constexpr uint32_t LBO_A = 18 * 10 * 16, SBO_A = 10 * 16;
@@ -506,6 +529,56 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                         }
                     }
                     n_base += nout + 2;
+                    t_base += nout;
+                } else if (KIND == 4) {
+                    // plane-driven like KIND 1, one accumulator (all kd) per output like KIND 3
+                    constexpr uint32_t idesc_hi3 = make_idesc(3 * NB, FP16 ? 0u : 1u);
+                    constexpr uint32_t a_hiw = desc_hi(8 * 16);
+                    constexpr uint32_t LBO_E = 8 * 256, LBO_O = 9 * 256;
+                    const int nplanes = 2 * nout + 1;
+                    auto issue_kd = [&](uint32_t a_stage, uint32_t t, int kd) {
+                        const uint32_t acc = tmem_base + (t & 1) * S::ACC_COLS;
+                        const uint32_t e_lo0 = desc_lo(a_stage, LBO_E);
+                        const uint32_t o_lo0 = desc_lo(a_stage + Geo<4>::EVEN_BYTES, LBO_O);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                            for (int kk = 0; kk < CBK / 2; ++kk) {
+                                const bool first = (kd == 0 && kh == 0 && kk == 0);
+                                const uint64_t db = desc_of(b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
+                                // kh=1: even rows, local row = oh; kh=0: odd rows, row oh; kh=2: odd rows, row oh+1
+                                const uint32_t lo = kh == 1 ? e_lo0 + ((2 * kk * LBO_E) >> 4)
+                                                            : o_lo0 + (((kh == 2 ? 256u : 0u) + 2 * kk * LBO_O) >> 4);
+                                tcgen05_mma_bf16(acc, desc_of(lo, a_hiw), db, idesc_main, first ? 0u : 1u);
+                                if (SPLIT)
+                                    tcgen05_mma_bf16(acc + 3 * NB, desc_of(lo + (S::PLANE_BYTES >> 4), a_hiw), db, idesc_hi3, 1u);
+                            }
+                        }
+                    };
+                    for (int j = 0; j < nplanes; ++j) {
+                        const uint32_t n = n_base + j;
+                        const uint32_t slot = n % NSTAGE;
+                        mbar_wait(&full[slot], (n / NSTAGE) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t a_stage = planes_addr + slot * S::STAGE_BYTES;
+                        if (j & 1) {
+                            issue_kd(a_stage, t_base + ((j - 1) >> 1), 1);
+                        } else {
+                            if (j >= 2) {
+                                const uint32_t t = t_base + (j >> 1) - 1;
+                                issue_kd(a_stage, t, 2);
+                                tcgen05_commit(&tfull[t & 1]);
+                            }
+                            if ((j >> 1) < nout) {
+                                const uint32_t t = t_base + (j >> 1);
+                                mbar_wait(&tempty[t & 1], ((t >> 1) & 1) ^ 1);
+                                tcgen05_fence_after();
+                                issue_kd(a_stage, t, 0);
+                            }
+                        }
+                        tcgen05_commit(&empty[slot]);
+                    }
+                    n_base += nplanes;
                     t_base += nout;
                 } else if (KIND == 1) {
                     // plane-driven: input plane 2*od-1+kd feeds chain kd of output od
@@ -634,17 +707,22 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         // ================================ epilogue =====================================
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
-        const int hl = KIND == 3 ? (m >> 4) : (m >> 3), wl = KIND == 3 ? (m & 15) : (m & 7);
+        const int hl = (KIND == 3 || KIND == 4) ? (m >> 4) : (m >> 3), wl = (KIND == 3 || KIND == 4) ? (m & 15) : (m & 7);
         float bias[NB];
 #pragma unroll
         for (int c = 0; c < NB; ++c) bias[c] = (p.bias && c < p.n_valid_out) ? __ldg(p.bias + c) : 0.f;
         uint32_t t = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const Item it = decode_item<(KIND == 3 ? TH3 : TH), (KIND == 3 ? TWV : TW)>(p, item);
-            const int h = it.h0 + hl, w = KIND == 3 ? it.w0 - 1 + wl : it.w0 + wl;
-            const bool valid = KIND == 3 ? (h < p.Hm && wl >= 1 && wl <= TWV && w < p.Wm) : (h < p.Hm && w < p.Wm);
+            const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
+            const int h = it.h0 + hl;
+            // KIND 3/4: tile columns are input columns w0-1 .. w0+14; KIND 4 keeps the even centres (ow = w/2)
+            const int win = it.w0 - 1 + wl;
+            const int w = KIND == 3 ? win : (KIND == 4 ? (win >> 1) : it.w0 + wl);
+            const bool valid = KIND == 3 ? (h < p.Hm && wl >= 1 && wl <= TWV && w < p.Wm)
+                             : KIND == 4 ? (h < p.Hm && wl >= 1 && wl <= TWV && (win & 1) == 0 && win < p.Wm)
+                                         : (h < p.Hm && w < p.Wm);
             for (int d = it.d0; d < it.d1; ++d) {
-                if (KIND == 3) {
+                if (KIND == 3 || KIND == 4) {
                     const uint32_t buf = t & 1;
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
                     tcgen05_fence_after();
@@ -880,7 +958,18 @@ static int launch_kind(const Maps& maps, const Params& p, int grid, bool split, 
 }
 
 static int cbk_of(int kind) { return kind == 1 ? Geo<1>::CBK : 4; }
-static int nkw_of(int kind) { return kind == 3 ? 3 : 1; }
+static int nkw_of(int kind) { return (kind == 3 || kind == 4) ? 3 : 1; }
+
+// row-parity map (ph) over the whole batch: dims (w*8, H/2, D, cb, b); row h2 of parity ph is input row 2*h2+ph
+static int make_rowparity_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W, int ph, int rows,
+                              int fp16) {
+    const unsigned char* b0 = reinterpret_cast<const unsigned char*>(base) + (size_t)ph * W * 16;
+    const cuuint64_t dims[5] = {(cuuint64_t)W * 8, (cuuint64_t)H / 2, (cuuint64_t)D, (cuuint64_t)CBS, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {(cuuint64_t)2 * W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
+                                   (cuuint64_t)CBS * D * H * W * 16};
+    const cuuint32_t box[5] = {(cuuint32_t)TW3 * 8, (cuuint32_t)rows, 1, 4, 1};
+    return encode(map, b0, dims, strides, box, fp16);
+}
 
 }  // namespace tc
 }  // namespace dmb
@@ -891,7 +980,7 @@ using namespace dmb::tc;
 extern "C" int dmb_b200_conv3d_tc_available(void) { return device_ok(); }
 
 extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split, int kind) {
-    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 3) return 0;
+    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 4) return 0;
     const int cbk = cbk_of(kind);
     const int64_t blob = (int64_t)TAPS * cbk * (split ? 64 : 32) * 16;
     return blob * (Cin / (8 * cbk)) * ((Cout + 31) / 32);
@@ -900,7 +989,7 @@ extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split,
 extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split,
                                                int fp16, float scale, int kind, void* stream) {
     DMB_REQUIRE(w_packed && w_blob, "conv3d_tc_pack_weights: null pointer");
-    DMB_REQUIRE(kind >= 0 && kind <= 3, "conv3d_tc_pack_weights: kind must be 0..3");
+    DMB_REQUIRE(kind >= 0 && kind <= 4, "conv3d_tc_pack_weights: kind must be 0..4");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc_pack_weights: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(Cout > 0 && (Cout % 32 == 0 || Cout < 32), "conv3d_tc_pack_weights: Cout=%d must be <32 or a multiple of 32", Cout);
     DMB_REQUIRE(scale > 0.f, "conv3d_tc_pack_weights: scale must be positive");
@@ -916,7 +1005,7 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                                   int relu, int fp16, void* stream) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
-    DMB_REQUIRE(kind >= 0 && kind <= 3, "conv3d_tc: kind must be 0/3 (stride 1), 1 (stride 2) or 2 (transposed stride 2)");
+    DMB_REQUIRE(kind >= 0 && kind <= 4, "conv3d_tc: kind must be 0/3 (stride 1), 1/4 (stride 2) or 2 (transposed stride 2)");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(w_scale > 0.f, "conv3d_tc: w_scale must be positive");
     const bool scalar_out = (Cout == 1);
@@ -926,7 +1015,8 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     else
         DMB_REQUIRE(y_hi && !y_f32 && !res_f32, "conv3d_tc: Cout>=32 writes the blocked 16-bit output");
     DMB_REQUIRE(!res_lo || res_hi, "conv3d_tc: res_lo without res_hi");
-    if (kind == 1) DMB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "conv3d_tc: stride-2 needs even input extents");
+    if (kind == 1 || kind == 4)
+        DMB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "conv3d_tc: stride-2 needs even input extents");
     if (!device_ok()) return fail(DMB_ERR_UNSUPPORTED, "conv3d_tc: needs an sm_100 device and a TMA-capable driver");
     const bool split = x_lo != nullptr;
     DMB_REQUIRE(scalar_out || split == (y_lo != nullptr), "conv3d_tc: x_lo and y_lo must both be given or both be NULL");
@@ -937,15 +1027,17 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
 
     Params p;
     p.B = (kind == 1) ? 1 : B;
-    p.Dm = kind == 1 ? D / 2 : D; p.Hm = kind == 1 ? H / 2 : H; p.Wm = kind == 1 ? W / 2 : W;
+    const bool s2 = (kind == 1 || kind == 4);
+    // KIND 4 tiles W in INPUT columns (every column is computed, even centres are kept)
+    p.Dm = s2 ? D / 2 : D; p.Hm = s2 ? H / 2 : H; p.Wm = kind == 1 ? W / 2 : W;
     const bool same = (kind == 0 || kind == 3);
-    p.Do = same ? D : (kind == 1 ? D / 2 : 2 * D);
-    p.Ho = same ? H : (kind == 1 ? H / 2 : 2 * H);
-    p.Wo = same ? W : (kind == 1 ? W / 2 : 2 * W);
+    p.Do = same ? D : (s2 ? D / 2 : 2 * D);
+    p.Ho = same ? H : (s2 ? H / 2 : 2 * H);
+    p.Wo = same ? W : (s2 ? W / 2 : 2 * W);
     p.n_valid_out = scalar_out ? 1 : 32;
     p.acc_scale = 1.0f / w_scale;
-    p.tiles_h = (int)cdiv(p.Hm, kind == 3 ? TH3 : TH);
-    p.tiles_w = (int)cdiv(p.Wm, kind == 3 ? TWV : TW);
+    p.tiles_h = (int)cdiv(p.Hm, (kind == 3 || kind == 4) ? TH3 : TH);
+    p.tiles_w = (int)cdiv(p.Wm, (kind == 3 || kind == 4) ? TWV : TW);
     // depth segments: ~8 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
     // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
     const int cols = p.tiles_h * p.tiles_w * p.B;
@@ -979,6 +1071,16 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                 rc = make_parity_map(&maps.m[sub * 2 + 1], xl, CBS, D, H, W, sub >> 1, sub & 1, cbk, fp16);
                 if (rc) return rc;
             }
+        } else if (kind == 4) {
+            rc = make_rowparity_map(&maps.m[0], xh, B, CBS, D, H, W, 0, 8, fp16);
+            if (rc) return rc;
+            rc = make_rowparity_map(&maps.m[1], xl, B, CBS, D, H, W, 0, 8, fp16);
+            if (rc) return rc;
+            rc = make_rowparity_map(&maps.m[2], xh, B, CBS, D, H, W, 1, 9, fp16);
+            if (rc) return rc;
+            rc = make_rowparity_map(&maps.m[3], xl, B, CBS, D, H, W, 1, 9, fp16);
+            if (rc) return rc;
+            for (int i = 4; i < 8; ++i) maps.m[i] = maps.m[0];
         } else {
             const int bh = kind == 2 ? 17 : (kind == 3 ? TH3 + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? TW3 : 9);
             rc = make_dense_map(&maps.m[0], xh, B, CBS, D, H, W, bh, bw, cbk, fp16);
@@ -1016,7 +1118,8 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                 if (kind == 0) rc = launch_kind<0>(maps, p, grid, split, fp16, stream);
                 else if (kind == 1) rc = launch_kind<1>(maps, p, grid, split, fp16, stream);
                 else if (kind == 2) rc = launch_kind<2>(maps, p, grid, split, fp16, stream);
-                else rc = launch_kind<3>(maps, p, grid, split, fp16, stream);
+                else if (kind == 3) rc = launch_kind<3>(maps, p, grid, split, fp16, stream);
+                else rc = launch_kind<4>(maps, p, grid, split, fp16, stream);
                 if (rc) return rc;
             }
         }

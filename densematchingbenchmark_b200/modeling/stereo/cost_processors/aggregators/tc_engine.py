@@ -18,8 +18,8 @@ from .....ops import functional as F_
 from ...layers.basic_layers import FusedConvUnit
 
 
-# stride-1 layers: kind 3 (kw taps merged into the MMA N dimension, the fast kernel) or kind 0 (one
-# MMA per tap; kept as the simpler reference implementation, DMB_B200_TC_KW_MERGE=0 selects it)
+# stride-1 / stride-2 layers: kinds 3 / 4 (kw taps merged into the MMA N dimension, the fast kernels) or
+# kinds 0 / 1 (one MMA per tap; kept as the simpler reference implementations, DMB_B200_TC_KW_MERGE=0)
 KW_MERGE = os.environ.get("DMB_B200_TC_KW_MERGE", "1") != "0"
 
 PRECISIONS = {          # name -> (split, fp16)
@@ -99,7 +99,7 @@ def _kind_of(layer):
     if tuple(conv.stride) == (1, 1, 1):
         return 3 if KW_MERGE else 0
     if tuple(conv.stride) == (2, 2, 2):
-        return 1
+        return 4 if KW_MERGE else 1
     raise NotImplementedError("stride %s is not supported on tcgen05" % (tuple(conv.stride),))
 
 
@@ -145,9 +145,9 @@ def conv_tc(layer, x, residual=None, relu=False, res_f32=None):
     if Cin != x.C:
         raise ValueError("layer expects %d input channels, activation has %d" % (Cin, x.C))
     D, H, W = x.dims
-    if kind == 1 and (D % 2 or H % 2 or W % 2):
+    if kind in (1, 4) and (D % 2 or H % 2 or W % 2):
         raise ValueError("stride-2 convolution on tcgen05 needs even extents, got %s" % (x.dims,))
-    odims = x.dims if kind in (0, 3) else (tuple(n // 2 for n in x.dims) if kind == 1 else tuple(2 * n for n in x.dims))
+    odims = x.dims if kind in (0, 3) else (tuple(n // 2 for n in x.dims) if kind in (1, 4) else tuple(2 * n for n in x.dims))
     dev = x.hi.device
     fp16 = 1 if x.fp16 else 0
     if Cout == 1:

@@ -157,6 +157,7 @@ int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out
  *   kind 3: stride 1, pad 1, the three kw taps merged into the MMA N dimension (same result,
  *           3x fewer A-operand reads; the production kernel for stride-1 layers)
  *   kind 1: stride 2, pad 1 (even input extents)  (Hourglass conv1/conv3, utils/hourglass.py:35-48)
+ *   kind 4: the same convolution on the kw-merged scheme (row-parity TMA boxes; production kernel)
  *   kind 2: transposed, stride 2, pad 1, output_padding 1 (Hourglass conv5/conv6, :53-60)
  * x_hi/x_lo: [B][Cin/8][D][H][W][8] (x_lo NULL => single plane, else the (hi,lo) split pair);
  * B,D,H,W are the INPUT extents; the output grid is the same / halved / doubled.

@@ -477,10 +477,12 @@ TC_STRIDED_CASES = [
 ]
 
 
+@pytest.mark.parametrize("kw_merge", [True, False])
 @pytest.mark.parametrize("precision", ["fp16x3", "bf16"])
 @pytest.mark.parametrize("case", TC_STRIDED_CASES)
-def test_conv3d_tc_strided_vs_torch_cpu(P, case, precision):
+def test_conv3d_tc_strided_vs_torch_cpu(P, case, precision, kw_merge, monkeypatch):
     tc = _tc_or_skip()
+    monkeypatch.setattr(tc, "KW_MERGE", kw_merge)
     split, fp16 = tc.PRECISIONS[precision]
     dt = torch.float16 if fp16 else torch.bfloat16
     kind, cin, cout, dims, bias, residual, relu = case
