@@ -474,7 +474,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=2,
+                    help="stereo pairs per GPU per step (2 measured +11%% pairs/s over 1; 4: +14%%)")
     ap.add_argument("--engine", default="auto", choices=["auto", "tc", "direct"])
     ap.add_argument("--precision", default="fp16x3", choices=["fp16x3", "bf16x3", "fp16", "bf16"])
     ap.add_argument("--backbone-dtype", default="bf16", choices=["bf16", "fp32"],

@@ -397,68 +397,7 @@ __global__ void __launch_bounds__(128) sga_horizontal_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------
-// LGA, radius 2 (5x5 window, 75 weights per pixel held in registers).  One thread per pixel,
-// marching over d with the three d-planes of the 5x5 neighbourhood kept in registers, so each
-// step loads 25 new values and issues 75 FMAs.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) lga_r2_kernel(const float* __restrict__ x, const float* __restrict__ guid,
-                                                     float* __restrict__ out, int D, int H, int W) {
-    const int px = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int py = blockIdx.y * 4 + (threadIdx.x >> 5);
-    const int b = blockIdx.z;
-    if (px >= W || py >= H) return;
-    const size_t plane = (size_t)H * W;
-    const float* gb = guid + (size_t)b * 75 * plane + (size_t)py * W + px;
-    float w[75];
-    float nrm = 0.f;
-#pragma unroll
-    for (int i = 0; i < 75; ++i) {
-        w[i] = __ldg(gb + (size_t)i * plane);
-        nrm += fabsf(w[i]);
-    }
-    nrm = fmaxf(nrm, 1e-12f);
-#pragma unroll
-    for (int i = 0; i < 75; ++i) w[i] = w[i] / nrm;
-
-    int noff[25];
-    bool nv[25];
-#pragma unroll
-    for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-            const int yy = py + ky - 2, xx = px + kx - 2;
-            nv[ky * 5 + kx] = yy >= 0 && yy < H && xx >= 0 && xx < W;
-            noff[ky * 5 + kx] = nv[ky * 5 + kx] ? yy * W + xx : 0;
-        }
-    const float* xb = x + (size_t)b * D * plane;
-    float* ob = out + (size_t)b * D * plane + (size_t)py * W + px;
-    float vm[25], v0[25], vp[25];   // planes d-1, d, d+1
-#pragma unroll
-    for (int i = 0; i < 25; ++i) {
-        vm[i] = 0.f;
-        v0[i] = nv[i] ? __ldg(xb + noff[i]) : 0.f;
-    }
-    for (int d = 0; d < D; ++d) {
-        const bool has_next = d + 1 < D;
-        const float* xn = xb + (size_t)(has_next ? d + 1 : d) * plane;
-#pragma unroll
-        for (int i = 0; i < 25; ++i) vp[i] = (has_next && nv[i]) ? __ldg(xn + noff[i]) : 0.f;
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 25; ++i) {
-            acc = fmaf(w[i], v0[i], acc);
-            acc = fmaf(w[25 + i], vm[i], acc);
-            acc = fmaf(w[50 + i], vp[i], acc);
-        }
-        st_cs_f(ob + (size_t)d * plane, acc);
-#pragma unroll
-        for (int i = 0; i < 25; ++i) {
-            vm[i] = v0[i];
-            v0[i] = vp[i];
-        }
-    }
-}
-
+// LGA, radius 2 (5x5 window, 75 L1-normalised weights per pixel held in registers).
 // Tiled variant: a 32x8 pixel tile per CTA; the NEW depth plane (d+1) of the tile + halo is staged in
 // shared memory once per step (double buffered, one barrier per step, the global loads of plane d+2
 // are in flight while plane d is computed); the planes d-1, d, d+1 of each thread's 5x5 neighbourhood

@@ -1,5 +1,6 @@
 // Raw cost-volume builders: concatenation, difference, group-wise correlation, warped
-// ("fast_mode") variants, and the channels-last bf16 volume feeding the tensor-core trunk.
+// ("fast_mode") variants, the concatenation volume written straight into the tensor-core trunk's
+// blocked 16-bit layout, and the layout converters at the trunk boundary.
 //
 // Reference behaviour restated by oracle/dmb_oracle.py (cat_volume, dif_volume, gwc_volume,
 // warp_volume); reference sources: dmb/modeling/stereo/cost_processors/utils/cat_fms.py:7-82,
