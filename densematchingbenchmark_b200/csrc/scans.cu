@@ -317,18 +317,32 @@ __global__ void __launch_bounds__(128) sga_horizontal_kernel(const float* __rest
         const int tile = rev ? ntiles - 1 - ti : ti;
         const int t0 = tile * TT;
         const int tx = t0 + tl;
-        for (int r = wy * (32 / tpl) + seg_in_warp; r < D * YT; r += rows_per_iter) {
-            const int yy = r % YT, d = r / YT;
-            const int y = y0 + yy;
-            float v = 0.f, o = -INFINITY;
-            if (y < H && tx < W) {
-                const size_t a = (size_t)d * plane + (size_t)y * W + tx;
-                v = __ldg(xb + a);
-                if (!first) o = ob[a];
+        // batches of 8 (d,row) segments per thread: all global loads of a batch are in flight together
+        for (int r0 = wy * (32 / tpl) + seg_in_warp; r0 < D * YT; r0 += 8 * rows_per_iter) {
+            float v[8], o[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u * rows_per_iter;
+                const int yy = r % YT, d = r / YT;
+                const int y = y0 + yy;
+                v[u] = 0.f;
+                o[u] = -INFINITY;
+                if (r < D * YT && y < H && tx < W) {
+                    const size_t a = (size_t)d * plane + (size_t)y * W + tx;
+                    v[u] = __ldg(xb + a);
+                    if (!first) o[u] = ob[a];
+                }
             }
-            const size_t si = ((size_t)yy * TT + tl) * Dp + d;
-            xt[si] = v;
-            ot[si] = o;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u * rows_per_iter;
+                if (r < D * YT) {
+                    const int yy = r % YT, d = r / YT;
+                    const size_t si = ((size_t)yy * TT + tl) * Dp + d;
+                    xt[si] = v[u];
+                    ot[si] = o[u];
+                }
+            }
         }
         for (int r = wy * (32 / tpl) + seg_in_warp; r < 5 * YT; r += rows_per_iter) {
             const int yy = r % YT, k = r / YT;
@@ -387,10 +401,21 @@ __global__ void __launch_bounds__(128) sga_horizontal_kernel(const float* __rest
             started = true;
         }
         __syncthreads();
-        for (int r = wy * (32 / tpl) + seg_in_warp; r < D * YT; r += rows_per_iter) {
-            const int yy = r % YT, d = r / YT;
-            const int y = y0 + yy;
-            if (y < H && tx < W) ob[(size_t)d * plane + (size_t)y * W + tx] = ot[((size_t)yy * TT + tl) * Dp + d];
+        for (int r0 = wy * (32 / tpl) + seg_in_warp; r0 < D * YT; r0 += 8 * rows_per_iter) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u * rows_per_iter;
+                const int yy = r % YT, d = r / YT;
+                v[u] = (r < D * YT) ? ot[((size_t)yy * TT + tl) * Dp + d] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u * rows_per_iter;
+                const int yy = r % YT, d = r / YT;
+                const int y = y0 + yy;
+                if (r < D * YT && y < H && tx < W) ob[(size_t)d * plane + (size_t)y * W + tx] = v[u];
+            }
         }
         __syncthreads();
     }
