@@ -68,8 +68,20 @@ class PSMNetBackbone(nn.Module):
         quarter = self.layer2(half)
         deep = self.layer4(self.layer3(quarter))
         size = deep.shape[2:]
-        pooled = [F.interpolate(getattr(self, "branch%d" % i)(deep), size, mode='bilinear', align_corners=True)
-                  for i in (4, 3, 2, 1)]
+        # SPP: the 8/16/32/64 average pools nest exactly (stride == window, floor mode), so each level is a
+        # 2x2 pool of the previous one instead of a fresh pass with a 64x64 window over the full map
+        # (reference: four independent nn.AvgPool2d, backbones/PSMNet.py:42-57; same windows, same values
+        # up to fp32 rounding)
+        pooled = []
+        level = None
+        for i, win in ((4, 8), (3, 16), (2, 32), (1, 64)):
+            branch = getattr(self, "branch%d" % i)
+            if tuple(branch[0].kernel_size) != (win, win):          # non-standard checkpoint: pool directly
+                level_i = branch[0](deep)
+            else:
+                level = F.avg_pool2d(deep, 8, 8) if level is None else F.avg_pool2d(level, 2, 2)
+                level_i = level
+            pooled.append(F.interpolate(branch[1](level_i), size, mode='bilinear', align_corners=True))
         return self.lastconv(torch.cat([quarter, deep] + pooled, 1))
 
     def forward(self, *input):
