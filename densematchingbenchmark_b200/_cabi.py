@@ -6,7 +6,7 @@ There is NO fallback: if `csrc/libdmb_b200.so` is missing or an entry point fail
 """
 import ctypes
 import os
-from ctypes import c_float, c_int, c_int64, c_void_p, c_char_p, POINTER
+from ctypes import c_double, c_float, c_int, c_int64, c_longlong, c_void_p, c_char_p, POINTER
 
 import torch
 
@@ -17,6 +17,8 @@ _P = c_void_p
 _I = c_int
 _F = c_float
 _IP = POINTER(c_int)
+_D = c_double
+_LL = c_longlong
 
 # name -> argtypes, exactly as declared in include/dmb_b200.h
 SIGNATURES = {
@@ -37,6 +39,16 @@ SIGNATURES = {
     "dmb_b200_conv3d_tc_pack_weights": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "dmb_b200_ncdhw_to_blocked": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_blocked_to_ncdhw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dmb_b200_bn_stats": [_P, _P, _I, _I, _LL, _P],
+    "dmb_b200_bn_finalize": [_P, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _I, _P],
+    "dmb_b200_bn_apply": [_P, _P, _P, _P, _P, _I, _I, _LL, _I, _P],
+    "dmb_b200_bn_backward_reduce": [_P, _P, _P, _P, _P, _P, _I, _I, _LL, _P],
+    "dmb_b200_bn_backward_apply": [_P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _I, _I, _LL, _P],
+    "dmb_b200_conv3d_wgrad": [_P, _P, _P, _I, _I, _I, _IP, _IP, _I, _I, _P],
+    "dmb_b200_upsample_deconv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dmb_b200_upsample_trilinear_backward": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dmb_b200_soft_argmin_backward": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _F, _F, _P, _P],
+    "dmb_b200_cat_volume_backward": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
 }
 # entry points that do not return a status code
 OTHER = {

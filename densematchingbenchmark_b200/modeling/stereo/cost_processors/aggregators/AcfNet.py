@@ -5,6 +5,7 @@ import torch.nn as nn
 from .PSMNet import PSMTrunk
 from .deferred import DeferredCost
 from .....ops import functional as F_
+from .....ops.autograd import UpsampleDeconvFn
 
 
 class AcfAggregator(PSMTrunk):
@@ -26,4 +27,6 @@ class AcfAggregator(PSMTrunk):
         pairs = ((cost3, self.deconv3), (cost2, self.deconv2), (cost1, self.deconv1))
         if self.defer_upsample and not self.training:
             return [DeferredCost(c[:, 0].contiguous(), size, "deconv", up.weight.detach()) for c, up in pairs]
+        if self.training:
+            return [UpsampleDeconvFn.apply(c, up.weight, size) for c, up in pairs]
         return [F_.upsample_regress(c, size, "deconv", up.weight.detach())[0] for c, up in pairs]

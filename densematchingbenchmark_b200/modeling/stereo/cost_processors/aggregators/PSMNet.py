@@ -6,6 +6,7 @@ from ...layers.basic_layers import conv3d_bn, conv3d_bn_relu, fused_plain_conv3d
 from ..utils.hourglass import Hourglass
 from .deferred import DeferredCost
 from .....ops import functional as F_
+from .....ops.autograd import UpsampleTrilinearFn
 
 
 class PSMTrunk(nn.Module):
@@ -69,7 +70,7 @@ class PSMTrunk(nn.Module):
         return tc_engine.cat_volume_blocked(ref_fms, tgt_fms, max_disp, start_disp, dilation, self.precision)
 
     def _use_tc(self, raw_cost):
-        if self.engine == "direct":
+        if self.engine == "direct" or self.training:      # training runs the fp32 autograd path
             return False
         from .tc_engine import tc_supported
         ok = tc_supported(self, raw_cost)
@@ -92,4 +93,6 @@ class PSMAggregator(PSMTrunk):
         size = (self.max_disp, H * 4, W * 4)
         if self.defer_upsample and not self.training:
             return [DeferredCost(c[:, 0].contiguous(), size, "trilinear") for c in (cost3, cost2, cost1)]
+        if self.training:
+            return [UpsampleTrilinearFn.apply(c, size) for c in (cost3, cost2, cost1)]
         return [F_.upsample_regress(c, size, "trilinear")[0] for c in (cost3, cost2, cost1)]

@@ -1,11 +1,14 @@
 """CAT_FUNCS -- concatenation cost volumes (reference: cost_processors/utils/cat_fms.py:7-88)."""
 from .....ops import functional as F_
+from .....ops.autograd import CatVolumeFn, wants_grad
 
 
 def cat_fms(reference_fm, target_fm, max_disp=192, start_disp=0, dilation=1, disp_sample=None):
     """[B,C,H,W] x2 -> [B,2C,D,H,W] float32; `disp_sample` is ignored like in the reference
     (cat_fms.py:7).  One fused kernel instead of ~2*D slice-assign launches plus a CPU zeros +
     H2D copy (cat_fms.py:32-45)."""
+    if wants_grad(reference_fm, target_fm):          # training: the same kernel + its backward
+        return CatVolumeFn.apply(reference_fm, target_fm, max_disp, start_disp, dilation)
     return F_.cat_volume(reference_fm, target_fm, max_disp, start_disp, dilation)
 
 

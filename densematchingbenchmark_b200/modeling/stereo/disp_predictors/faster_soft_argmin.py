@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from ....ops import functional as F_
+from ....ops.autograd import SoftArgminFn, wants_grad
 from ..cost_processors.aggregators.deferred import DeferredCost
 
 
@@ -41,6 +42,8 @@ class FasterSoftArgmin(nn.Module):
         kw = dict(alpha=self.alpha, normalize=self.normalize, disp_values=values)
         if isinstance(cost_volume, DeferredCost):
             return cost_volume.regress(**kw)
+        if wants_grad(cost_volume):
+            return SoftArgminFn.apply(cost_volume, self.alpha, self.normalize, 0.0, 1.0, values)
         return F_.soft_argmin(cost_volume, **kw)
 
     def __repr__(self):

@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from ....ops import functional as F_
+from ....ops.autograd import SoftArgminFn, wants_grad
 from ..cost_processors.aggregators.deferred import DeferredCost
 
 
@@ -35,8 +36,13 @@ class SoftArgmin(nn.Module):
             kw = dict(alpha=self.alpha, normalize=self.normalize, disp_values=self._values(cost_volume.device))
             if isinstance(cost_volume, DeferredCost):
                 return cost_volume.regress(**kw)
+            if wants_grad(cost_volume):
+                return SoftArgminFn.apply(cost_volume, self.alpha, self.normalize, 0.0, 1.0, kw["disp_values"])
             return F_.soft_argmin(cost_volume, **kw)
         assert D == disp_sample.shape[1], 'The number of disparity samples should be consistent!'
+        if wants_grad(cost_volume):
+            raise NotImplementedError("SoftArgmin: the backward of the per-pixel disp_sample variant is not built "
+                                      "(no shipped training config uses it)")
         return F_.soft_argmin(cost_volume, alpha=self.alpha, normalize=self.normalize, disp_sample=disp_sample)
 
     def __repr__(self):

@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from ....ops import functional as F_
+from ....ops.autograd import ConvUnitFn
 
 
 def consistent_padding_with_dilation(padding, dilation):
@@ -37,6 +38,8 @@ class FusedConvUnit(nn.Sequential):
         self._has_relu = relu
         self._cache_key = None
         self._cache_val = None
+        # training: None = per-process batch statistics; True / a process group = synchronised BatchNorm
+        self.sync_group = None
 
     # -- parameters ---------------------------------------------------------------------
     @property
@@ -91,16 +94,37 @@ class FusedConvUnit(nn.Sequential):
     def forward(self, x, residual=None, relu_after=False):
         """`residual` is added before the (optional) final ReLU requested with `relu_after`;
         the unit's own ReLU (conv3d_bn_relu) cannot be combined with a residual."""
-        if self.training and self._has_bn:
-            raise NotImplementedError(
-                "FusedConvUnit: training-mode BatchNorm (batch statistics) is not implemented on the "
-                "CUDA path yet; call .eval() (inference) -- see DESIGN.md 'out of scope this round'")
         if self._has_relu and residual is not None:
             raise ValueError("conv+bn+relu unit cannot take a fused residual")
+        if self.training:
+            return self._forward_train(x, residual, relu_after)
         w, b = self.folded()
         ksize, stride, pad, opad = self.geometry()
         return F_.conv3d_fused(x, w, b, ksize, stride, pad, self.transposed, opad, residual,
                                relu=self._has_relu or relu_after)
+
+
+def _unit_forward_train(conv, bn, x, residual, relu, sync_group=None):
+    """Training-mode forward of one conv(+bn)(+relu) unit through the autograd Function whose forward and
+    backward are the library's kernels (batch statistics, running-stat update as nn.BatchNorm3d)."""
+    transposed = isinstance(conv, nn.ConvTranspose3d)
+    for name in ("stride", "padding", "dilation"):
+        if len(set(getattr(conv, name))) != 1:
+            raise NotImplementedError("anisotropic %s is not supported by the CUDA path" % name)
+    if conv.dilation[0] != 1 or conv.groups != 1:
+        raise NotImplementedError("dilated / grouped 3-D convolution is not on the hot path")
+    cfg = dict(transposed=transposed, ksize=tuple(conv.kernel_size), stride=conv.stride[0], pad=conv.padding[0],
+               opad=conv.output_padding[0] if transposed else 0, relu=relu, bn=bn, sync_group=sync_group)
+    gamma = bn.weight if bn is not None else None
+    beta = bn.bias if bn is not None else None
+    return ConvUnitFn.apply(x, conv.weight, conv.bias, gamma, beta, residual, cfg)
+
+
+def _ff_train(self, x, residual=None, relu_after=False):
+    return _unit_forward_train(self.conv, self.bn, x, residual, self._has_relu or relu_after, self.sync_group)
+
+
+FusedConvUnit._forward_train = _ff_train
 
 
 def conv3d_bn(batchNorm, in_planes, out_planes, kernel_size=3, stride=1, padding=1, dilation=1, bias=True):
@@ -137,6 +161,8 @@ class _PlainCache(object):
 def fused_plain_conv3d(conv, x, residual=None, relu=False):
     """Run a bare nn.Conv3d / nn.ConvTranspose3d (e.g. the 32->1 classifier heads,
     aggregators/PSMNet.py:41-52) through the fused kernel, with an optional residual."""
+    if conv.training:
+        return _unit_forward_train(conv, None, x, residual, relu)
     cache = conv.__dict__.setdefault("_dmb_b200_cache", _PlainCache())
     tensors = [conv.weight, conv.bias]
     key = tuple((t.data_ptr(), t._version, str(t.device)) if t is not None else None for t in tensors)

@@ -1,0 +1,240 @@
+"""Training-mode autograd of the cost-volume path: every Function below is a forward AND a backward
+made of the library's own kernels (csrc/train.cu, csrc/conv3d_direct.cu, csrc/regress.cu,
+csrc/volumes.cu) -- torch.autograd only strings them together.
+
+Reference behaviour being reproduced: autograd over `nn.Sequential(Conv3d|ConvTranspose3d,
+BatchNorm3d (batch statistics, running-stat update), ReLU)` (layers/basic_layers.py:68-216), the
+trilinear / ConvTranspose3d(1,1,8,4,2) cost upsampling (aggregators/PSMNet.py:75-88,
+AcfNet.py:55-57,81-83), FasterSoftArgmin / SoftArgmin (disp_predictors/*.py) and cat_fms
+(cost_processors/utils/cat_fms.py:7-48).  Synchronised BatchNorm (dmb/apis/train.py:95-97 converts the
+model with apex) = all-reducing the raw per-channel sums between the two passes of each direction.
+"""
+import torch
+import torch.distributed as dist
+
+from .. import _cabi as C
+from . import functional as F_
+
+
+def _sync_world(group):
+    if group is None or not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(group if group is not True else None)
+
+
+def _all_reduce_sums(sums, group):
+    dist.all_reduce(sums, group=None if group is True else group)
+
+
+def _dgrad(dz, weight, transposed, ksize, stride, pad, x_dims):
+    """Gradient w.r.t. the conv input = the forward kernel with the weight's roles swapped:
+    Conv3d weight [Cout,Cin,k] read as a ConvTranspose3d weight (in=Cout, out=Cin), and vice versa."""
+    w = F_.pack_conv_weight(weight.detach(), transposed=not transposed)
+    return F_.conv3d_fused(dz, w, None, ksize, stride, pad, transposed=not transposed, out_dims=x_dims)
+
+
+def _wgrad(x, dz, transposed, ksize, stride, pad, weight_shape):
+    if tuple(ksize) != (3, 3, 3):
+        raise NotImplementedError("conv weight gradient: only 3x3x3 kernels are on the training path")
+    a, g = (dz, x) if transposed else (x, dz)          # transposed: the roles of input and output swap
+    B, Ca = a.shape[:2]
+    Cg = g.shape[1]
+    dw = torch.zeros(27, Ca, Cg, device=x.device, dtype=torch.float32)
+    C.call("dmb_b200_conv3d_wgrad", C.ptr(a), C.ptr(g), C.ptr(dw), B, Ca, Cg, C.int_array(list(a.shape[2:])),
+           C.int_array(list(g.shape[2:])), stride, pad, C.stream(x.device))
+    # packed [27][in-role][out-role] -> [out-role][in-role][3][3][3]: Conv3d [Cout,Cin,..]; for the transposed
+    # conv out-role = its Cin, in-role = its Cout, i.e. exactly the ConvTranspose3d layout [Cin,Cout,..]
+    return dw.permute(2, 1, 0).reshape(weight_shape).contiguous()
+
+
+class ConvUnitFn(torch.autograd.Function):
+    """y = relu?( bn_train?( conv(x, weight) + bias ) + residual? )"""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, residual, cfg):
+        x = C.f32(x)
+        transposed, ksize, stride, pad, opad = cfg["transposed"], cfg["ksize"], cfg["stride"], cfg["pad"], cfg["opad"]
+        relu, bn, group = cfg["relu"], cfg.get("bn"), cfg.get("sync_group")
+        w_packed = F_.pack_conv_weight(weight.detach(), transposed)
+        b = bias.detach().float().contiguous() if bias is not None else None
+        res = C.f32(residual) if residual is not None else None
+        ctx.cfg = cfg
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.x_dims = tuple(x.shape[2:])
+        if bn is None:
+            y = F_.conv3d_fused(x, w_packed, b, ksize, stride, pad, transposed, opad, res, relu=relu)
+            ctx.save_for_backward(x, weight, y if relu else None, None, None, None, None)
+            return y
+        z = F_.conv3d_fused(x, w_packed, b, ksize, stride, pad, transposed, opad, None, relu=False)
+        B, Co = z.shape[:2]
+        S = z.numel() // (B * Co)
+        dev = z.device
+        sums = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
+        C.call("dmb_b200_bn_stats", C.ptr(z), C.ptr(sums), B, Co, S, C.stream(dev))
+        world = _sync_world(group)
+        if world > 1:
+            _all_reduce_sums(sums, group)
+        count = float(B * S * world)
+        mean, invstd, scale, shift = (torch.empty(Co, device=dev, dtype=torch.float32) for _ in range(4))
+        track = bn.track_running_stats and bn.running_mean is not None
+        momentum = bn.momentum
+        if track:
+            bn.num_batches_tracked += 1
+            if momentum is None:                              # cumulative moving average
+                momentum = 1.0 / float(bn.num_batches_tracked)
+        g = gamma.detach().float().contiguous() if gamma is not None else None
+        bt = beta.detach().float().contiguous() if beta is not None else None
+        C.call("dmb_b200_bn_finalize", C.ptr(sums), count, C.ptr(g), C.ptr(bt), float(bn.eps),
+               float(momentum if momentum is not None else 0.0), C.ptr(bn.running_mean if track else None),
+               C.ptr(bn.running_var if track else None), C.ptr(mean), C.ptr(invstd), C.ptr(scale), C.ptr(shift), Co,
+               C.stream(dev))
+        y = torch.empty_like(z)
+        C.call("dmb_b200_bn_apply", C.ptr(z), C.ptr(scale), C.ptr(shift), C.ptr(res), C.ptr(y), B, Co, S,
+               1 if relu else 0, C.stream(dev))
+        ctx.count = count
+        ctx.save_for_backward(x, weight, y if relu else None, z, mean, invstd, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y_relu, z, mean, invstd, gamma = ctx.saved_tensors
+        cfg = ctx.cfg
+        transposed, ksize, stride, pad = cfg["transposed"], cfg["ksize"], cfg["stride"], cfg["pad"]
+        bn, group = cfg.get("bn"), cfg.get("sync_group")
+        dy = C.f32(dy)
+        B, Co = dy.shape[:2]
+        S = dy.numel() // (B * Co)
+        dev = dy.device
+        need_x, need_w, need_b, need_g, need_bt, need_res = ctx.needs_input_grad[:6]
+        need_res = need_res and ctx.has_res
+        dgamma = dbeta = dbias = dres = None
+        if bn is not None:
+            sums = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
+            C.call("dmb_b200_bn_backward_reduce", C.ptr(dy), C.ptr(y_relu), C.ptr(z), C.ptr(mean), C.ptr(invstd),
+                   C.ptr(sums), B, Co, S, C.stream(dev))
+            if gamma is not None:
+                dbeta, dgamma = sums[:Co].float(), sums[Co:].float()        # local sums (DDP averages them later)
+            if _sync_world(group) > 1:
+                _all_reduce_sums(sums, group)
+            dz = torch.empty_like(dy)
+            dres = torch.empty_like(dy) if need_res else None
+            C.call("dmb_b200_bn_backward_apply", C.ptr(dy), C.ptr(y_relu), C.ptr(z), C.ptr(mean), C.ptr(invstd),
+                   C.ptr(gamma), C.ptr(sums), ctx.count, C.ptr(dz), C.ptr(dres), B, Co, S, C.stream(dev))
+            if ctx.has_bias and need_b:
+                dbias = torch.zeros(Co, device=dev, dtype=torch.float32)    # batch norm removes the mean: exactly 0
+        else:
+            if y_relu is not None:
+                dz = torch.empty_like(dy)
+                C.call("dmb_b200_bn_backward_apply", C.ptr(dy), C.ptr(y_relu), None, None, None, None, None, 1.0,
+                       C.ptr(dz), None, B, Co, S, C.stream(dev))
+            else:
+                dz = dy
+            dres = dz if need_res else None
+            if ctx.has_bias and need_b:
+                sums = torch.zeros(2 * Co, device=dev, dtype=torch.float64)
+                C.call("dmb_b200_bn_backward_reduce", C.ptr(dz), None, None, None, None, C.ptr(sums), B, Co, S,
+                       C.stream(dev))
+                dbias = sums[:Co].float()
+        dx = _dgrad(dz, weight, transposed, ksize, stride, pad, ctx.x_dims) if need_x else None
+        dw = _wgrad(x, dz, transposed, ksize, stride, pad, weight.shape) if need_w else None
+        return dx, dw, dbias, (dgamma if need_g else None), (dbeta if need_bt else None), dres, None
+
+
+class CatVolumeFn(torch.autograd.Function):
+    """cat_fms forward + backward (cost_processors/utils/cat_fms.py:7-48)."""
+
+    @staticmethod
+    def forward(ctx, left, right, max_disp, start_disp, dilation):
+        ctx.args = (max_disp, start_disp, dilation)
+        ctx.shape = tuple(left.shape)
+        return F_.cat_volume(left, right, max_disp, start_disp, dilation)
+
+    @staticmethod
+    def backward(ctx, dvol):
+        dvol = C.f32(dvol)
+        B, Ch, H, W = ctx.shape
+        idx = F_.disp_indices(*ctx.args)
+        dl = torch.empty(ctx.shape, device=dvol.device, dtype=torch.float32)
+        dr = torch.empty_like(dl)
+        C.call("dmb_b200_cat_volume_backward", C.ptr(dvol), C.ptr(dl), C.ptr(dr), B, Ch, H, W, C.int_array(idx),
+               len(idx), C.stream(dvol.device))
+        return dl, dr, None, None, None
+
+
+class UpsampleTrilinearFn(torch.autograd.Function):
+    """[B,1,Dl,Hl,Wl] -> [B,D,H,W] (F.interpolate trilinear align_corners=True + squeeze, PSMNet.py:75-88)."""
+
+    @staticmethod
+    def forward(ctx, cost_low, size):
+        ctx.low_shape = tuple(cost_low.shape)
+        ctx.size = tuple(size)
+        return F_.upsample_regress(cost_low, size, "trilinear")[0]
+
+    @staticmethod
+    def backward(ctx, dcost):
+        dcost = C.f32(dcost)
+        B = ctx.low_shape[0]
+        Dl, Hl, Wl = ctx.low_shape[-3:]
+        D, H, W = ctx.size
+        dlow = torch.empty(ctx.low_shape, device=dcost.device, dtype=torch.float32)
+        C.call("dmb_b200_upsample_trilinear_backward", C.ptr(dcost), C.ptr(dlow), B, Dl, Hl, Wl, D, H, W,
+               C.stream(dcost.device))
+        return dlow, None
+
+
+class UpsampleDeconvFn(torch.autograd.Function):
+    """AcfNet's learned upsampling ConvTranspose3d(1,1,8,4,2) (aggregators/AcfNet.py:55-57,81-83)."""
+
+    @staticmethod
+    def forward(ctx, cost_low, weight, size):
+        low = C.f32(cost_low)
+        ctx.size = tuple(size)
+        ctx.save_for_backward(low, weight)
+        return F_.upsample_regress(low, size, "deconv", weight.detach())[0]
+
+    @staticmethod
+    def backward(ctx, dcost):
+        low, weight = ctx.saved_tensors
+        dcost = C.f32(dcost)
+        B = low.shape[0]
+        Dl, Hl, Wl = low.shape[-3:]
+        D, H, W = ctx.size
+        dlow = dw = None
+        if ctx.needs_input_grad[0]:
+            # gradient of a transposed conv w.r.t. its input = the plain conv with the same weight
+            w = F_.pack_conv_weight(weight.detach(), transposed=False)
+            dlow = F_.conv3d_fused(dcost.view(B, 1, D, H, W), w, None, (8, 8, 8), 4, 2).view(low.shape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(512, device=dcost.device, dtype=torch.float32)
+            C.call("dmb_b200_upsample_deconv_wgrad", C.ptr(low), C.ptr(dcost), C.ptr(dw), B, Dl, Hl, Wl, D, H, W,
+                   C.stream(dcost.device))
+            dw = dw.view(weight.shape)
+        return dlow, dw, None
+
+
+class SoftArgminFn(torch.autograd.Function):
+    """SoftArgmin / FasterSoftArgmin with a shared list of disparity samples."""
+
+    @staticmethod
+    def forward(ctx, cost, alpha, normalize, start_disp, disp_step, disp_values):
+        cost = C.f32(cost)
+        ctx.args = (float(alpha), bool(normalize), float(start_disp), float(disp_step))
+        dv = C.f32(disp_values).reshape(-1) if disp_values is not None else None
+        ctx.save_for_backward(cost, dv)
+        return F_.soft_argmin(cost, alpha, normalize, start_disp, disp_step, dv)
+
+    @staticmethod
+    def backward(ctx, gdisp):
+        cost, dv = ctx.saved_tensors
+        alpha, normalize, start_disp, disp_step = ctx.args
+        g = C.f32(gdisp)
+        B, D, H, W = cost.shape
+        dcost = torch.empty_like(cost)
+        C.call("dmb_b200_soft_argmin_backward", C.ptr(cost), C.ptr(g), C.ptr(dcost), B, D, H, W, alpha,
+               1 if normalize else 0, start_disp, disp_step, C.ptr(dv), C.stream(cost.device))
+        return dcost, None, None, None, None, None
+
+
+def wants_grad(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)

@@ -81,8 +81,10 @@ def pack_conv_weight(weight, transposed=False):
 
 
 def conv3d_fused(x, w_packed, bias, ksize, stride=1, pad=1, transposed=False, output_padding=0,
-                 residual=None, relu=False):
-    """y = act(conv(x) + bias + residual), fp32 NCDHW, generic direct kernel."""
+                 residual=None, relu=False, out_dims=None):
+    """y = act(conv(x) + bias + residual), fp32 NCDHW, generic direct kernel.  `out_dims` (transposed
+    only) names the output extent explicitly -- per-dimension output padding, as
+    ConvTranspose3d(output_size=...) / a conv input-gradient needs; the library validates it."""
     x = C.f32(x)
     B, Cin, Di, Hi, Wi = x.shape
     K3, Cin_w, Cout = w_packed.shape
@@ -91,6 +93,8 @@ def conv3d_fused(x, w_packed, bias, ksize, stride=1, pad=1, transposed=False, ou
                          % (tuple(w_packed.shape), Cin, ksize))
     if transposed:
         dims_out = [(n - 1) * stride - 2 * pad + k + output_padding for n, k in zip((Di, Hi, Wi), ksize)]
+        if out_dims is not None:
+            dims_out = [int(v) for v in out_dims]
     else:
         dims_out = [(n + 2 * pad - k) // stride + 1 for n, k in zip((Di, Hi, Wi), ksize)]
     y = torch.empty(B, Cout, *dims_out, device=x.device, dtype=torch.float32)

@@ -189,6 +189,53 @@ int dmb_b200_conv3d_tc_available(void);
 int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, int fp16, void* stream);
 int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W, int fp16, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-mode kernels (BASELINE config 5).  The reference trains through autograd over
+ * cuDNN/ATen: Conv3d + BatchNorm3d(batch statistics) + ReLU (layers/basic_layers.py:68-216),
+ * upsampling (aggregators/PSMNet.py:75-88, AcfNet.py:55-57,81-83), softmax regression
+ * (disp_predictors/faster_soft_argmin.py:51-75) and the volume builder (utils/cat_fms.py:7-48).
+ * All tensors float32 NCDHW, S = D*H*W.  conv dgrad is dmb_b200_conv3d_direct with the weight
+ * roles swapped (see densematchingbenchmark_b200/ops/autograd.py).
+ * ---------------------------------------------------------------------------------------- */
+/* sums [2C] float64, zero-initialised by the caller: sums[c] += sum z, sums[C+c] += sum z^2.
+ * Kept as raw sums so that a multi-GPU run can all-reduce them before finalize (SyncBN). */
+int dmb_b200_bn_stats(const float* z, double* sums, int B, int C, long long S, void* stream);
+/* mean/invstd/scale/shift [C] from the sums over `count` elements per channel; running stats
+ * (nullable) updated like nn.BatchNorm3d: momentum, unbiased variance. gamma/beta nullable. */
+int dmb_b200_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, float* mean, float* invstd,
+                         float* scale, float* shift, int C, void* stream);
+/* y = relu?( z * scale[c] + shift[c] + residual ) */
+int dmb_b200_bn_apply(const float* z, const float* scale, const float* shift, const float* residual, float* y,
+                      int B, int C, long long S, int relu, void* stream);
+/* g = dy * (y_relu > 0) (y_relu nullable: no ReLU).  sums [2C] float64 zero-initialised:
+ * sums[c] += sum g; sums[C+c] += sum g * (z - mean) * invstd (skipped when mean is NULL). */
+int dmb_b200_bn_backward_reduce(const float* dy, const float* y_relu, const float* z, const float* mean,
+                                const float* invstd, double* sums, int B, int C, long long S, void* stream);
+/* dz = gamma*invstd*(g - sums[c]/count - xhat*sums[C+c]/count) (mean != NULL) or g; dres (nullable) = g. */
+int dmb_b200_bn_backward_apply(const float* dy, const float* y_relu, const float* z, const float* mean,
+                               const float* invstd, const float* gamma, const double* sums, double count,
+                               float* dz, float* dres, int B, int C, long long S, void* stream);
+/* 3x3x3 conv weight gradient, regular-conv geometry (in = out*stride - pad + tap), stride 1 or 2:
+ * dw_packed [27][Cin][Cout] float32 (the conv3d_direct packing), zero-initialised by the caller,
+ * += sum_{b,o} dz[b,co,o] * x[b,ci,in(o,tap)].  A ConvTranspose3d's gradient is obtained by swapping
+ * the roles of x and dz. */
+int dmb_b200_conv3d_wgrad(const float* x, const float* dz, float* dw_packed, int B, int Cin, int Cout,
+                          const int* dims_in, const int* dims_out, int stride, int pad, void* stream);
+/* weight gradient of AcfNet's ConvTranspose3d(1,1,8,4,2) upsampling: dw [512] zero-initialised. */
+int dmb_b200_upsample_deconv_wgrad(const float* cost_low, const float* dcost, float* dw, int B, int Dl, int Hl,
+                                   int Wl, int D, int H, int W, void* stream);
+/* backward of the trilinear (align_corners=True) cost upsampling: dcost [B,D,H,W] -> dcost_low [B,Dl,Hl,Wl] */
+int dmb_b200_upsample_trilinear_backward(const float* dcost, float* dcost_low, int B, int Dl, int Hl, int Wl,
+                                         int D, int H, int W, void* stream);
+/* backward of dmb_b200_soft_argmin (disp_values / ramp variants): dcost [B,D,H,W] fully written */
+int dmb_b200_soft_argmin_backward(const float* cost, const float* grad_disp, float* dcost, int B, int D, int H, int W,
+                                  float alpha, int normalize, float start_disp, float disp_step,
+                                  const float* disp_values, void* stream);
+/* backward of dmb_b200_cat_volume: dvol [B,2C,D,H,W] -> dleft, dright [B,C,H,W]; D <= 256 */
+int dmb_b200_cat_volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
+                                 const int* disp_idx_host, int D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

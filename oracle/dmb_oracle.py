@@ -187,15 +187,33 @@ def gwc_volume(left, right, num_groups, max_disp=192, start_disp=0, dilation=1):
 # --------------------------------------------------------------------------------------
 # 3-D conv building blocks, addressed by reference state-dict keys
 # --------------------------------------------------------------------------------------
-def _bn(sd, key, x):
-    """Eval-mode BatchNorm3d with running statistics (nn.BatchNorm3d, basic_layers.py:74)."""
+BN_MOMENTUM = 0.1  # nn.BatchNorm3d default
+
+
+def _bn(sd, key, x, train=None):
+    """BatchNorm3d (nn.BatchNorm3d, basic_layers.py:74).  `train=None`: eval mode, running statistics.
+    `train` = dict: training mode -- biased batch statistics over (B,D,H,W) normalise the activations and
+    the running statistics the module would hold afterwards (momentum 0.1, unbiased variance,
+    num_batches_tracked + 1) are recorded in train['running']."""
     shape = (1, -1, 1, 1, 1)
     w = sd[key + ".weight"].view(shape); b = sd[key + ".bias"].view(shape)
+    if train is not None:
+        dims = (0, 2, 3, 4)
+        mean = x.mean(dim=dims)
+        var = x.var(dim=dims, unbiased=False)
+        n = x.numel() // x.shape[1]
+        run = train.setdefault("running", {})
+        with torch.no_grad():
+            run[key + ".running_mean"] = (1 - BN_MOMENTUM) * sd[key + ".running_mean"] + BN_MOMENTUM * mean
+            run[key + ".running_var"] = ((1 - BN_MOMENTUM) * sd[key + ".running_var"]
+                                         + BN_MOMENTUM * var * (n / max(n - 1, 1)))
+            run[key + ".num_batches_tracked"] = sd[key + ".num_batches_tracked"] + 1
+        return (x - mean.view(shape)) / torch.sqrt(var.view(shape) + BN_EPS) * w + b
     m = sd[key + ".running_mean"].view(shape); v = sd[key + ".running_var"].view(shape)
     return (x - m) / torch.sqrt(v + BN_EPS) * w + b
 
 
-def conv_unit(sd, key, x, stride=1, relu=False, transposed=False, batch_norm=True):
+def conv_unit(sd, key, x, stride=1, relu=False, transposed=False, batch_norm=True, train=None):
     """One `nn.Sequential(Conv3d|ConvTranspose3d, [BatchNorm3d], [ReLU])` of
     layers/basic_layers.py:68-216: `<key>.0` is the conv, `<key>.1` the BN.  3x3x3, padding 1,
     (transposed: output_padding 1 as in hourglass.py:53-60)."""
@@ -206,46 +224,48 @@ def conv_unit(sd, key, x, stride=1, relu=False, transposed=False, batch_norm=Tru
     else:
         y = F.conv3d(x, w, b, stride=stride, padding=1)
     if batch_norm:
-        y = _bn(sd, key + ".1", y)
+        y = _bn(sd, key + ".1", y, train)
     return F.relu(y) if relu else y
 
 
-def hourglass(sd, key, x, presqu=None, postsqu=None, batch_norm=True):
+def hourglass(sd, key, x, presqu=None, postsqu=None, batch_norm=True, train=None):
     """Hourglass.forward (cost_processors/utils/hourglass.py:62-86)."""
-    out = conv_unit(sd, key + ".conv1", x, stride=2, relu=True, batch_norm=batch_norm)
-    pre = conv_unit(sd, key + ".conv2", out, batch_norm=batch_norm)
+    bn = dict(batch_norm=batch_norm, train=train)
+    out = conv_unit(sd, key + ".conv1", x, stride=2, relu=True, **bn)
+    pre = conv_unit(sd, key + ".conv2", out, **bn)
     pre = F.relu(pre + postsqu) if postsqu is not None else F.relu(pre)
-    out = conv_unit(sd, key + ".conv3", pre, stride=2, relu=True, batch_norm=batch_norm)
-    out = conv_unit(sd, key + ".conv4", out, relu=True, batch_norm=batch_norm)
-    up = conv_unit(sd, key + ".conv5", out, stride=2, transposed=True, batch_norm=batch_norm)
+    out = conv_unit(sd, key + ".conv3", pre, stride=2, relu=True, **bn)
+    out = conv_unit(sd, key + ".conv4", out, relu=True, **bn)
+    up = conv_unit(sd, key + ".conv5", out, stride=2, transposed=True, **bn)
     post = F.relu(up + (presqu if presqu is not None else pre))
-    out = conv_unit(sd, key + ".conv6", post, stride=2, transposed=True, batch_norm=batch_norm)
+    out = conv_unit(sd, key + ".conv6", post, stride=2, transposed=True, **bn)
     return out, pre, post
 
 
-def _classif(sd, key, x, batch_norm=True):
-    y = conv_unit(sd, key + ".0", x, relu=True, batch_norm=batch_norm)
+def _classif(sd, key, x, batch_norm=True, train=None):
+    y = conv_unit(sd, key + ".0", x, relu=True, batch_norm=batch_norm, train=train)
     return F.conv3d(y, sd[key + ".1.weight"], sd.get(key + ".1.bias"), padding=1)
 
 
-def psm_trunk(sd, raw_cost, prefix="", batch_norm=True):
+def psm_trunk(sd, raw_cost, prefix="", batch_norm=True, train=None):
     """PSMAggregator.forward up to the three low-res costs (aggregators/PSMNet.py:55-72);
     AcfAggregator shares it (aggregators/AcfNet.py:62-76).  Returns (cost1, cost2, cost3),
     each [B,1,D4,H4,W4]."""
     p = prefix
-    c0 = conv_unit(sd, p + "dres0.0", raw_cost, relu=True, batch_norm=batch_norm)
-    c0 = conv_unit(sd, p + "dres0.1", c0, relu=True, batch_norm=batch_norm)
-    t = conv_unit(sd, p + "dres1.0", c0, relu=True, batch_norm=batch_norm)
-    c0 = conv_unit(sd, p + "dres1.1", t, batch_norm=batch_norm) + c0
-    o1, pre1, post1 = hourglass(sd, p + "dres2", c0, None, None, batch_norm)
+    bn = dict(batch_norm=batch_norm, train=train)
+    c0 = conv_unit(sd, p + "dres0.0", raw_cost, relu=True, **bn)
+    c0 = conv_unit(sd, p + "dres0.1", c0, relu=True, **bn)
+    t = conv_unit(sd, p + "dres1.0", c0, relu=True, **bn)
+    c0 = conv_unit(sd, p + "dres1.1", t, **bn) + c0
+    o1, pre1, post1 = hourglass(sd, p + "dres2", c0, None, None, batch_norm, train)
     o1 = o1 + c0
-    o2, pre2, post2 = hourglass(sd, p + "dres3", o1, pre1, post1, batch_norm)
+    o2, pre2, post2 = hourglass(sd, p + "dres3", o1, pre1, post1, batch_norm, train)
     o2 = o2 + c0
-    o3, _, _ = hourglass(sd, p + "dres4", o2, pre2, post2, batch_norm)
+    o3, _, _ = hourglass(sd, p + "dres4", o2, pre2, post2, batch_norm, train)
     o3 = o3 + c0
-    cost1 = _classif(sd, p + "classif1", o1, batch_norm)
-    cost2 = _classif(sd, p + "classif2", o2, batch_norm) + cost1
-    cost3 = _classif(sd, p + "classif3", o3, batch_norm) + cost2
+    cost1 = _classif(sd, p + "classif1", o1, batch_norm, train)
+    cost2 = _classif(sd, p + "classif2", o2, batch_norm, train) + cost1
+    cost3 = _classif(sd, p + "classif3", o3, batch_norm, train) + cost2
     return cost1, cost2, cost3
 
 
@@ -268,19 +288,19 @@ def trilinear_up(cost, out_dhw):
     return x
 
 
-def psm_aggregator(sd, raw_cost, max_disp, prefix="", batch_norm=True):
+def psm_aggregator(sd, raw_cost, max_disp, prefix="", batch_norm=True, train=None):
     """PSMAggregator.forward (aggregators/PSMNet.py:55-95) -> [cost3, cost2, cost1]."""
     B, C, D, H, W = raw_cost.shape
-    c1, c2, c3 = psm_trunk(sd, raw_cost, prefix, batch_norm)
+    c1, c2, c3 = psm_trunk(sd, raw_cost, prefix, batch_norm, train)
     size = [max_disp, H * 4, W * 4]
     up = [F.interpolate(c, size, mode="trilinear", align_corners=True).squeeze(1) for c in (c3, c2, c1)]
     return up
 
 
-def acf_aggregator(sd, raw_cost, max_disp, prefix="", batch_norm=True):
+def acf_aggregator(sd, raw_cost, max_disp, prefix="", batch_norm=True, train=None):
     """AcfAggregator.forward (aggregators/AcfNet.py:59-89): same trunk, learned
     ConvTranspose3d(1,1,8,4,2) upsampling (:55-57,81-83)."""
-    c1, c2, c3 = psm_trunk(sd, raw_cost, prefix, batch_norm)
+    c1, c2, c3 = psm_trunk(sd, raw_cost, prefix, batch_norm, train)
     outs = []
     for c, name in ((c3, "deconv3"), (c2, "deconv2"), (c1, "deconv1")):
         outs.append(F.conv_transpose3d(c, sd[prefix + name + ".weight"], None, stride=4, padding=2).squeeze(1))
@@ -504,3 +524,43 @@ def psm_hot_path(sd, left_fm, right_fm, max_disp=192, prefix="cost_processor.agg
     costs = psm_aggregator(sd, raw, max_disp, prefix)
     disps = [soft_argmin(c, max_disp) for c in costs]
     return costs, disps
+
+
+# --------------------------------------------------------------------------------------
+# training step of the hot path (BASELINE config 5)
+# --------------------------------------------------------------------------------------
+def disp_smooth_l1(disps, gt, max_disp, start_disp=0, weights=(1.0, 0.7, 0.5)):
+    """DispSmoothL1Loss at full resolution (losses/smooth_l1_loss.py:39-91): per level the mean
+    smooth-L1 over start_disp < gt < max_disp, weighted (configs/PSMNet/scene_flow.py:55-63)."""
+    mask = (gt > start_disp) & (gt < max_disp)
+    total = 0.0
+    for w, d in zip(weights, disps):
+        total = total + w * F.smooth_l1_loss(d[mask], gt[mask], reduction="mean")
+    return total
+
+
+def train_step(sd, left_fm, right_fm, gt, max_disp, kind="PSMNet", prefix="", weights=(1.0, 0.7, 0.5), shards=1):
+    """One forward + backward of cat volume -> aggregator (training-mode BatchNorm) -> soft-argmin ->
+    smooth-L1, through torch autograd on the functional restatement above.  Returns the loss, the three
+    disparity maps, d(loss)/d(every floating-point parameter), d(loss)/d(features) and the running
+    statistics the BatchNorm layers hold afterwards.  `shards` > 1 restates the data-parallel step with
+    synchronised BatchNorm: the batch statistics span the whole batch, the loss is the mean over `shards`
+    equal batch slices of each slice's own masked mean (what averaging per-rank gradients computes)."""
+    names = [k for k, v in sd.items() if v.is_floating_point() and "running_" not in k]
+    leaf = dict(sd)
+    for k in names:
+        leaf[k] = sd[k].clone().requires_grad_(True)
+    l = left_fm.clone().requires_grad_(True)
+    r = right_fm.clone().requires_grad_(True)
+    train = {}
+    raw = cat_volume(l, r, max_disp // 4, 0, 1)
+    agg = acf_aggregator if kind == "AcfNet" else psm_aggregator
+    costs = agg(leaf, raw, max_disp, prefix, True, train)
+    disps = [soft_argmin(c, max_disp) for c in costs]
+    n = gt.shape[0] // shards
+    loss = sum(disp_smooth_l1([d[i * n:(i + 1) * n] for d in disps], gt[i * n:(i + 1) * n], max_disp, 0, weights)
+               for i in range(shards)) / shards
+    loss.backward()
+    grads = {k: (leaf[k].grad if leaf[k].grad is not None else torch.zeros_like(sd[k])) for k in names}
+    return dict(loss=loss.detach(), disps=[d.detach() for d in disps], grads=grads, dleft=l.grad, dright=r.grad,
+                running=train["running"])

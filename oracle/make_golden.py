@@ -143,6 +143,61 @@ def gen_aggregators():
     print("aggregators.pt", len(out))
 
 
+TRAIN_CASE = dict(B=2, C=32, H4=8, W4=16, feat_disp=8, max_disp=32, seed=3, feat_seed=21, shift=2)
+
+
+def train_inputs():
+    """Seeded inputs of the training-step fixture (regenerated identically at test time)."""
+    c = TRAIN_CASE
+    l, r = seeded.feature_pair(c["B"], c["C"], c["H4"], c["W4"], seed=c["feat_seed"], scale=0.5, shift=c["shift"])
+    g = torch.Generator().manual_seed(c["feat_seed"] + 1)
+    gt = torch.rand(c["B"], 1, c["H4"] * 4, c["W4"] * 4, generator=g) * (c["max_disp"] + 8) - 4   # some masked out
+    return l, r, gt
+
+
+def grad_summary(t, n=32):
+    """(sum, abs-sum, strided sample) of a gradient tensor: keeps the fixture small."""
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return dict(sum=float(f.double().sum()), abssum=float(f.double().abs().sum()), sample=f[::step][:n].clone(),
+                step=step)
+
+
+def gen_train_step():
+    """One training step (forward with batch-statistics BatchNorm, smooth-L1 loss, backward) of the
+    REFERENCE cost processor + predictor: loss, disparities, gradient summaries, running statistics."""
+    ref_import.install()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_smooth_l1", os.path.join(ref_import.REFERENCE_ROOT, "dmb/modeling/stereo/losses/smooth_l1_loss.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    c = TRAIN_CASE
+    out = {}
+    for agg_type in ("PSMNet", "AcfNet"):
+        proc, pred = build_ref_processor(agg_type, c["feat_disp"], c["max_disp"])
+        proc.train(); pred.train()
+        entries = seeded.aggregator_entries(agg_type, 64)
+        sd = seeded.seeded_state_dict(entries, seed=c["seed"])
+        proc.aggregator.load_state_dict(sd)
+        l, r, gt = train_inputs()
+        l.requires_grad_(True); r.requires_grad_(True)
+        costs = proc(l, r)
+        disps = [pred(cost) for cost in costs]
+        losses = mod.DispSmoothL1Loss(c["max_disp"], weights=(1.0, 0.7, 0.5))(disps, gt)
+        loss = sum(losses.values())
+        loss.backward()
+        grads = {k: grad_summary(p.grad if p.grad is not None else torch.zeros_like(p))
+                 for k, p in proc.aggregator.named_parameters()}
+        after = proc.aggregator.state_dict()
+        running = {k: v.clone() for k, v in after.items() if "running_" in k or "num_batches" in k}
+        out[agg_type] = dict(case=dict(c), weight_checksum=seeded.checksum(sd), loss=float(loss),
+                             disps=[d.detach().clone() for d in disps], grads=grads,
+                             dleft=l.grad.clone(), dright=r.grad.clone(), running=running)
+        print("train", agg_type, "loss", float(loss), "|dleft|", float(l.grad.abs().sum()))
+    torch.save(out, os.path.join(OUT, "train_step.pt"))
+    print("train_step.pt")
+
+
 def gen_hourglass():
     """A bare Hourglass (cost_processors/utils/hourglass.py) with presqu/postsqu given."""
     ref_import.install()
@@ -190,3 +245,4 @@ if __name__ == "__main__":
     gen_hourglass()
     gen_epe()
     gen_aggregators()
+    gen_train_step()

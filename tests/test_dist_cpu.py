@@ -45,3 +45,72 @@ def test_reference_arm_only_rank0_prints():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
                         "--steps", "1", "--warmup", "1"], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from densematchingbenchmark_b200.utils.dist_utils import GradReducer, all_reduce_grads
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def make():
+            torch.manual_seed(0)                                   # identical replicas
+            return torch.nn.Sequential(torch.nn.Linear(6, 16), torch.nn.ReLU(), torch.nn.Linear(16, 16),
+                                       torch.nn.ReLU(), torch.nn.Linear(16, 3), torch.nn.Linear(3, 2))
+        g = torch.Generator().manual_seed(100 + rank)              # different data per rank
+        x = torch.randn(5, 6, generator=g)
+        # local gradients, then the exact mean over ranks through plain all_reduce as the expectation
+        ref = make()
+        ref[5].weight.requires_grad_(False)                        # a frozen parameter is skipped
+        ref(x).square().mean().backward()
+        want = []
+        for p in ref.parameters():
+            if p.requires_grad:
+                t = p.grad.clone()
+                dist.all_reduce(t)
+                want.append(t / world)
+        # (1) reference-compatible function, coalesced with small buckets and un-coalesced
+        for kw in (dict(coalesce=True, bucket_size_mb=-1), dict(coalesce=True, bucket_size_mb=1), dict(coalesce=False)):
+            m = make(); m[5].weight.requires_grad_(False)
+            m(x).square().mean().backward()
+            all_reduce_grads(m, **kw)
+            got = [p.grad for p in m.parameters() if p.requires_grad]
+            ok1 = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(got, want))
+            if not ok1:
+                break
+        # (2) overlapped reducer with tiny buckets (several collectives launched inside backward), two steps,
+        # the second one leaving the last layer without a gradient on every rank
+        m = make(); m[5].weight.requires_grad_(False)
+        red = GradReducer(m.parameters(), bucket_mb=0.0005)
+        m(x).square().mean().backward()
+        early = red.launched_early
+        red.finish()
+        got = [p.grad for p in m.parameters() if p.requires_grad]
+        ok2 = all(torch.allclose(a, b, atol=1e-6) for a, b in zip(got, want)) and early >= 2
+        for p in m.parameters():
+            p.grad = None
+        h = m[3](m[2](m[1](m[0](x))))                             # stops before the last two layers
+        h.square().mean().backward()
+        red.finish()
+        ok3 = m[4].weight.grad is not None and float(m[4].weight.grad.abs().max()) == 0.0
+        t = m[0].weight.grad.clone()
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3), len(red.buckets), float(t.abs().sum())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_grad_reducer_and_all_reduce_grads_gloo():
+    """The training path's one collective (mean all-reduce of gradients), world size 2 on gloo."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29870 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] and r[2] and r[3] for r in res), res
+    assert res[0][4] >= 3                                        # the tiny bucket size really split the parameters
+    assert abs(res[0][5] - res[1][5]) < 1e-6                     # both ranks hold the same averaged gradient

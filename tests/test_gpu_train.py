@@ -1,0 +1,332 @@
+"""GPU parity of the TRAINING path (BASELINE config 5): every backward kernel against torch autograd of the
+CPU oracle, the whole training step against the fixture produced by the reference's own modules
+(tests/golden/train_step.pt), and the data-parallel step (NCCL gradient all-reduce + synchronised
+BatchNorm) against the oracle's sharded restatement.
+
+Tolerances: gradients are sums of up to ~1e5 fp32 products accumulated in a different order than ATen's,
+so they are compared relative to the tensor's own scale (rtol 2e-3 of max |g|); forward values at the
+fp32 rounding level."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dmb_oracle as O
+import seeded
+from make_golden import train_inputs
+from test_oracle_golden import check_grad_summary
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def P():
+    import densematchingbenchmark_b200 as pkg
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return pkg
+
+
+def close(got, want, rtol=2e-3, what=""):
+    scale = float(want.abs().max())
+    err = float((got.detach().cpu() - want).abs().max())
+    assert err <= rtol * scale + 1e-6, "%s: max err %.3e vs scale %.3e" % (what, err, scale)
+
+
+# ---------------------------------------------------------------------------- conv + bn (+relu) units
+UNIT_CASES = [
+    # name, cin, cout, stride, transposed, bias, bn, relu, residual, dims (B, D, H, W)
+    ("s1_bn_relu", 32, 32, 1, False, False, True, True, False, (2, 6, 5, 37)),
+    ("s1_bn_res", 32, 32, 1, False, True, True, False, True, (2, 4, 6, 40)),
+    ("s1_wide_in", 64, 32, 1, False, False, True, True, False, (1, 4, 4, 72)),
+    ("s2_bn_relu", 32, 64, 2, False, False, True, True, False, (2, 8, 6, 20)),
+    ("s2_odd", 8, 16, 2, False, True, True, True, False, (1, 5, 7, 9)),
+    ("t2_bn_res_relu", 64, 64, 2, True, False, True, False, True, (2, 3, 4, 10)),
+    ("t2_bn", 64, 32, 2, True, False, True, False, False, (1, 4, 3, 18)),
+    ("head_plain", 32, 1, 1, False, False, False, False, True, (2, 4, 5, 33)),
+    ("nobn_bias_relu", 16, 24, 1, False, True, False, True, False, (1, 3, 4, 11)),
+]
+
+
+@pytest.mark.parametrize("case", UNIT_CASES, ids=[c[0] for c in UNIT_CASES])
+def test_conv_unit_train_forward_backward(P, case):
+    from densematchingbenchmark_b200.modeling.stereo.layers import basic_layers as L
+    name, cin, cout, stride, transposed, bias, bn, relu, with_res, dims = case
+    B, D, H, W = dims
+    g = torch.Generator().manual_seed(len(name) + cin)
+    if transposed:
+        unit = L.FusedConvUnit(torch.nn.ConvTranspose3d(cin, cout, 3, stride, 1, output_padding=1, bias=bias),
+                               torch.nn.BatchNorm3d(cout) if bn else None, relu=relu)
+    else:
+        unit = L.FusedConvUnit(torch.nn.Conv3d(cin, cout, 3, stride, 1, bias=bias),
+                               torch.nn.BatchNorm3d(cout) if bn else None, relu=relu)
+    with torch.no_grad():
+        for p in unit.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.2 if p.dim() > 1 else 0.5) + (1.0 if p.dim() == 1 else 0.0))
+        if bn:
+            unit[1].running_mean.copy_(torch.randn(cout, generator=g) * 0.1)
+            unit[1].running_var.copy_(torch.rand(cout, generator=g) + 0.5)
+    x = torch.randn(B, cin, D, H, W, generator=g)
+
+    # ---- torch autograd on CPU (what the reference's nn.Sequential does)
+    if transposed:
+        ref_conv = torch.nn.ConvTranspose3d(cin, cout, 3, stride, 1, output_padding=1, bias=bias)
+    else:
+        ref_conv = torch.nn.Conv3d(cin, cout, 3, stride, 1, bias=bias)
+    ref = torch.nn.Sequential(*([ref_conv] + ([torch.nn.BatchNorm3d(cout)] if bn else []))).train()
+    ref.load_state_dict({k: v.clone() for k, v in unit.state_dict().items()})
+    xr = x.clone().requires_grad_(True)
+    yr = ref(xr)
+    res = torch.randn(yr.shape, generator=g) if with_res else None
+    rr = res.clone().requires_grad_(True) if with_res else None
+    if with_res:
+        yr = yr + rr
+    relu_after = with_res and name.endswith("relu")
+    if relu or relu_after:
+        yr = F.relu(yr)
+    gy = torch.randn(yr.shape, generator=g)
+    yr.backward(gy)
+
+    # ---- ours
+    unit = unit.to(DEV).train()
+    xg = x.to(DEV).requires_grad_(True)
+    rg = res.to(DEV).requires_grad_(True) if with_res else None
+    y = unit(xg, residual=rg, relu_after=relu_after)
+    y.backward(gy.to(DEV))
+    close(y, yr.detach(), 1e-4, "y")
+    close(xg.grad, xr.grad, what="dx")
+    if with_res:
+        close(rg.grad, rr.grad, 1e-5, "dres")
+    got = dict(unit.named_parameters())
+    for k, p in ref.named_parameters():
+        if k == "0.bias" and bn:
+            assert float(got[k].grad.abs().max()) == 0.0 and float(p.grad.abs().max()) < 1e-3
+            continue
+        close(got[k].grad, p.grad, what="d" + k)
+    if bn:
+        for k in ("running_mean", "running_var"):
+            torch.testing.assert_close(getattr(unit[1], k).cpu(), getattr(ref[1], k), rtol=1e-4, atol=1e-5)
+        assert int(unit[1].num_batches_tracked) == int(ref[1].num_batches_tracked) == 1
+
+
+def test_conv_wgrad_multi_tile_and_segments(P):
+    """Raw C-ABI call: 64->64 channels (4 channel tiles), W = 100 (4 row segments, ragged tail), B = 3."""
+    from densematchingbenchmark_b200 import _cabi as C
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 64, 3, 4, 100, generator=g)
+    w = torch.randn(64, 64, 3, 3, 3, generator=g).requires_grad_(True)
+    y = F.conv3d(x, w, padding=1)
+    gy = torch.randn(y.shape, generator=g)
+    y.backward(gy)
+    dw = torch.zeros(27, 64, 64, device=DEV)
+    xg, gg = x.to(DEV), gy.to(DEV)               # keep the device copies alive across the launches
+    C.call("dmb_b200_conv3d_wgrad", C.ptr(xg), C.ptr(gg), C.ptr(dw), 3, 64, 64,
+           C.int_array([3, 4, 100]), C.int_array([3, 4, 100]), 1, 1, C.stream(torch.device(DEV)))
+    got = dw.permute(2, 1, 0).reshape(64, 64, 3, 3, 3)
+    close(got, w.grad, 1e-3, "dw")
+    with pytest.raises(C.DmbB200Error):          # geometry is validated
+        C.call("dmb_b200_conv3d_wgrad", C.ptr(xg), C.ptr(gg), C.ptr(dw), 3, 64, 64,
+               C.int_array([3, 4, 100]), C.int_array([3, 4, 99]), 1, 1, C.stream(torch.device(DEV)))
+
+
+# ---------------------------------------------------------------------------- upsampling / regression / volume
+@pytest.mark.parametrize("shape", [(2, 3, 5, 7, 12, 20, 28), (1, 6, 4, 9, 24, 16, 36), (1, 2, 2, 3, 5, 7, 11)])
+def test_upsample_trilinear_backward(P, shape):
+    from densematchingbenchmark_b200.ops.autograd import UpsampleTrilinearFn
+    B, Dl, Hl, Wl, D, H, W = shape
+    g = torch.Generator().manual_seed(D)
+    low = torch.randn(B, 1, Dl, Hl, Wl, generator=g)
+    gy = torch.randn(B, D, H, W, generator=g)
+    lr = low.clone().requires_grad_(True)
+    F.interpolate(lr, [D, H, W], mode="trilinear", align_corners=True).squeeze(1).backward(gy)
+    lg = low.to(DEV).requires_grad_(True)
+    out = UpsampleTrilinearFn.apply(lg, (D, H, W))
+    out.backward(gy.to(DEV))
+    close(out, F.interpolate(low, [D, H, W], mode="trilinear", align_corners=True).squeeze(1), 1e-5, "cost")
+    close(lg.grad, lr.grad, 1e-4, "dlow")
+
+
+def test_upsample_deconv_backward(P):
+    from densematchingbenchmark_b200.ops.autograd import UpsampleDeconvFn
+    g = torch.Generator().manual_seed(8)
+    low = torch.randn(2, 1, 3, 5, 6, generator=g)
+    w = torch.randn(1, 1, 8, 8, 8, generator=g) * 0.1
+    gy = torch.randn(2, 12, 20, 24, generator=g)
+    lr, wr = low.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    F.conv_transpose3d(lr, wr, None, stride=4, padding=2).squeeze(1).backward(gy)
+    lg, wg = low.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    UpsampleDeconvFn.apply(lg, wg, (12, 20, 24)).backward(gy.to(DEV))
+    close(lg.grad, lr.grad, 1e-4, "dlow")
+    close(wg.grad, wr.grad, 1e-4, "dw")
+
+
+@pytest.mark.parametrize("alpha,normalize", [(1.0, True), (-2.5, True), (0.7, False)])
+def test_soft_argmin_backward(P, alpha, normalize):
+    pred = P.PREDICTORS["FASTER"](max_disp=24, alpha=alpha, normalize=normalize).to(DEV)
+    g = torch.Generator().manual_seed(3)
+    cost = torch.randn(2, 24, 9, 13, generator=g) * 3
+    gy = torch.randn(2, 1, 9, 13, generator=g)
+    cr = cost.clone().requires_grad_(True)
+    O.soft_argmin(cr, 24, alpha=alpha, normalize=normalize).backward(gy)
+    cg = cost.to(DEV).requires_grad_(True)
+    d = pred(cg)
+    d.backward(gy.to(DEV))
+    close(d, O.soft_argmin(cost, 24, alpha=alpha, normalize=normalize), 1e-5, "disp")
+    close(cg.grad, cr.grad, 1e-4, "dcost")
+
+
+@pytest.mark.parametrize("shape", [(2, 4, 5, 16, 6, 0, 1), (1, 3, 4, 20, 9, -3, 2), (1, 2, 2, 6, 9, -4, 1),
+                                   (1, 32, 8, 130, 40, 0, 1)])
+def test_cat_volume_backward(P, shape):
+    B, C, H, W, md, sd, dil = shape
+    l, r = seeded.feature_pair(B, C, H, W, seed=W)
+    kw = dict(max_disp=md, start_disp=sd, dilation=dil)
+    lr, rr = l.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    vol = O.cat_volume(lr, rr, **kw)
+    gy = torch.randn(vol.shape, generator=torch.Generator().manual_seed(1))
+    vol.backward(gy)
+    lg, rg = l.to(DEV).requires_grad_(True), r.to(DEV).requires_grad_(True)
+    out = P.CAT_FUNCS["default"](lg, rg, **kw)
+    assert torch.equal(out.detach().cpu(), vol.detach())
+    out.backward(gy.to(DEV))
+    close(lg.grad, lr.grad, 1e-5, "dleft")
+    close(rg.grad, rr.grad, 1e-5, "dright")
+
+
+# ---------------------------------------------------------------------------- the whole training step
+def _cfg(P, agg, feat_disp, max_disp):
+    return P.ConfigDict(model=dict(
+        batch_norm=True,
+        cost_processor=dict(type="Concatenation",
+                            cost_computation=dict(type="default", max_disp=feat_disp, start_disp=0, dilation=1),
+                            cost_aggregator=dict(type=agg, max_disp=max_disp, in_planes=64)),
+        disp_predictor=dict(type="FASTER", max_disp=max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=True)))
+
+
+def run_train_step(P, kind, sd, l, r, gt, case, device=DEV, sync=False, reducer=False):
+    """Forward + backward of our cost processor + predictor in train() mode with the smooth-L1 loss of
+    configs/PSMNet/scene_flow.py:55-63 (plain torch ops on the disparity maps: outside the path)."""
+    cfg = _cfg(P, kind, case["feat_disp"], case["max_disp"])
+    proc = P.build_cost_processor(cfg).to(device)
+    pred = P.build_disp_predictor(cfg).to(device)
+    proc.aggregator.load_state_dict(sd)
+    proc.train(); pred.train()
+    red = None
+    if sync:
+        from densematchingbenchmark_b200.utils.dist_utils import enable_sync_batchnorm, GradReducer
+        assert enable_sync_batchnorm(proc) > 20
+        if reducer:
+            red = GradReducer(proc.parameters(), bucket_mb=1.0)
+    lg, rg = l.to(device).requires_grad_(True), r.to(device).requires_grad_(True)
+    costs = proc(lg, rg)
+    disps = [pred(c) for c in costs]
+    loss = O.disp_smooth_l1(disps, gt.to(device), case["max_disp"])
+    loss.backward()
+    if red is not None:
+        red.finish()
+    return proc, loss.detach(), [d.detach() for d in disps], lg.grad, rg.grad, red
+
+
+@pytest.mark.parametrize("kind", ["PSMNet", "AcfNet"])
+def test_train_step_vs_reference_golden_and_oracle(P, golden_dir, kind):
+    rec = torch.load(os.path.join(golden_dir, "train_step.pt"), weights_only=False)[kind]
+    c = rec["case"]
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries(kind, 64), seed=c["seed"])
+    l, r, gt = train_inputs()
+    proc, loss, disps, dl, dr, _ = run_train_step(P, kind, sd, l, r, gt, c)
+    # (1) against the reference's own modules (fixture)
+    assert abs(float(loss) - rec["loss"]) < 1e-4 * abs(rec["loss"])
+    for a, b in zip(disps, rec["disps"]):
+        assert float((a.cpu() - b).abs().max()) < 1e-3                     # the north-star forward tolerance
+    close(dl, rec["dleft"], what="dleft")
+    close(dr, rec["dright"], what="dright")
+    params = dict(proc.aggregator.named_parameters())
+    assert set(params) == set(rec["grads"])
+    for k, want in rec["grads"].items():
+        if k.endswith(".0.bias"):
+            assert float(params[k].grad.abs().max()) < 1e-4
+            continue
+        check_grad_summary(params[k].grad, want, rtol=3e-3, what=k)
+    after = proc.aggregator.state_dict()
+    for k, want in rec["running"].items():
+        torch.testing.assert_close(after[k].cpu().to(want.dtype), want, rtol=1e-4, atol=1e-5)
+    # (2) every gradient element against the oracle's autograd
+    want = O.train_step(sd, l, r, gt, c["max_disp"], kind)
+    for k, g in want["grads"].items():
+        if k.endswith(".0.bias"):
+            continue
+        close(params[k].grad, g, 3e-3, k)
+
+
+def test_train_mode_is_not_the_inference_engine(P):
+    """train() must never route through the BN-folded tensor-core trunk (it uses running statistics)."""
+    cfg = _cfg(P, "PSMNet", 8, 32)
+    proc = P.build_cost_processor(cfg).to(DEV).train()
+    raw = torch.zeros(1, 64, 8, 8, 16, device=DEV)
+    assert proc.aggregator._use_tc(raw) is False
+    assert proc.aggregator.blocked_cat_volume(torch.zeros(1, 32, 8, 16, device=DEV), torch.zeros(1, 32, 8, 16, device=DEV),
+                                              max_disp=8) is None
+
+
+# ---------------------------------------------------------------------------- data parallel (2 GPUs, NCCL)
+def _ddp_worker(rank, world, port, kind, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    import densematchingbenchmark_b200 as pkg
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        from make_golden import TRAIN_CASE
+        sd = seeded.seeded_state_dict(seeded.aggregator_entries(kind, 64), seed=TRAIN_CASE["seed"])
+        l, r, gt = train_inputs()
+        sl = slice(rank, rank + 1)                      # one pair per rank
+        proc, loss, disps, dl, dr, red = run_train_step(pkg, kind, sd, l[sl], r[sl], gt[sl], TRAIN_CASE,
+                                                        device="cuda:%d" % rank, sync=True, reducer=True)
+        grads = {k: p.grad.cpu() for k, p in proc.aggregator.named_parameters()}
+        running = {k: v.cpu() for k, v in proc.aggregator.state_dict().items() if "running_" in k}
+        q.put((rank, float(loss), grads, running, dl.cpu(), red.launched_early))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["PSMNet"])
+def test_data_parallel_train_step_two_gpus(P, kind):
+    """2 ranks x 1 pair with synchronised BatchNorm and the overlapped gradient all-reduce == the oracle's
+    2-pair step whose loss is the mean of the per-shard losses."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    from make_golden import TRAIN_CASE
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29750 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_ddp_worker, args=(rk, 2, port, kind, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries(kind, 64), seed=TRAIN_CASE["seed"])
+    l, r, gt = train_inputs()
+    want = O.train_step(sd, l, r, gt, TRAIN_CASE["max_disp"], kind, shards=2)
+    assert abs(0.5 * (res[0][1] + res[1][1]) - float(want["loss"])) < 1e-4 * float(want["loss"])
+    for k, g in want["grads"].items():
+        if k.endswith(".0.bias"):
+            continue
+        close(res[0][2][k], g, 3e-3, k)
+        assert torch.equal(res[0][2][k], res[1][2][k]), k          # both ranks hold the same averaged gradient
+    for k, v in want["running"].items():
+        if "running_" in k:
+            torch.testing.assert_close(res[0][3][k], v, rtol=1e-4, atol=1e-5)
+    # per-rank feature gradients are NOT averaged (they feed each rank's own backbone): rank r holds shard r's,
+    # scaled by 1/world only through the loss definition of the oracle
+    close(res[0][4] * 0.5, want["dleft"][0:1], 3e-3, "dleft rank 0")
+    assert res[0][5] >= 1                                          # at least one bucket reduced inside backward

@@ -158,10 +158,12 @@ def test_deferred_cost_dispatch(P, monkeypatch):
     assert calls["n"] == 2       # one regress + one materialisation
 
 
-def test_training_forward_is_refused_on_cpu_too(P):
+def test_training_forward_has_no_cpu_path_either(P):
+    """train() routes through the autograd Functions of ops/autograd.py -- CUDA kernels only."""
+    from densematchingbenchmark_b200._cabi import DmbB200Error
     from densematchingbenchmark_b200.modeling.stereo.layers.basic_layers import conv3d_bn
     unit = conv3d_bn(True, 4, 4, 3, 1, 1).train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(DmbB200Error):
         unit(torch.zeros(1, 4, 2, 2, 2))
 
 

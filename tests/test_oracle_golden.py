@@ -134,3 +134,40 @@ def test_sga_lga_basic_properties():
     c = torch.randn(1, 6, 5, 7, generator=g)
     gl = torch.zeros(1, 3, 5, 5, 5, 7); gl[:, 0, 2, 2] = 2.0        # centre tap only
     torch.testing.assert_close(O.lga(c, gl.view(1, 75, 5, 7)), c)
+
+
+def check_grad_summary(got, want, rtol=2e-3, what=""):
+    """Compare a gradient tensor with the (sum, abs-sum, strided sample) summary stored in the fixture."""
+    f = got.detach().reshape(-1).cpu()
+    scale = want["abssum"] / max(f.numel(), 1)                  # mean |g|: the absolute scale of this tensor
+    sample = f[::want["step"]][:want["sample"].numel()]
+    assert float((sample - want["sample"]).abs().max()) <= rtol * float(want["sample"].abs().max()) + 20 * rtol * scale + 1e-7, what
+    assert abs(float(f.double().abs().sum()) - want["abssum"]) <= rtol * want["abssum"] + 1e-6, what
+    assert abs(float(f.double().sum()) - want["sum"]) <= rtol * want["abssum"] + 1e-6, what
+
+
+@pytest.mark.parametrize("kind", ["PSMNet", "AcfNet"])
+def test_train_step_matches_reference(golden_dir, kind):
+    """Training-mode forward/backward of the oracle (batch-statistics BatchNorm, smooth-L1) against the
+    reference modules' own autograd (fixture made by oracle/make_golden.py:gen_train_step)."""
+    from make_golden import train_inputs
+    rec = _load(golden_dir, "train_step.pt")[kind]
+    c = rec["case"]
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries(kind, 64), seed=c["seed"])
+    assert abs(seeded.checksum(sd) - rec["weight_checksum"]) < 1e-3 * rec["weight_checksum"]
+    l, r, gt = train_inputs()
+    got = O.train_step(sd, l, r, gt, c["max_disp"], kind)
+    assert abs(float(got["loss"]) - rec["loss"]) < 1e-4 * abs(rec["loss"])
+    for a, b in zip(got["disps"], rec["disps"]):
+        assert float((a - b).abs().max()) < 1e-3
+    torch.testing.assert_close(got["dleft"], rec["dleft"], rtol=1e-3, atol=1e-3 * float(rec["dleft"].abs().max()))
+    torch.testing.assert_close(got["dright"], rec["dright"], rtol=1e-3, atol=1e-3 * float(rec["dright"].abs().max()))
+    assert set(got["grads"]) == set(rec["grads"])
+    for k, want in rec["grads"].items():
+        if k.endswith(".0.bias"):
+            # a conv bias in front of a batch norm: the true gradient is 0, autograd leaves rounding noise
+            assert float(got["grads"][k].abs().max()) < 1e-4
+            continue
+        check_grad_summary(got["grads"][k], want, what=k)
+    for k, want in rec["running"].items():
+        torch.testing.assert_close(got["running"][k].to(want.dtype), want, rtol=1e-5, atol=1e-6)
