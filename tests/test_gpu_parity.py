@@ -289,12 +289,16 @@ def test_gc_and_stereonet_aggregators_vs_torch_modules(P):
     torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-3)
 
 
-def test_training_mode_fails_loudly(P):
+def test_training_mode_runs_the_autograd_path(P):
+    """.train() used to raise; it now runs the library's training kernels (tests/test_gpu_train.py holds the
+    parity checks) -- here only: batch statistics are used (output differs from eval) and gradients flow."""
     proc = P.build_cost_processor(_cfg(P)).to(DEV).train()
-    proc.aggregator.engine = "direct"
     l, r = seeded.feature_pair(1, 32, 8, 16, seed=1)
-    with pytest.raises(NotImplementedError):
-        proc(l.to(DEV), r.to(DEV))
+    l = l.to(DEV).requires_grad_(True)
+    costs = proc(l, r.to(DEV))
+    assert len(costs) == 3 and costs[0].requires_grad
+    costs[0].sum().backward()
+    assert l.grad is not None and bool(torch.isfinite(l.grad).all())
 
 
 @pytest.mark.parametrize("engine,precision", [("direct", "fp16x3"), ("auto", "fp16x3"), ("auto", "bf16x3")])
