@@ -117,6 +117,11 @@ struct Params {
     int relu;
     int n_valid_out;           // output channels that exist (1 in y_f32 mode, else 32)
     float acc_scale;           // 2^-k undoing the power-of-two weight pre-scaling (exact)
+    // fused classifier head (KIND 3 only): instead of storing the 32-channel activation a, the epilogue
+    // writes its 27 per-tap projections T[tap][voxel] = sum_c a[c] * head_w[tap][c]; the 32->1 3x3x3
+    // convolution that follows is then a 27-term gather (head_gather_kernel)
+    const float* head_w;       // [27][32] fp32 or null
+    float* head_t;             // [B][27][Do][Ho][Wo] fp32
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -221,7 +226,8 @@ struct Smem {
     static constexpr int NST = nstage_of(KIND);
     static constexpr int PLANES_OFF = W_BYTES;
     static constexpr int BAR_OFF = PLANES_OFF + NST * STAGE_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256;
+    static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [27][32] fp32 head weights (KIND 3)
+    static constexpr int TOTAL = HEAD_OFF + (KIND == 3 ? TAPS * NB * 4 : 0);
     static constexpr uint32_t LBO_B = ROWS * 16;
     static constexpr uint32_t SBO_B = 128;
     // The tensor core adds each K=16 partial product into the fp32 accumulator with truncation
@@ -311,6 +317,73 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
     }
 }
 
+// fused classifier head: bias + ReLU, then the 27 per-tap projections of the voxel's 32 channels
+// (fp32 FMAs on the un-rounded activation), one coalesced fp32 store per tap plane
+__device__ __forceinline__ void store_head(const Params& p, float (&v)[NB], const float (&bias)[NB],
+                                           const float4* __restrict__ hw, int b, int d, int h, int w) {
+    const size_t vol = (size_t)p.Do * p.Ho * p.Wo;
+    float* t = p.head_t + (size_t)b * TAPS * vol + ((size_t)d * p.Ho + h) * p.Wo + w;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) {
+        v[c] += bias[c];
+        if (p.relu) v[c] = fmaxf(v[c], 0.f);
+    }
+#pragma unroll
+    for (int tap = 0; tap < TAPS; ++tap) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < NB / 4; c4 += 2) {
+            const float4 w0 = hw[tap * (NB / 4) + c4];
+            const float4 w1 = hw[tap * (NB / 4) + c4 + 1];
+            a0 = fmaf(v[4 * c4 + 0], w0.x, a0);
+            a0 = fmaf(v[4 * c4 + 1], w0.y, a0);
+            a0 = fmaf(v[4 * c4 + 2], w0.z, a0);
+            a0 = fmaf(v[4 * c4 + 3], w0.w, a0);
+            a1 = fmaf(v[4 * c4 + 4], w1.x, a1);
+            a1 = fmaf(v[4 * c4 + 5], w1.y, a1);
+            a1 = fmaf(v[4 * c4 + 6], w1.z, a1);
+            a1 = fmaf(v[4 * c4 + 7], w1.w, a1);
+        }
+        t[(size_t)tap * vol] = a0 + a1;
+    }
+}
+
+// out[b,d,h,w] = res + sum_tap T[b][tap][d+kd-1][h+kh-1][w+kw-1] (zero outside the volume): the
+// 32->1 3x3x3 head (aggregators/PSMNet.py:41-52) after store_head; every T element is read once
+__global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ T, const float* __restrict__ res,
+                                                          float* __restrict__ y, int B, int D, int H, int W) {
+    const size_t vol = (size_t)D * H * W;
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * vol) return;
+    const int b = (int)(i / vol);
+    size_t r = i - (size_t)b * vol;
+    const int d = (int)(r / ((size_t)H * W));
+    r -= (size_t)d * H * W;
+    const int h = (int)(r / W), w = (int)(r - (size_t)h * W);
+    const float* tb = T + (size_t)b * TAPS * vol;
+    float acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+        const int dd = d + kd - 1;
+        if (dd < 0 || dd >= D) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int hh = h + kh - 1;
+            if (hh < 0 || hh >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ww = w + kw - 1;
+                if (ww < 0 || ww >= W) continue;
+                const int tap = (kd * 3 + kh) * 3 + kw;
+                acc[kd] += __ldg(tb + (size_t)tap * vol + ((size_t)dd * H + hh) * W + ww);
+            }
+        }
+    }
+    float o = (acc[0] + acc[1]) + acc[2];
+    if (res) o += __ldg(res + i);
+    y[i] = o;
+}
+
 template <int KIND, bool SPLIT, bool FP16>
 __global__ void __launch_bounds__(nthreads_of(KIND), 1)
 conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
@@ -331,6 +404,10 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    if (KIND == 3 && p.head_w) {
+        float* hw = reinterpret_cast<float*>(smem + S::HEAD_OFF);
+        for (int i = threadIdx.x; i < TAPS * NB; i += blockDim.x) hw[i] = __ldg(p.head_w + i);
+    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
             mbar_init(&full[i], 1);
@@ -748,7 +825,12 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                     ++t;
-                    if (valid) store_voxel<FP16>(p, v, bias, it.b, d, h, w);
+                    if (valid) {
+                        if (KIND == 3 && p.head_t)
+                            store_head(p, v, bias, reinterpret_cast<const float4*>(smem + S::HEAD_OFF), it.b, d, h, w);
+                        else
+                            store_voxel<FP16>(p, v, bias, it.b, d, h, w);
+                    }
                 } else if (KIND != 2) {
                     const uint32_t buf = t & 1;
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
@@ -999,10 +1081,10 @@ extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_bl
     return check_launch("pack_weights_kernel");
 }
 
-extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
-                                  const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
-                                  int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind,
-                                  int relu, int fp16, void* stream) {
+static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
+                          const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
+                          int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind,
+                          int relu, int fp16, const float* head_w, float* head_t, void* stream) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
     DMB_REQUIRE(kind >= 0 && kind <= 4, "conv3d_tc: kind must be 0/3 (stride 1), 1/4 (stride 2) or 2 (transposed stride 2)");
@@ -1010,7 +1092,11 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
     DMB_REQUIRE(w_scale > 0.f, "conv3d_tc: w_scale must be positive");
     const bool scalar_out = (Cout == 1);
     DMB_REQUIRE(scalar_out || (Cout > 0 && Cout % 32 == 0), "conv3d_tc: Cout=%d must be 1 or a multiple of 32", Cout);
-    if (scalar_out)
+    const bool head = head_t != nullptr;
+    if (head)
+        DMB_REQUIRE(head_w && kind == 3 && Cin == 32 && Cout == 32 && !y_hi && !y_lo && !y_f32 && !res_hi && !res_f32,
+                    "conv3d_tc_head: needs a 32->32 stride-1 layer (kind 3), no residual, no activation output");
+    else if (scalar_out)
         DMB_REQUIRE(y_f32 && !y_hi, "conv3d_tc: Cout==1 writes y_f32 only");
     else
         DMB_REQUIRE(y_hi && !y_f32 && !res_f32, "conv3d_tc: Cout>=32 writes the blocked 16-bit output");
@@ -1019,13 +1105,15 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
         DMB_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "conv3d_tc: stride-2 needs even input extents");
     if (!device_ok()) return fail(DMB_ERR_UNSUPPORTED, "conv3d_tc: needs an sm_100 device and a TMA-capable driver");
     const bool split = x_lo != nullptr;
-    DMB_REQUIRE(scalar_out || split == (y_lo != nullptr), "conv3d_tc: x_lo and y_lo must both be given or both be NULL");
+    DMB_REQUIRE(head || scalar_out || split == (y_lo != nullptr), "conv3d_tc: x_lo and y_lo must both be given or both be NULL");
 
     const int cbk = cbk_of(kind);
     const int IB = Cin / (8 * cbk), OB = scalar_out ? 1 : Cout / 32;
     const int CBS = Cin / 8;
 
     Params p;
+    p.head_w = head_w;
+    p.head_t = head_t;
     p.B = (kind == 1) ? 1 : B;
     const bool s2 = (kind == 1 || kind == 4);
     // KIND 4 tiles W in INPUT columns (every column is computed, even centres are kept)
@@ -1125,4 +1213,29 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
         }
     }
     return DMB_OK;
+}
+
+extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
+                                  const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
+                                  int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind,
+                                  int relu, int fp16, void* stream) {
+    return conv3d_tc_impl(x_hi, x_lo, Cin, w_blob, w_scale, bias, res_hi, res_lo, y_hi, y_lo, Cout, y_f32, res_f32, B, D, H,
+                          W, kind, relu, fp16, nullptr, nullptr, stream);
+}
+
+extern "C" int dmb_b200_conv3d_tc_head(const void* x_hi, const void* x_lo, const void* w_blob, float w_scale,
+                                       const float* bias, const float* head_w, float* head_t, int B, int D, int H, int W,
+                                       int relu, int fp16, void* stream) {
+    DMB_REQUIRE(head_w && head_t, "conv3d_tc_head: null head weights / tap buffer");
+    return conv3d_tc_impl(x_hi, x_lo, 32, w_blob, w_scale, bias, nullptr, nullptr, nullptr, nullptr, 32, nullptr, nullptr, B,
+                          D, H, W, 3, relu, fp16, head_w, head_t, stream);
+}
+
+extern "C" int dmb_b200_head_gather(const float* head_t, const float* res, float* y, int B, int D, int H, int W,
+                                    void* stream) {
+    DMB_REQUIRE(head_t && y, "head_gather: null pointer");
+    DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "head_gather: non-positive dimension");
+    const int64_t n = (int64_t)B * D * H * W;
+    head_gather_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(head_t, res, y, B, D, H, W);
+    return check_launch("head_gather_kernel");
 }

@@ -18,7 +18,13 @@ namespace dmb {
 // e^x for x <= 0 as exp2f(x * log2(e)): the subtraction (c - m) is done first, so the product's rounding
 // error is relative to the SHIFTED argument (|x| < ~20 for every term that matters) -- 2-ulp exp2f keeps
 // the softmax weights within ~1e-6 relative of expf at a third of its instruction count.
-__device__ __forceinline__ float exp_neg(float x) { return exp2f(x * 1.4426950408889634f); }
+// ex2.approx.ftz is the instruction exp2f() itself is built on (max rel. error 2^-22); the wrapper code that
+// exp2f adds for denormal results is not needed: arguments are <= 0 and a flushed e^-88 contributes nothing
+__device__ __forceinline__ float exp_neg(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+}
 
 struct SoftState {
     float m, s, t;
@@ -277,6 +283,82 @@ __global__ void __launch_bounds__(256) upsample_trilinear_kernel(const float* __
     if (REGRESS) disp_out[(size_t)b * oplane + (size_t)y * p.W + x] = p.normalize ? st.result() : lin;
 }
 
+// Inference fast path of the above (no cost write, softmax regression): the per-disparity interpolation
+// table {byte offset of source plane i0, of i1, l0, l1} and the disparity values are the same for every
+// pixel, so each CTA computes them once into shared memory.  The depth march then has no int<->float
+// conversions (quarter-rate XU instructions, which -- 3 per value -- bounded the generic kernel) and
+// costs two broadcast table loads, two column loads, a blend and the online-softmax update per value.
+__global__ void __launch_bounds__(256) upsample_trilinear_regress_kernel(const float* __restrict__ low,
+                                                                         float* __restrict__ disp_out,
+                                                                         const float* __restrict__ dvals,
+                                                                         RegressParams p) {
+    extern __shared__ float sa[];
+    uint4* tab = reinterpret_cast<uint4*>(sa + (size_t)p.Dl * 256);   // [D]
+    float* dvt = reinterpret_cast<float*>(tab + p.D);                 // [D]
+    const float sy = p.H > 1 ? (float)(p.Hl - 1) / (float)(p.H - 1) : 0.f;
+    const float sx = p.W > 1 ? (float)(p.Wl - 1) / (float)(p.W - 1) : 0.f;
+    const float sd = p.D > 1 ? (float)(p.Dl - 1) / (float)(p.D - 1) : 0.f;
+    for (int d = threadIdx.x; d < p.D; d += 256) {
+        const float fd = sd * (float)d;
+        const int i0 = (int)fd;
+        const int i1 = i0 + (i0 < p.Dl - 1 ? 1 : 0);
+        const float l1 = fd - (float)i0, l0 = 1.f - l1;
+        tab[d] = make_uint4((uint32_t)i0 * 1024u, (uint32_t)i1 * 1024u, __float_as_uint(l0), __float_as_uint(l1));
+        dvt[d] = disp_value(dvals, p, d);
+    }
+    const int xr = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int yr = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int b = blockIdx.z;
+    const bool active = xr < p.W && yr < p.H;
+    const int x = min(xr, p.W - 1), y = min(yr, p.H - 1);
+    const size_t lplane = (size_t)p.Hl * p.Wl;
+    const float* lb = low + (size_t)b * p.Dl * lplane;
+    float* col = sa + threadIdx.x;
+    {
+        const float fy = sy * (float)y, fx = sx * (float)x;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < p.Hl - 1 ? 1 : 0), x1 = x0 + (x0 < p.Wl - 1 ? 1 : 0);
+        const float ly1 = fy - (float)y0, ly0 = 1.f - ly1;
+        const float lx1 = fx - (float)x0, lx0 = 1.f - lx1;
+        const float* q00 = lb + y0 * p.Wl + x0;
+        const float* q01 = lb + y0 * p.Wl + x1;
+        const float* q10 = lb + y1 * p.Wl + x0;
+        const float* q11 = lb + y1 * p.Wl + x1;
+#pragma unroll 4
+        for (int dl = 0; dl < p.Dl; ++dl) {
+            const size_t o = (size_t)dl * lplane;
+            col[dl * 256] = ly0 * (lx0 * __ldg(q00 + o) + lx1 * __ldg(q01 + o)) +
+                            ly1 * (lx0 * __ldg(q10 + o) + lx1 * __ldg(q11 + o));
+        }
+    }
+    __syncthreads();
+    const unsigned char* colb = reinterpret_cast<const unsigned char*>(col);
+    SoftState st;
+    st.init();
+    int d0 = 0;
+    for (; d0 + 4 <= p.D; d0 += 4) {
+        float c[4], dv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 e = tab[d0 + j];
+            const float a0 = *reinterpret_cast<const float*>(colb + e.x);
+            const float a1 = *reinterpret_cast<const float*>(colb + e.y);
+            const float v = __uint_as_float(e.z) * a0 + __uint_as_float(e.w) * a1;
+            c[j] = v * p.alpha;
+            dv[j] = dvt[d0 + j];
+        }
+        st.push4(c, dv);
+    }
+    for (; d0 < p.D; ++d0) {
+        const uint4 e = tab[d0];
+        const float a0 = *reinterpret_cast<const float*>(colb + e.x);
+        const float a1 = *reinterpret_cast<const float*>(colb + e.y);
+        const float v = __uint_as_float(e.z) * a0 + __uint_as_float(e.w) * a1;
+        st.push1(v * p.alpha, dvt[d0]);
+    }
+    if (active) disp_out[(size_t)b * p.H * p.W + (size_t)y * p.W + x] = st.result();
+}
+
 // stand-alone soft-argmin over a materialised cost [B,D,H,W]; one thread per pixel, 8 loads in
 // flight per thread, coalesced across x.
 template <bool PER_PIXEL>
@@ -384,6 +466,14 @@ extern "C" int dmb_b200_upsample_regress(const float* cost_low, const float* up_
 #define DMB_LAUNCH_UP(M, WC, RG) \
     upsample_regress_kernel<M, WC, RG><<<grid, 256, 0, s>>>(cost_low, up_weight, cost_out, disp_out, disp_values, p)
     const size_t tri_smem = (size_t)Dl * 256 * sizeof(float);
+    const size_t fast_smem = tri_smem + (size_t)D * 20;
+    if (mode == 0 && !cost_out && normalize && fast_smem <= 160 * 1024) {
+        if (fast_smem > 48 * 1024)
+            DMB_CUDA(cudaFuncSetAttribute(upsample_trilinear_regress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)fast_smem));
+        upsample_trilinear_regress_kernel<<<grid, 256, fast_smem, s>>>(cost_low, disp_out, disp_values, p);
+        return check_launch("upsample_trilinear_regress_kernel");
+    }
     if (mode == 0 && tri_smem <= 160 * 1024) {
 #define DMB_LAUNCH_TRI(WC, RG)                                                                                          \
     do {                                                                                                                \

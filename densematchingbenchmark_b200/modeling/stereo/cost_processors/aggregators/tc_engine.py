@@ -122,6 +122,14 @@ def _blob(layer, split, fp16):
     if w is None:
         w = F_.pack_conv_weight(layer.weight.detach(), isinstance(layer, torch.nn.ConvTranspose3d))
         b = layer.bias.detach().float().contiguous() if layer.bias is not None else None
+    blob, Cin, Cout, scale = pack_blob(w, kind, split, fp16)
+    val = (blob, b, Cin, Cout, scale, kind, w)      # `w` is kept alive so that id(w) stays unique
+    cache[mode] = (key, val)
+    return val
+
+
+def pack_blob(w, kind, split, fp16):
+    """w: packed fp32 weight [27,Cin,Cout] (ops.functional.pack_conv_weight) -> (tcgen05 blob, Cin, Cout, scale)."""
     K3, Cin, Cout = w.shape
     scale = 1.0
     if fp16:
@@ -134,14 +142,16 @@ def _blob(layer, split, fp16):
     blob = torch.empty(nbytes // 2, dtype=torch.float16 if fp16 else torch.bfloat16, device=w.device)
     C.call("dmb_b200_conv3d_tc_pack_weights", C.ptr(w), C.ptr(blob), Cin, Cout, 1 if split else 0,
            1 if fp16 else 0, float(scale), kind, C.stream(w.device))
-    val = (blob, b, Cin, Cout, scale, kind, w)      # `w` is kept alive so that id(w) stays unique
-    cache[mode] = (key, val)
-    return val
+    return blob, Cin, Cout, scale
 
 
 def conv_tc(layer, x, residual=None, relu=False, res_f32=None):
     """x: Blocked.  Returns Blocked (Cout % 32 == 0) or a float32 [B,1,D,H,W] tensor (Cout == 1)."""
     blob, bias, Cin, Cout, scale, kind, _ = _blob(layer, x.split, x.fp16)
+    return conv_tc_raw(x, blob, bias, Cin, Cout, scale, kind, residual, relu, res_f32)
+
+
+def conv_tc_raw(x, blob, bias, Cin, Cout, scale, kind, residual=None, relu=False, res_f32=None):
     if Cin != x.C:
         raise ValueError("layer expects %d input channels, activation has %d" % (Cin, x.C))
     D, H, W = x.dims
@@ -164,6 +174,79 @@ def conv_tc(layer, x, residual=None, relu=False, res_f32=None):
            C.ptr(residual.hi) if residual is not None else None,
            C.ptr(residual.lo) if residual is not None else None,
            C.ptr(y.hi), C.ptr(y.lo), Cout, None, None, x.B, D, H, W, kind, 1 if relu else 0, fp16, C.stream(dev))
+    return y
+
+
+def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False):
+    """One 3x3x3 / pad 1 convolution (stride 1 | stride 2 | transposed stride 2 with output_padding 1) of a float32
+    NCDHW tensor on the tcgen05 kernels: layout conversion in, conv, layout conversion out.  Used by the training
+    path (ops/autograd.py), whose weights change every step -- nothing is cached.  Returns float32 NCDHW."""
+    split, fp16 = PRECISIONS[precision]
+    kind = 2 if transposed else ((3 if KW_MERGE else 0) if stride == 1 else (4 if KW_MERGE else 1))
+    blob, Cin, Cout, scale = pack_blob(w_packed, kind, split, fp16)
+    xb = Blocked.from_ncdhw(x, split, fp16)
+    if Cout == 1:
+        return conv_tc_raw(xb, blob, bias, Cin, Cout, scale, kind, None, relu, residual)
+    rb = Blocked.from_ncdhw(residual, split, fp16) if residual is not None else None
+    return conv_tc_raw(xb, blob, bias, Cin, Cout, scale, kind, rb, relu).to_ncdhw()
+
+
+def conv3d_tc_eligible(x, Cin, Cout, ksize, stride, pad, transposed, opad, out_dims=None):
+    """Geometry the tcgen05 kernels implement (see _kind_of) on a CUDA tensor of an sm_100 device."""
+    if not x.is_cuda or tuple(ksize) != (3, 3, 3) or pad != 1 or Cin % 32 or not (Cout % 32 == 0 or Cout == 1):
+        return False
+    dims = tuple(x.shape[2:])
+    if transposed:
+        if stride != 2 or Cout == 1:
+            return False
+        want = tuple(2 * n for n in dims)
+        if out_dims is not None:
+            if tuple(int(v) for v in out_dims) != want:
+                return False
+        elif opad != 1:
+            return False
+    elif stride == 2:
+        if any(n % 2 for n in dims) or Cout == 1:
+            return False
+    elif stride != 1:
+        return False
+    return tc_available()
+
+
+# 32->1 classifier heads: fused into the epilogue of the preceding 32->32 layer + a 27-term gather
+# (DMB_B200_TC_FUSED_HEAD=0: the head as its own tensor-core launch, kept for A/B)
+FUSED_HEAD = os.environ.get("DMB_B200_TC_FUSED_HEAD", "1") != "0"
+
+
+def _head_weight(conv):
+    """Conv3d(32,1,3,1,1,bias=False) weight as [27][32] float32, cached until the parameter changes."""
+    cache = conv.__dict__.setdefault("_dmb_b200_head_cache", {})
+    key = (conv.weight.data_ptr(), conv.weight._version)
+    if cache.get("key") != key:
+        w = F_.pack_conv_weight(conv.weight.detach(), False)           # [27, 32, 1]
+        cache["w"] = w.reshape(w.shape[0], w.shape[1]).contiguous()
+        cache["key"] = key
+    return cache["w"]
+
+
+def classif_head(seq, x, res_f32=None):
+    """classifN = Sequential(conv3d_bn_relu(32,32), Conv3d(32,1)) (+ the previous cost) -> float32 [B,1,D,H,W]."""
+    unit, conv = seq[0], seq[1]
+    fusable = (FUSED_HEAD and KW_MERGE and x.C == 32 and conv.bias is None and conv.out_channels == 1
+               and conv.in_channels == 32 and _kind_of(unit) == 3 and _kind_of(conv) == 3)
+    if not fusable:
+        return conv_tc(conv, _unit(unit, x), res_f32=res_f32)
+    if unit.training and unit.bn is not None:
+        raise NotImplementedError("training-mode BatchNorm is not implemented on the tcgen05 path")
+    blob, bias, Cin, Cout, scale, kind, _ = _blob(unit, x.split, x.fp16)
+    D, H, W = x.dims
+    dev = x.hi.device
+    taps = torch.empty(x.B, 27, D, H, W, dtype=torch.float32, device=dev)
+    C.call("dmb_b200_conv3d_tc_head", C.ptr(x.hi), C.ptr(x.lo), C.ptr(blob), float(scale), C.ptr(bias),
+           C.ptr(_head_weight(conv)), C.ptr(taps), x.B, D, H, W, 1 if unit._has_relu else 0, 1 if x.fp16 else 0,
+           C.stream(dev))
+    y = torch.empty(x.B, 1, D, H, W, dtype=torch.float32, device=dev)
+    C.call("dmb_b200_head_gather", C.ptr(taps), C.ptr(res_f32), C.ptr(y), x.B, D, H, W, C.stream(dev))
     return y
 
 
@@ -208,7 +291,7 @@ def run_trunk_tc(trunk, raw_cost):
     out1, pre1, post1 = _hourglass(trunk.dres2, cost0, None, None, cost0)
     out2, pre2, post2 = _hourglass(trunk.dres3, out1, pre1, post1, cost0)
     out3, pre3, post3 = _hourglass(trunk.dres4, out2, pre2, post2, cost0)
-    cost1 = conv_tc(trunk.classif1[1], _unit(trunk.classif1[0], out1))
-    cost2 = conv_tc(trunk.classif2[1], _unit(trunk.classif2[0], out2), res_f32=cost1)
-    cost3 = conv_tc(trunk.classif3[1], _unit(trunk.classif3[0], out3), res_f32=cost2)
+    cost1 = classif_head(trunk.classif1, out1)
+    cost2 = classif_head(trunk.classif2, out2, res_f32=cost1)
+    cost3 = classif_head(trunk.classif3, out3, res_f32=cost2)
     return cost1, cost2, cost3

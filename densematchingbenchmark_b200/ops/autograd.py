@@ -9,11 +9,38 @@ AcfNet.py:55-57,81-83), FasterSoftArgmin / SoftArgmin (disp_predictors/*.py) and
 (cost_processors/utils/cat_fms.py:7-48).  Synchronised BatchNorm (dmb/apis/train.py:95-97 converts the
 model with apex) = all-reducing the raw per-channel sums between the two passes of each direction.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
 from .. import _cabi as C
 from . import functional as F_
+
+# Training convolutions (forward and input gradient) run on the tcgen05 kernels whenever the layer geometry
+# allows it (3x3x3, pad 1, stride 1 / 2 / transposed 2, Cin % 32 == 0, Cout % 32 == 0 or 1); everything else
+# uses the fp32 SIMT kernel.  Forward: split IEEE-half arithmetic (fp32-grade, DESIGN.md section 3).  Input
+# gradients: split bfloat16 (full fp32 exponent range -- gradients can be arbitrarily small -- at ~2^-16
+# relative precision).  DMB_B200_TRAIN_TC=0 forces the SIMT kernels (A/B and the reference for the tests).
+TRAIN_TC = os.environ.get("DMB_B200_TRAIN_TC", "1") != "0"
+TRAIN_TC_FWD = "fp16x3"
+TRAIN_TC_BWD = "bf16x3"
+
+
+def _conv(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, relu, out_dims=None, precision=None):
+    """y = act(conv(x) + bias + residual) for the training path: tcgen05 if eligible, else conv3d_direct."""
+    if TRAIN_TC and precision is not None:
+        from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
+        K3, Cin, Cout = w_packed.shape
+        if transposed and stride == 1 and tuple(ksize) == (3, 3, 3) and pad == 1 and \
+                (out_dims is None or tuple(int(v) for v in out_dims) == tuple(x.shape[2:])):
+            # a stride-1 transposed convolution is the plain convolution with the taps mirrored
+            if T.conv3d_tc_eligible(x, Cin, Cout, ksize, 1, pad, False, 0):
+                return T.conv3d_ncdhw_tc(x, w_packed.flip(0).contiguous(), bias, 1, False, precision, residual, relu)
+        elif T.conv3d_tc_eligible(x, Cin, Cout, ksize, stride, pad, transposed, opad, out_dims):
+            return T.conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual, relu)
+    return F_.conv3d_fused(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, relu=relu,
+                           out_dims=out_dims)
 
 
 def _sync_world(group):
@@ -30,7 +57,8 @@ def _dgrad(dz, weight, transposed, ksize, stride, pad, x_dims):
     """Gradient w.r.t. the conv input = the forward kernel with the weight's roles swapped:
     Conv3d weight [Cout,Cin,k] read as a ConvTranspose3d weight (in=Cout, out=Cin), and vice versa."""
     w = F_.pack_conv_weight(weight.detach(), transposed=not transposed)
-    return F_.conv3d_fused(dz, w, None, ksize, stride, pad, transposed=not transposed, out_dims=x_dims)
+    return _conv(dz, w, None, ksize, stride, pad, not transposed, 0, None, False, out_dims=x_dims,
+                 precision=TRAIN_TC_BWD)
 
 
 def _wgrad(x, dz, transposed, ksize, stride, pad, weight_shape):
@@ -63,10 +91,10 @@ class ConvUnitFn(torch.autograd.Function):
         ctx.has_res = residual is not None
         ctx.x_dims = tuple(x.shape[2:])
         if bn is None:
-            y = F_.conv3d_fused(x, w_packed, b, ksize, stride, pad, transposed, opad, res, relu=relu)
+            y = _conv(x, w_packed, b, ksize, stride, pad, transposed, opad, res, relu, precision=TRAIN_TC_FWD)
             ctx.save_for_backward(x, weight, y if relu else None, None, None, None, None)
             return y
-        z = F_.conv3d_fused(x, w_packed, b, ksize, stride, pad, transposed, opad, None, relu=False)
+        z = _conv(x, w_packed, b, ksize, stride, pad, transposed, opad, None, False, precision=TRAIN_TC_FWD)
         B, Co = z.shape[:2]
         S = z.numel() // (B * Co)
         dev = z.device

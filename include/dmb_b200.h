@@ -173,6 +173,16 @@ int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* 
                        const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
                        float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind, int relu, int fp16,
                        void* stream);
+/* Fused classifier head (replaces the nn.Sequential(conv3d_bn_relu(32,32), Conv3d(32,1,3,1,1,bias=False)) of
+ * aggregators/PSMNet.py:41-52 / AcfNet.py:43-53): the 32->32 stride-1 layer (w_blob packed for kind 3, BatchNorm
+ * folded, bias or NULL) runs on tcgen05 and its epilogue writes, instead of the activation a, the 27 per-tap
+ * projections head_t[b][tap][d][h][w] = sum_c relu?(a[c]) * head_w[tap][c] (float32, head_w = the Conv3d(32,1)
+ * weight as [27][32]).  dmb_b200_head_gather then forms y[b,d,h,w] = res? + sum_tap head_t[b][tap][d+kd-1][h+kh-1]
+ * [w+kw-1] (zero padding): the 32->1 convolution as one streaming pass instead of a second tensor-core launch. */
+int dmb_b200_conv3d_tc_head(const void* x_hi, const void* x_lo, const void* w_blob, float w_scale, const float* bias,
+                            const float* head_w, float* head_t, int B, int D, int H, int W, int relu, int fp16,
+                            void* stream);
+int dmb_b200_head_gather(const float* head_t, const float* res, float* y, int B, int D, int H, int W, void* stream);
 /* w_packed: [27][Cin][Cout] float32 (the conv3d_direct packing; for kind 2 the ConvTranspose3d
  * weight packed the same way, un-flipped) -> w_blob (16-bit), one [27][cbk][32|64][8] block per
  * (32 out, 8*cbk in) channel pair; split=1 stores hi rows then lo rows.  `scale` (a power of two)

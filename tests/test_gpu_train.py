@@ -262,6 +262,45 @@ def test_train_step_vs_reference_golden_and_oracle(P, golden_dir, kind):
         close(params[k].grad, g, 3e-3, k)
 
 
+def test_training_convs_run_on_tcgen05(P, monkeypatch):
+    """Forward and input-gradient convolutions of a training step take the tensor-core kernels wherever the layer
+    geometry allows (all 25 trunk units + 3 heads forward; every dgrad except the 1->32 heads'), and the result
+    agrees with the SIMT fp32 kernels (DMB_B200_TRAIN_TC=0 behaviour) at the documented precision."""
+    from densematchingbenchmark_b200.ops import autograd as A
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators import tc_engine as T
+    if not T.tc_available():
+        pytest.skip("tcgen05 path unavailable on this device")
+    calls = []
+    real = T.conv3d_ncdhw_tc
+
+    def counting(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False):
+        calls.append((tuple(w_packed.shape[1:]), stride, transposed, precision))
+        return real(x, w_packed, bias, stride, transposed, precision, residual, relu)
+
+    monkeypatch.setattr(T, "conv3d_ncdhw_tc", counting)
+    from make_golden import TRAIN_CASE
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=TRAIN_CASE["seed"])
+    l, r, gt = train_inputs()
+    proc, loss, disps, dl, dr, _ = run_train_step(P, "PSMNet", sd, l, r, gt, TRAIN_CASE)
+    fwd = [c for c in calls if c[3] == A.TRAIN_TC_FWD]
+    bwd = [c for c in calls if c[3] == A.TRAIN_TC_BWD]
+    assert len(fwd) == 4 + 3 * 6 + 3 * 2, len(fwd)          # dres0/1, three hourglasses, classif units + heads
+    assert len(bwd) == 4 + 3 * 6 + 3, len(bwd)              # every dgrad but the three 1->32 head dgrads
+    g_tc = {k: p.grad.clone() for k, p in proc.aggregator.named_parameters()}
+    monkeypatch.setattr(A, "TRAIN_TC", False)
+    n = len(calls)
+    proc2, loss2, disps2, dl2, dr2, _ = run_train_step(P, "PSMNet", sd, l, r, gt, TRAIN_CASE)
+    assert len(calls) == n
+    assert abs(float(loss) - float(loss2)) < 1e-5 * abs(float(loss2))
+    for a, b in zip(disps, disps2):
+        assert float((a - b).abs().max()) < 1e-3
+    close(dl, dl2.cpu(), 2e-3, "dleft tc vs simt")
+    for k, p in proc2.aggregator.named_parameters():
+        if k.endswith(".0.bias"):
+            continue
+        close(g_tc[k], p.grad.cpu(), 3e-3, k)
+
+
 def test_train_mode_is_not_the_inference_engine(P):
     """train() must never route through the BN-folded tensor-core trunk (it uses running statistics)."""
     cfg = _cfg(P, "PSMNet", 8, 32)
