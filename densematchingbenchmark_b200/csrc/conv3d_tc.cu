@@ -43,7 +43,7 @@ constexpr int NB = 32;                      // output channels per pass
 constexpr int TAPS = 27;
 // threads: warp 0 = TMA producer, warp 1 = MMA issuer, then 4 epilogue warps (8 for the transposed
 // kernel, whose tiles carry 8 output parity classes = 8x the epilogue work per MMA tile)
-__host__ __device__ constexpr int nthreads_of(int kind) { return kind == 2 ? 320 : 192; }
+__host__ __device__ constexpr int nthreads_of(int kind, bool head = false) { return (kind == 2 || head) ? 320 : 192; }
 // depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
 // work-item boundaries)
 __host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 5 : (kind == 4 ? 3 : 4); }
@@ -120,8 +120,8 @@ struct Params {
     // fused classifier head (KIND 3 only): instead of storing the 32-channel activation a, the epilogue
     // writes its 27 per-tap projections T[tap][voxel] = sum_c a[c] * head_w[tap][c]; the 32->1 3x3x3
     // convolution that follows is then a 27-term gather (head_gather_kernel)
-    const float* head_w;       // [27][32] fp32 or null
-    float* head_t;             // [B][27][Do][Ho][Wo] fp32
+    const float* head_w;       // [27][32] fp32 (device) or null
+    float* head_t;             // [B][27][Do][Ho][Wo] fp32 (null: ordinary layer)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -226,7 +226,7 @@ struct Smem {
     static constexpr int NST = nstage_of(KIND);
     static constexpr int PLANES_OFF = W_BYTES;
     static constexpr int BAR_OFF = PLANES_OFF + NST * STAGE_BYTES;
-    static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [27][32] fp32 head weights (KIND 3)
+    static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [27][32] fp32 head weights (KIND 3 head variant)
     static constexpr int TOTAL = HEAD_OFF + (KIND == 3 ? TAPS * NB * 4 : 0);
     static constexpr uint32_t LBO_B = ROWS * 16;
     static constexpr uint32_t SBO_B = 128;
@@ -317,8 +317,11 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
     }
 }
 
-// fused classifier head: bias + ReLU, then the 27 per-tap projections of the voxel's 32 channels
-// (fp32 FMAs on the un-rounded activation), one coalesced fp32 store per tap plane
+// fused classifier head: bias + ReLU, then the per-tap projections of the voxel's 32 channels for taps
+// [T0, T1) (fp32 FMAs on the un-rounded activation; weights broadcast from shared memory), one coalesced fp32
+// store per tap plane.  Three taps x four partial sums = 12 independent FMA chains: the epilogue warp is alone
+// on its scheduler, so instruction-level parallelism is what hides the FMA / shared-load latency.
+template <int T0, int T1>
 __device__ __forceinline__ void store_head(const Params& p, float (&v)[NB], const float (&bias)[NB],
                                            const float4* __restrict__ hw, int b, int d, int h, int w) {
     const size_t vol = (size_t)p.Do * p.Ho * p.Wo;
@@ -329,22 +332,26 @@ __device__ __forceinline__ void store_head(const Params& p, float (&v)[NB], cons
         if (p.relu) v[c] = fmaxf(v[c], 0.f);
     }
 #pragma unroll
-    for (int tap = 0; tap < TAPS; ++tap) {
-        float a0 = 0.f, a1 = 0.f;
+    for (int g = T0; g < T1; g += 3) {
+        float acc[3][4];
 #pragma unroll
-        for (int c4 = 0; c4 < NB / 4; c4 += 2) {
-            const float4 w0 = hw[tap * (NB / 4) + c4];
-            const float4 w1 = hw[tap * (NB / 4) + c4 + 1];
-            a0 = fmaf(v[4 * c4 + 0], w0.x, a0);
-            a0 = fmaf(v[4 * c4 + 1], w0.y, a0);
-            a0 = fmaf(v[4 * c4 + 2], w0.z, a0);
-            a0 = fmaf(v[4 * c4 + 3], w0.w, a0);
-            a1 = fmaf(v[4 * c4 + 4], w1.x, a1);
-            a1 = fmaf(v[4 * c4 + 5], w1.y, a1);
-            a1 = fmaf(v[4 * c4 + 6], w1.z, a1);
-            a1 = fmaf(v[4 * c4 + 7], w1.w, a1);
+        for (int j = 0; j < 3; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+#pragma unroll
+        for (int c4 = 0; c4 < NB / 4; ++c4) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (g + j < T1) {
+                    const float4 wv = hw[(g + j) * (NB / 4) + c4];
+                    acc[j][0] = fmaf(v[4 * c4 + 0], wv.x, acc[j][0]);
+                    acc[j][1] = fmaf(v[4 * c4 + 1], wv.y, acc[j][1]);
+                    acc[j][2] = fmaf(v[4 * c4 + 2], wv.z, acc[j][2]);
+                    acc[j][3] = fmaf(v[4 * c4 + 3], wv.w, acc[j][3]);
+                }
+            }
         }
-        t[(size_t)tap * vol] = a0 + a1;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (g + j < T1) t[(size_t)(g + j) * vol] = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
     }
 }
 
@@ -384,13 +391,14 @@ __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restric
     y[i] = o;
 }
 
-template <int KIND, bool SPLIT, bool FP16>
-__global__ void __launch_bounds__(nthreads_of(KIND), 1)
+template <int KIND, bool SPLIT, bool FP16, bool HEAD>
+__global__ void __launch_bounds__(nthreads_of(KIND, HEAD), 1)
 conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+    static_assert(!HEAD || KIND == 3, "the fused classifier head exists for the stride-1 kernel only");
     using S = Smem<KIND, SPLIT>;
     constexpr int CBK = S::CBK;
     constexpr int NSTAGE = S::NST;
-    constexpr int EPI_WARPS = nthreads_of(KIND) / 32 - 2;
+    constexpr int EPI_WARPS = nthreads_of(KIND, HEAD) / 32 - 2;
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* w_smem = smem;
     unsigned char* planes = smem + S::PLANES_OFF;
@@ -404,7 +412,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    if (KIND == 3 && p.head_w) {
+    if (HEAD) {
         float* hw = reinterpret_cast<float*>(smem + S::HEAD_OFF);
         for (int i = threadIdx.x; i < TAPS * NB; i += blockDim.x) hw[i] = __ldg(p.head_w + i);
     }
@@ -826,9 +834,12 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                     ++t;
                     if (valid) {
-                        if (KIND == 3 && p.head_t)
-                            store_head(p, v, bias, reinterpret_cast<const float4*>(smem + S::HEAD_OFF), it.b, d, h, w);
-                        else
+                        if constexpr (HEAD) {
+                            // two warps per TMEM lane quarter: warps 2..5 project taps 0..13, warps 6..9 taps 14..26
+                            const float4* hw4 = reinterpret_cast<const float4*>(smem + S::HEAD_OFF);
+                            if (warp < 6) store_head<0, 14>(p, v, bias, hw4, it.b, d, h, w);
+                            else store_head<14, TAPS>(p, v, bias, hw4, it.b, d, h, w);
+                        } else
                             store_voxel<FP16>(p, v, bias, it.b, d, h, w);
                     }
                 } else if (KIND != 2) {
@@ -1027,9 +1038,17 @@ static int device_ok() {
 template <int KIND, bool SPLIT, bool FP16>
 static int launch_pass(const Maps& maps, const Params& p, int grid, void* stream) {
     const size_t smem = Smem<KIND, SPLIT>::TOTAL;
-    DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KIND, SPLIT, FP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv3d_tc_kernel<KIND, SPLIT, FP16><<<grid, nthreads_of(KIND), smem, as_stream(stream)>>>(maps, p);
+    DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<KIND, SPLIT, FP16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_tc_kernel<KIND, SPLIT, FP16, false><<<grid, nthreads_of(KIND), smem, as_stream(stream)>>>(maps, p);
     return check_launch("conv3d_tc_kernel");
+}
+
+template <bool SPLIT, bool FP16>
+static int launch_head(const Maps& maps, const Params& p, int grid, void* stream) {
+    const size_t smem = Smem<3, SPLIT>::TOTAL;
+    DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<3, SPLIT, FP16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv3d_tc_kernel<3, SPLIT, FP16, true><<<grid, nthreads_of(3, true), smem, as_stream(stream)>>>(maps, p);
+    return check_launch("conv3d_tc_kernel<head>");
 }
 
 template <int KIND>
@@ -1203,7 +1222,12 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
                     p.res_lo = p.y_lo;
                     p.res_f32 = p.y_f32;
                 }
-                if (kind == 0) rc = launch_kind<0>(maps, p, grid, split, fp16, stream);
+                if (head) {
+                    rc = split ? (fp16 ? launch_head<true, true>(maps, p, grid, stream)
+                                       : launch_head<true, false>(maps, p, grid, stream))
+                               : (fp16 ? launch_head<false, true>(maps, p, grid, stream)
+                                       : launch_head<false, false>(maps, p, grid, stream));
+                } else if (kind == 0) rc = launch_kind<0>(maps, p, grid, split, fp16, stream);
                 else if (kind == 1) rc = launch_kind<1>(maps, p, grid, split, fp16, stream);
                 else if (kind == 2) rc = launch_kind<2>(maps, p, grid, split, fp16, stream);
                 else if (kind == 3) rc = launch_kind<3>(maps, p, grid, split, fp16, stream);

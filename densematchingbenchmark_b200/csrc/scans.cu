@@ -5,6 +5,9 @@
 // row on the legacy stream); here ONE launch per call, one CTA per (n,c) plane marching over the
 // scan axis with the previous line kept in shared memory.
 // SGA / LGA have no reference code; semantics = oracle/dmb_oracle.py.
+#include <stdint.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dmb {
@@ -422,6 +425,176 @@ __global__ void __launch_bounds__(128) sga_horizontal_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------
+// SGA, register-resident kernels (D <= 128 / 64): a group of G adjacent lanes owns one scan line and each lane
+// keeps DPL consecutive disparities of the running aggregate in registers, so the recurrence needs no shared
+// memory and no barrier: d-1 / d+1 across the lane boundary are two shuffles, the max over d is a local max
+// plus log2(G) xor-shuffles.  All HBM traffic is issued one step (vertical) or one 4-step chunk (horizontal)
+// ahead of its use, straight from global memory:
+//   vertical   (dir 2/3): lanes run along x -> every load/store instruction covers G row segments of 128/G bytes;
+//   horizontal (dir 0/1): lanes run along y, a lane moves 16 bytes (4 scan steps) per disparity and chunk; the
+//                         second half of each 32-byte sector is consumed one chunk later out of L1.
+// ---------------------------------------------------------------------------------------
+template <int DPL, int G>
+__device__ __forceinline__ void sga_lane_step(float (&A)[DPL], const float (&xv)[DPL], float (&w)[5], bool started,
+                                              int q, int dbase, int D, float (&cur)[DPL]) {
+    float nrm = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nrm += fabsf(w[k]);
+    const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) w[k] *= inv;
+    float below = __shfl_up_sync(0xffffffffu, A[DPL - 1], 1);      // A(p-r, dbase-1)
+    float above = __shfl_down_sync(0xffffffffu, A[0], 1);          // A(p-r, dbase+DPL)
+    if (q == 0) below = 0.f;
+    if (q == G - 1) above = 0.f;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < DPL; ++j)
+        if (dbase + j < D) mx = fmaxf(mx, A[j]);
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) {
+        const int d = dbase + j;
+        float v = 0.f;
+        if (d < D) {
+            v = w[0] * xv[j];
+            if (started) {
+                const float dm = j > 0 ? A[j > 0 ? j - 1 : 0] : below;
+                const float dp = (d + 1 < D) ? (j < DPL - 1 ? A[j < DPL - 1 ? j + 1 : j] : above) : 0.f;
+                v += w[1] * A[j] + w[2] * dm + w[3] * dp + w[4] * mx;
+            }
+        }
+        cur[j] = v;
+    }
+}
+
+template <int DPL, int G>
+__global__ void __launch_bounds__(128) sga_v_lanes_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                          float* __restrict__ out, int C, int D, int H, int W, int dir,
+                                                          int first) {
+    constexpr int CPB = 128 / G;                              // columns per CTA
+    const int q = threadIdx.x % G;
+    const int col = blockIdx.x * CPB + threadIdx.x / G;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const bool colok = col < W;
+    const int dbase = q * DPL;
+    const size_t plane = (size_t)H * W;
+    const size_t base = ((size_t)(b * C + c) * D + dbase) * plane + (colok ? col : 0);
+    const float* xb = x + base;
+    float* ob = out + base;
+    const float* gb = guid + (((size_t)(b * 4 + dir) * 5) * C + c) * plane + (colok ? col : 0);
+    const size_t gk = (size_t)C * plane;
+    const bool rev = dir == 3;
+    float A[DPL], xn[DPL], on[DPL], wn[5];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) A[j] = 0.f;
+    auto fetch = [&](int step) {
+        const size_t row = (size_t)(rev ? H - 1 - step : step) * W;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) wn[k] = colok ? __ldg(gb + k * gk + row) : 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            const bool ok = colok && dbase + j < D;
+            xn[j] = ok ? __ldcs(xb + (size_t)j * plane + row) : 0.f;
+            on[j] = (ok && !first) ? __ldcs(ob + (size_t)j * plane + row) : -INFINITY;
+        }
+    };
+    fetch(0);
+    for (int step = 0; step < H; ++step) {
+        const size_t row = (size_t)(rev ? H - 1 - step : step) * W;
+        float xv[DPL], ov[DPL], w[5], cur[DPL];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) w[k] = wn[k];
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            xv[j] = xn[j];
+            ov[j] = on[j];
+        }
+        if (step + 1 < H) fetch(step + 1);
+        sga_lane_step<DPL, G>(A, xv, w, step > 0, q, dbase, D, cur);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            if (colok && dbase + j < D) ob[(size_t)j * plane + row] = fmaxf(ov[j], cur[j]);   // ov = -inf when first
+            A[j] = cur[j];
+        }
+    }
+}
+
+template <int DPL, int G, bool REV>
+__global__ void __launch_bounds__(128) sga_h_lanes_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                          float* __restrict__ out, int C, int D, int H, int W, int dir,
+                                                          int first) {
+    constexpr int RPB = 128 / G;                              // rows per CTA
+    const int q = threadIdx.x % G;
+    const int rowi = blockIdx.x * RPB + threadIdx.x / G;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const bool rowok = rowi < H;
+    const int dbase = q * DPL;
+    const size_t plane = (size_t)H * W;
+    const size_t base = ((size_t)(b * C + c) * D + dbase) * plane + (size_t)(rowok ? rowi : 0) * W;
+    const float* xb = x + base;
+    float* ob = out + base;
+    const float* gb = guid + (((size_t)(b * 4 + dir) * 5) * C + c) * plane + (size_t)(rowok ? rowi : 0) * W;
+    const size_t gk = (size_t)C * plane;
+    const int nchunks = W / 4;                                // W % 4 == 0 (checked by the host)
+    float A[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) A[j] = 0.f;
+    float4 xn[DPL], wn[5];
+    auto fetch = [&](int ci) {
+        const int t0 = 4 * ci;
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            wn[k] = rowok ? __ldg(reinterpret_cast<const float4*>(gb + k * gk + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+            xn[j] = (rowok && dbase + j < D) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * plane + t0))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    fetch(REV ? nchunks - 1 : 0);
+    bool started = false;
+    for (int i = 0; i < nchunks; ++i) {
+        const int t0 = 4 * (REV ? nchunks - 1 - i : i);
+        float xc[DPL][4], oc[DPL][4], wc[5][4];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            wc[k][0] = wn[k].x; wc[k][1] = wn[k].y; wc[k][2] = wn[k].z; wc[k][3] = wn[k].w;
+        }
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            xc[j][0] = xn[j].x; xc[j][1] = xn[j].y; xc[j][2] = xn[j].z; xc[j][3] = xn[j].w;
+            float4 o = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (!first && rowok && dbase + j < D) o = *reinterpret_cast<const float4*>(ob + (size_t)j * plane + t0);
+            oc[j][0] = o.x; oc[j][1] = o.y; oc[j][2] = o.z; oc[j][3] = o.w;
+        }
+        if (i + 1 < nchunks) fetch(REV ? nchunks - 2 - i : i + 1);
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int e = REV ? 3 - s : s;                    // compile-time after unrolling
+            float xv[DPL], w[5], cur[DPL];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[k] = wc[k][e];
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) xv[j] = xc[j][e];
+            sga_lane_step<DPL, G>(A, xv, w, started, q, dbase, D, cur);
+            started = true;
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                oc[j][e] = fmaxf(oc[j][e], cur[j]);           // -inf for the first direction
+                A[j] = cur[j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+            if (rowok && dbase + j < D)
+                *reinterpret_cast<float4*>(ob + (size_t)j * plane + t0) = make_float4(oc[j][0], oc[j][1], oc[j][2], oc[j][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // LGA, radius 2 (5x5 window, 75 L1-normalised weights per pixel held in registers).
 // Tiled variant: a 32x8 pixel tile per CTA; the NEW depth plane (d+1) of the tile + halo is staged in
 // shared memory once per step (double buffered, one barrier per step, the global loads of plane d+2
@@ -497,17 +670,25 @@ __global__ void __launch_bounds__(256, 1) lga_r2_tiled_kernel(const float* __res
     // step(d, M, Cn, Pl): plane d+1 (slot (d+1)&1) -> Pl; out(d) = w0.Cn + w1.M + w2.Pl; stage plane d+2, prefetch d+3
     auto step = [&](int d, float (&M)[25], float (&Cn)[25], float (&Pl)[25]) {
         const float* tb = ((d + 1) & 1) ? tbase1 : tbase0;
-        float acc = 0.f;
+        // six independent accumulation chains (one 75-deep chain left the FMA pipe idle 3 cycles out of 4)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 5; ++kx) {
                 const int i = ky * 5 + kx;
                 Pl[i] = tb[ky * PW + kx];
-                acc = fmaf(w[i], Cn[i], acc);
-                acc = fmaf(w[25 + i], M[i], acc);
-                acc = fmaf(w[50 + i], Pl[i], acc);
+                if (i & 1) {
+                    b0 = fmaf(w[i], Cn[i], b0);
+                    b1 = fmaf(w[25 + i], M[i], b1);
+                    b2 = fmaf(w[50 + i], Pl[i], b2);
+                } else {
+                    a0 = fmaf(w[i], Cn[i], a0);
+                    a1 = fmaf(w[25 + i], M[i], a1);
+                    a2 = fmaf(w[50 + i], Pl[i], a2);
+                }
             }
+        const float acc = ((a0 + b0) + (a1 + b1)) + (a2 + b2);
         if (inside) st_cs_f(ob + (size_t)d * plane, acc);
         // slot d&1 held plane d (already consumed into registers one step ago): refill it with plane d+2
         stage(d & 1, pre);
@@ -619,8 +800,41 @@ extern "C" int dmb_b200_sga(const float* x, const float* guidance, float* out, i
     DMB_REQUIRE(C <= 65535 && B <= 65535, "sga: grid dimension too large");
     cudaStream_t s = as_stream(stream);
     const bool tiled = D <= 256;
+    static int lanes_mode = -1;                    // DMB_B200_SGA_LANES=0: the shared-memory tiled kernels (A/B)
+    if (lanes_mode < 0) {
+        const char* e = getenv("DMB_B200_SGA_LANES");
+        lanes_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(guidance) |
+                            reinterpret_cast<uintptr_t>(out)) % 16 == 0;
     for (int dir = 0; dir < 4; ++dir) {
         const int first = dir == 0 ? 1 : 0;
+        if (lanes_mode && dir < 2 && D <= 64 && W % 4 == 0 && aligned16) {
+            // horizontal, G = 8 lanes per row, DPL = ceil(D / 8) rounded up to 2 / 4 / 8
+            dim3 grid((unsigned)cdiv(H, 16), C, B);
+#define DMB_SGA_H(DPL)                                                                                              \
+    do {                                                                                                            \
+        if (dir == 1) sga_h_lanes_kernel<DPL, 8, true><<<grid, 128, 0, s>>>(x, guidance, out, C, D, H, W, dir, first); \
+        else sga_h_lanes_kernel<DPL, 8, false><<<grid, 128, 0, s>>>(x, guidance, out, C, D, H, W, dir, first);      \
+    } while (0)
+            if (D <= 16) DMB_SGA_H(2);
+            else if (D <= 32) DMB_SGA_H(4);
+            else DMB_SGA_H(8);
+#undef DMB_SGA_H
+            int rc = check_launch("sga_h_lanes_kernel");
+            if (rc) return rc;
+            continue;
+        }
+        if (lanes_mode && dir >= 2 && D <= 128) {
+            if (D <= 8) { dim3 grid((unsigned)cdiv(W, 64), C, B); sga_v_lanes_kernel<4, 2><<<grid, 128, 0, s>>>(x, guidance, out, C, D, H, W, dir, first); }
+            else if (D <= 16) { dim3 grid((unsigned)cdiv(W, 64), C, B); sga_v_lanes_kernel<8, 2><<<grid, 128, 0, s>>>(x, guidance, out, C, D, H, W, dir, first); }
+            else if (D <= 32) { dim3 grid((unsigned)cdiv(W, 64), C, B); sga_v_lanes_kernel<16, 2><<<grid, 128, 0, s>>>(x, guidance, out, C, D, H, W, dir, first); }
+            else if (D <= 64) { dim3 grid((unsigned)cdiv(W, 32), C, B); sga_v_lanes_kernel<16, 4><<<grid, 128, 0, s>>>(x, guidance, out, C, D, H, W, dir, first); }
+            else { dim3 grid((unsigned)cdiv(W, 32), C, B); sga_v_lanes_kernel<32, 4><<<grid, 128, 0, s>>>(x, guidance, out, C, D, H, W, dir, first); }
+            int rc = check_launch("sga_v_lanes_kernel");
+            if (rc) return rc;
+            continue;
+        }
         if (tiled && dir < 2) {
             const int nj = (D + 31) / 32;
             int rc = 0;

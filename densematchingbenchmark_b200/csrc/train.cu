@@ -344,25 +344,64 @@ __global__ void __launch_bounds__(WG_THREADS, 1) conv3d_wgrad_k3_kernel(const fl
 }
 
 // weight gradient of AcfNet's learned upsampling ConvTranspose3d(1, 1, 8, stride 4, pad 2):
-// dw[k] += sum_i low[i] * dfull[4 i - 2 + k].  512 threads = the 512 taps; CTAs stride over source voxels.
+// dw[k] += sum_i low[i] * dfull[4 i - 2 + k].  Output-stationary: every dfull element is read exactly once
+// (coalesced, the 400 MB stream that bounds the kernel); per dimension an output index o pairs with the two
+// taps k = r, r + 4 (r = (o + 2) & 3) and the sources i = (o + 2) >> 2, i - 1, so a thread whose (od, oh, ow)
+// keep their residues mod 4 owns 8 fixed taps: 8 register accumulators for the whole kernel, one shared-memory
+// and one global atomic round at the end.  CTA = 128 (w) x 4 (h) threads, blockIdx.y = od & 3.
 __global__ void __launch_bounds__(512) wgrad_up8_kernel(const float* __restrict__ low, const float* __restrict__ dfull,
                                                         float* __restrict__ dw, int B, int Dl, int Hl, int Wl, int D,
                                                         int H, int W) {
-    const int kd = threadIdx.x >> 6, kh = (threadIdx.x >> 3) & 7, kw = threadIdx.x & 7;
-    const long long n = (long long)B * Dl * Hl * Wl;
-    float acc = 0.f;
-    for (long long v = blockIdx.x; v < n; v += gridDim.x) {
-        const int iw = (int)(v % Wl);
-        long long r = v / Wl;
-        const int ih = (int)(r % Hl);
+    __shared__ float bins[512];
+    const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+    bins[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int pd = blockIdx.y;
+    const int rd = (pd + 2) & 3, rh = (ty + 2) & 3, rw = (tx + 2) & 3;
+    const int wchunks = (W + 127) / 128;
+    const long long items = (long long)B * Dl * Hl * wchunks;      // D == 4 Dl, H == 4 Hl
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int wc = (int)(it % wchunks);
+        long long r = it / wchunks;
+        const int oh4 = (int)(r % Hl);
         r /= Hl;
-        const int id = (int)(r % Dl);
+        const int od4 = (int)(r % Dl);
         const int b = (int)(r / Dl);
-        const int od = 4 * id - 2 + kd, oh = 4 * ih - 2 + kh, ow = 4 * iw - 2 + kw;
-        if (od < 0 || od >= D || oh < 0 || oh >= H || ow < 0 || ow >= W) continue;
-        acc = fmaf(__ldg(low + v), __ldg(dfull + (((size_t)b * D + od) * H + oh) * W + ow), acc);
+        const int od = 4 * od4 + pd, oh = 4 * oh4 + ty, ow = wc * 128 + tx;
+        if (ow >= W) continue;
+        const float g = __ldcs(dfull + (((size_t)b * D + od) * H + oh) * W + ow);
+        const int ida = (od + 2) >> 2, iha = (oh + 2) >> 2, iwa = (ow + 2) >> 2;
+        const float* lb = low + (size_t)b * Dl * Hl * Wl;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int id = ida - a;
+            if (id < 0 || id >= Dl) continue;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int ih = iha - c;
+                if (ih < 0 || ih >= Hl) continue;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int iw = iwa - e;
+                    if (iw < 0 || iw >= Wl) continue;
+                    acc[(a * 2 + c) * 2 + e] = fmaf(__ldg(lb + ((size_t)id * Hl + ih) * Wl + iw), g, acc[(a * 2 + c) * 2 + e]);
+                }
+            }
+        }
     }
-    atomicAdd(dw + threadIdx.x, acc);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                atomicAdd(&bins[((rd + 4 * a) * 8 + (rh + 4 * c)) * 8 + (rw + 4 * e)], acc[(a * 2 + c) * 2 + e]);
+    __syncthreads();
+    const float v = bins[threadIdx.x];
+    if (v != 0.f) atomicAdd(dw + threadIdx.x, v);
 }
 
 // ---- trilinear upsampling backward (align_corners=True) ----------------------------------------
@@ -608,10 +647,11 @@ extern "C" int dmb_b200_upsample_deconv_wgrad(const float* cost_low, const float
     DMB_REQUIRE(cost_low && dcost && dw, "upsample_deconv_wgrad: null pointer");
     DMB_REQUIRE(B > 0 && Dl > 0 && Hl > 0 && Wl > 0, "upsample_deconv_wgrad: empty volume");
     DMB_REQUIRE(D == 4 * Dl && H == 4 * Hl && W == 4 * Wl, "upsample_deconv_wgrad: output must be 4x the input");
-    const long long n = (long long)B * Dl * Hl * Wl;
-    long long ctas = (long long)sm_count() * 4;
-    if (ctas > n) ctas = n;
-    wgrad_up8_kernel<<<(unsigned)ctas, 512, 0, as_stream(stream)>>>(cost_low, dcost, dw, B, Dl, Hl, Wl, D, H, W);
+    const long long items = (long long)B * Dl * Hl * ((W + 127) / 128);
+    long long ctas = (long long)sm_count();          // x 4 depth phases = 4 CTAs of 512 threads per SM
+    if (ctas > items) ctas = items;
+    dim3 grid((unsigned)ctas, 4, 1);
+    wgrad_up8_kernel<<<grid, 512, 0, as_stream(stream)>>>(cost_low, dcost, dw, B, Dl, Hl, Wl, D, H, W);
     return check_launch("wgrad_up8_kernel");
 }
 

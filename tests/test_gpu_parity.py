@@ -360,7 +360,11 @@ def test_spn_forward_backward_vs_oracle(P, shape):
                 torch.testing.assert_close(got.cpu(), w, atol=1e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("shape", [(1, 2, 6, 5, 7), (2, 3, 16, 9, 12), (1, 2, 70, 6, 10), (1, 1, 64, 19, 45), (1, 1, 300, 4, 6)])
+@pytest.mark.parametrize("shape", [(1, 2, 6, 5, 7), (2, 3, 16, 9, 12), (1, 2, 70, 6, 10), (1, 1, 64, 19, 45), (1, 1, 300, 4, 6),
+                                   # register-resident kernels: ragged D inside a lane group, rows / columns that do not
+                                   # fill a CTA, every DPL instantiation (D <= 16 / 32 / 64 horizontal, <= 8..128 vertical)
+                                   (1, 2, 20, 6, 16), (2, 2, 64, 9, 24), (1, 1, 37, 21, 8), (1, 1, 7, 3, 4), (1, 1, 100, 5, 40),
+                                   (1, 1, 33, 18, 72)])
 def test_sga_vs_oracle(P, shape):
     from densematchingbenchmark_b200.ops import SGA
     B, C, D, H, W = shape
