@@ -43,10 +43,12 @@ constexpr int NB = 32;                      // output channels per pass
 constexpr int TAPS = 27;
 // threads: warp 0 = TMA producer, warp 1 = MMA issuer, then 4 epilogue warps (8 for the transposed
 // kernel, whose tiles carry 8 output parity classes = 8x the epilogue work per MMA tile)
-__host__ __device__ constexpr int nthreads_of(int kind, bool head = false) { return (kind == 2 || head) ? 320 : 192; }
+__host__ __device__ constexpr int nthreads_of(int kind, bool head = false) { return (kind == 2 || kind == 5 || head) ? 320 : 192; }
+// output channels per pass: 32, except KIND 5 (16: all 64 input channels of the layer fit one pass instead)
+__host__ __device__ constexpr int nbo_of(int kind) { return kind == 5 ? 16 : 32; }
 // depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
 // work-item boundaries)
-__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 5 : (kind == 4 ? 3 : 4); }
+__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 5 : ((kind == 4 || kind == 5) ? 3 : 4); }
 constexpr int TMEM_COLS = 512;
 
 // KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane (reference kernel)
@@ -68,6 +70,14 @@ template <> struct Geo<1> {
 template <> struct Geo<2> {
     static constexpr int CBK = 4;
     static constexpr int PLANE_BYTES = 9856;                       // 4*17*9*16 = 9792, padded to 128
+};
+// KIND 5: the transposed conv with K = 64: one pass covers ALL input channels of a 64-channel layer and 16 output
+// channels (same 110 KB of weights as 32 x 32), so that a 64 -> 32 / 64 -> 64 layer runs as 2 / 4 passes that
+// each write their own output channels once -- instead of input-channel passes that read-modify-write the
+// output-resolution tensor in place (Hourglass conv6: 200 MB written, re-read and re-written per layer).
+template <> struct Geo<5> {
+    static constexpr int CBK = 8;
+    static constexpr int PLANE_BYTES = 8 * 17 * 9 * 16;            // 19584 = 153 * 128
 };
 // KIND 3: stride-1 conv with the three kw taps merged into the MMA's N dimension.  The 8 tile columns
 // are w0-1 .. w0+6; every MMA multiplies the UNSHIFTED column block with [W(kw=0)|W(kw=1)|W(kw=2)], the
@@ -163,6 +173,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor layout):
@@ -218,7 +229,8 @@ struct Smem {
     using G = Geo<KIND>;
     static constexpr int CBK = G::CBK;
     static constexpr int NKW = (KIND == 3 || KIND == 4) ? 3 : 1;   // kw taps merged into one B block
-    static constexpr int ROWS = (SPLIT ? 2 * NB : NB) * NKW;       // B-operand rows per channel block
+    static constexpr int NBO = nbo_of(KIND);                       // output channels per pass
+    static constexpr int ROWS = (SPLIT ? 2 * NBO : NBO) * NKW;     // B-operand rows per channel block
     static constexpr int TAP_BYTES = CBK * ROWS * 16;              // one B block (a tap, or a (kd,kh) tap row)
     static constexpr int W_BYTES = (TAPS / NKW) * TAP_BYTES;
     static constexpr int PLANE_BYTES = G::PLANE_BYTES;
@@ -237,9 +249,9 @@ struct Smem {
     static constexpr int KD_COLS = SPLIT ? 64 : 32;                // [hi*Whi | hi*Wlo] of one kd
     static constexpr int LH_COL = 3 * KD_COLS;                     // lo*Whi (split only)
     // KIND 2: one accumulator per output parity class (chains are <= 32 MMAs by construction)
-    static constexpr int CLS_COLS = SPLIT ? 64 : 32;
+    static constexpr int CLS_COLS = SPLIT ? 2 * NBO : NBO;
     static constexpr int ACC_COLS =
-        KIND == 2 ? 4 * CLS_COLS : ((KIND == 3 || KIND == 4) ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32));
+        (KIND == 2 || KIND == 5) ? 4 * CLS_COLS : ((KIND == 3 || KIND == 4) ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32));
     static_assert(2 * ACC_COLS <= TMEM_COLS, "accumulators exceed TMEM");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -264,7 +276,7 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
 }
 
 // bias + residual + ReLU + 16-bit (hi[,lo]) split + store of one output voxel's 32 channels
-template <bool FP16>
+template <bool FP16, int NCB = 4>
 __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], const float (&bias)[NB], int b, int d, int h,
                                             int w) {
     const size_t plane_sz = (size_t)p.Ho * p.Wo;
@@ -278,10 +290,10 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
         return;
     }
 #pragma unroll
-    for (int c = 0; c < NB; ++c) v[c] += bias[c];
+    for (int c = 0; c < 8 * NCB; ++c) v[c] += bias[c];
     if (p.res_hi) {
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
+        for (int cb = 0; cb < NCB; ++cb) {
             const size_t ri = ((size_t)(b * p.res_cbs + p.res_cb0 + cb) * p.Do) * plane_sz + vox;
             float f[8];
             unpack8<FP16>(__ldg(p.res_hi + ri), f);
@@ -296,10 +308,10 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
     }
     if (p.relu) {
 #pragma unroll
-        for (int c = 0; c < NB; ++c) v[c] = fmaxf(v[c], 0.f);
+        for (int c = 0; c < 8 * NCB; ++c) v[c] = fmaxf(v[c], 0.f);
     }
 #pragma unroll
-    for (int cb = 0; cb < 4; ++cb) {
+    for (int cb = 0; cb < NCB; ++cb) {
         const size_t yi = ((size_t)(b * p.y_cbs + p.y_cb0 + cb) * p.Do) * plane_sz + vox;
         float hi[8], lo[8];
 #pragma unroll
@@ -451,7 +463,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
                 const int nout = it.d1 - it.d0;
-                const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : ((KIND == 1 || KIND == 4) ? 2 * nout + 1 : nout + 1);
+                const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : ((KIND == 1 || KIND == 4) ? 2 * nout + 1 : nout + 1);   // KIND 2/5: nout + 1
                 const int pl0 = (KIND == 0 || KIND == 3) ? it.d0 - 1 : ((KIND == 1 || KIND == 4) ? 2 * it.d0 - 1 : it.d0);
                 for (int j = 0; j < nplanes; ++j, ++n) {
                     const int pl = pl0 + j;
@@ -480,7 +492,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             tma_load_5d(dst + S::PLANE_BYTES + Geo<4>::EVEN_BYTES, &maps.m[3], &full[slot], 8 * (it.w0 - 1),
                                         it.h0 - 1, pl, in_cb0_k4, it.b);
                         }
-                    } else if (KIND == 2) {
+                    } else if (KIND == 2 || KIND == 5) {
                         mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 17 * 9 * 16);
                         tma_load_5d(dst, &maps.m[0], &full[slot], 8 * it.w0, it.h0, pl, p.in_cb0, it.b);
                         if (SPLIT)
@@ -507,7 +519,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         // ================================ MMA issuer ==================================
         {
             constexpr uint32_t idesc_main = make_idesc(S::ROWS, FP16 ? 0u : 1u);
-            constexpr uint32_t idesc_lo = make_idesc(NB, FP16 ? 0u : 1u);
+            constexpr uint32_t idesc_lo = make_idesc(S::NBO, FP16 ? 0u : 1u);
             mbar_wait(wbar, 0);
             const uint32_t w_addr = smem_u32(w_smem);
             const uint32_t planes_addr = smem_u32(planes);
@@ -809,6 +821,16 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             for (int d = it.d0; d < it.d1; ++d) {
                 if (KIND == 3 || KIND == 4) {
                     const uint32_t buf = t & 1;
+                    if (!HEAD && p.res_hi && valid) {          // residual / in-place lines into L1 ahead of the accumulator
+                        const size_t plane_sz = (size_t)p.Ho * p.Wo;
+                        const size_t vox = (size_t)d * plane_sz + (size_t)h * p.Wo + w;
+#pragma unroll
+                        for (int cb = 0; cb < 4; ++cb) {
+                            const size_t ri = ((size_t)(it.b * p.res_cbs + p.res_cb0 + cb) * p.Do) * plane_sz + vox;
+                            prefetch_l1(p.res_hi + ri);
+                            if (p.res_lo) prefetch_l1(p.res_lo + ri);
+                        }
+                    }
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
                     tcgen05_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
@@ -842,7 +864,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                         } else
                             store_voxel<FP16>(p, v, bias, it.b, d, h, w);
                     }
-                } else if (KIND != 2) {
+                } else if (KIND != 2 && KIND != 5) {
                     const uint32_t buf = t & 1;
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
                     tcgen05_fence_after();
@@ -891,16 +913,39 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 } else {
 #pragma unroll 1
                     for (int rd = 0; rd < 2; ++rd, ++t) {
+                        const int cls0 = (warp - 2) >> 2;          // warps 2..5: classes 0,2; warps 6..9: classes 1,3
+                        // The residual (or, on an accumulating pass, the output itself) of this warp's two classes is
+                        // pulled into L1 while the MMAs of the tile are still running: the epilogue of the transposed
+                        // kernels was bound by the DRAM latency of these loads (one exposed round trip per class).
+                        if (p.res_hi && valid) {
+                            const size_t plane_sz = (size_t)p.Ho * p.Wo;
+#pragma unroll
+                            for (int ci = 0; ci < 2; ++ci) {
+                                const int cls = cls0 + 2 * ci;
+                                const size_t vox = (size_t)(2 * d + rd) * plane_sz + (size_t)(2 * h + (cls >> 1)) * p.Wo + 2 * w + (cls & 1);
+#pragma unroll
+                                for (int cb = 0; cb < (KIND == 5 ? 2 : 4); ++cb) {
+                                    const size_t ri = ((size_t)(it.b * p.res_cbs + p.res_cb0 + cb) * p.Do) * plane_sz + vox;
+                                    prefetch_l1(p.res_hi + ri);
+                                    if (p.res_lo) prefetch_l1(p.res_lo + ri);
+                                }
+                            }
+                        }
                         mbar_wait(&tfull[rd], (t >> 1) & 1);
                         tcgen05_fence_after();
                         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + rd * S::ACC_COLS;
-                        const int cls0 = (warp - 2) >> 2;          // warps 2..5: classes 0,2; warps 6..9: classes 1,3
 #pragma unroll 1
                         for (int cls = cls0; cls < 4; cls += 2) {
                             uint32_t r0[32];
                             float v[NB];
                             tmem_ld32(taddr + cls * S::CLS_COLS, r0);
-                            if (SPLIT) {
+                            if (SPLIT && KIND == 5) {
+                                // 16 output channels: [hi*Whi + lo*Whi | hi*Wlo] sit in one 32-column load
+                                tmem_ld_wait();
+#pragma unroll
+                                for (int c = 0; c < NB; ++c)
+                                    v[c] = c < 16 ? (__uint_as_float(r0[c]) + __uint_as_float(r0[(c & 15) + 16])) * p.acc_scale : 0.f;
+                            } else if (SPLIT) {
                                 uint32_t r1[32];
                                 tmem_ld32(taddr + cls * S::CLS_COLS + 32, r1);
                                 tmem_ld_wait();
@@ -916,7 +961,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                                 __syncwarp();
                                 if (lane == 0) mbar_arrive(&tempty[rd]);
                             }
-                            if (valid) store_voxel<FP16>(p, v, bias, it.b, 2 * d + rd, 2 * h + (cls >> 1), 2 * w + (cls & 1));
+                            if (valid) store_voxel<FP16, (KIND == 5 ? 2 : 4)>(p, v, bias, it.b, 2 * d + rd, 2 * h + (cls >> 1), 2 * w + (cls & 1));
                         }
                     }
                 }
@@ -937,11 +982,11 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
 // rows); one blob covers 8*cbk input channels x 32 output channels
 // nkw = 3 (KIND 3): a block covers one (kd,kh) tap row, rows = [hi kw0|hi kw1|hi kw2|lo kw0|lo kw1|lo kw2]
 __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int Cin, int Cout, int cbk,
-                                    int nkw, int split, int fp16, float scale) {
-    const int hi_rows = NB * nkw;
+                                    int nkw, int split, int fp16, float scale, int nb) {
+    const int hi_rows = nb * nkw;
     const int rows = split ? 2 * hi_rows : hi_rows;
     const int nblk = TAPS / nkw;
-    const int IB = Cin / (8 * cbk), OB = (Cout + 31) / 32;
+    const int IB = Cin / (8 * cbk), OB = (Cout + nb - 1) / nb;
     const size_t blob = (size_t)nblk * cbk * rows * 8;
     const size_t total = blob * IB * OB;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -954,8 +999,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, uint16_t* __res
         const int ob = r / IB;
         const bool is_lo = row >= hi_rows;
         const int rr = row % hi_rows;
-        const int tap = blk * nkw + rr / NB;
-        const int co = ob * 32 + (rr % NB);
+        const int tap = blk * nkw + rr / nb;
+        const int co = ob * nb + (rr % nb);
         const int ci = (ib * cbk + cb) * 8 + e;
         const float v = (co < Cout) ? w[((size_t)tap * Cin + ci) * Cout + co] * scale : 0.f;
         if (fp16) {
@@ -1058,7 +1103,7 @@ static int launch_kind(const Maps& maps, const Params& p, int grid, bool split, 
     return fp16 ? launch_pass<KIND, false, true>(maps, p, grid, stream) : launch_pass<KIND, false, false>(maps, p, grid, stream);
 }
 
-static int cbk_of(int kind) { return kind == 1 ? Geo<1>::CBK : 4; }
+static int cbk_of(int kind) { return kind == 1 ? Geo<1>::CBK : (kind == 5 ? Geo<5>::CBK : 4); }
 static int nkw_of(int kind) { return (kind == 3 || kind == 4) ? 3 : 1; }
 
 // row-parity map (ph) over the whole batch: dims (w*8, H/2, D, cb, b); row h2 of parity ph is input row 2*h2+ph
@@ -1081,22 +1126,25 @@ using namespace dmb::tc;
 extern "C" int dmb_b200_conv3d_tc_available(void) { return device_ok(); }
 
 extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split, int kind) {
-    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 4) return 0;
-    const int cbk = cbk_of(kind);
-    const int64_t blob = (int64_t)TAPS * cbk * (split ? 64 : 32) * 16;
-    return blob * (Cin / (8 * cbk)) * ((Cout + 31) / 32);
+    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 5) return 0;
+    const int cbk = cbk_of(kind), nb = nbo_of(kind);
+    if (Cin % (8 * cbk)) return 0;
+    const int64_t blob = (int64_t)TAPS * cbk * (split ? 2 * nb : nb) * 16;
+    return blob * (Cin / (8 * cbk)) * ((Cout + nb - 1) / nb);
 }
 
 extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split,
                                                int fp16, float scale, int kind, void* stream) {
     DMB_REQUIRE(w_packed && w_blob, "conv3d_tc_pack_weights: null pointer");
-    DMB_REQUIRE(kind >= 0 && kind <= 4, "conv3d_tc_pack_weights: kind must be 0..4");
+    DMB_REQUIRE(kind >= 0 && kind <= 5, "conv3d_tc_pack_weights: kind must be 0..5");
+    DMB_REQUIRE(kind != 5 || (Cin % 64 == 0 && Cout % 16 == 0), "conv3d_tc_pack_weights: kind 5 needs Cin %% 64 == 0 and Cout %% 16 == 0");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc_pack_weights: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(Cout > 0 && (Cout % 32 == 0 || Cout < 32), "conv3d_tc_pack_weights: Cout=%d must be <32 or a multiple of 32", Cout);
     DMB_REQUIRE(scale > 0.f, "conv3d_tc_pack_weights: scale must be positive");
     const int64_t n = dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, split, kind) / 2;
     pack_weights_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(w_packed, (uint16_t*)w_blob, Cin, Cout,
-                                                                                cbk_of(kind), nkw_of(kind), split ? 1 : 0, fp16 ? 1 : 0, scale);
+                                                                                cbk_of(kind), nkw_of(kind), split ? 1 : 0, fp16 ? 1 : 0, scale,
+                                                                                nbo_of(kind));
     return check_launch("pack_weights_kernel");
 }
 
@@ -1106,8 +1154,9 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
                           int relu, int fp16, const float* head_w, float* head_t, void* stream) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
-    DMB_REQUIRE(kind >= 0 && kind <= 4, "conv3d_tc: kind must be 0/3 (stride 1), 1/4 (stride 2) or 2 (transposed stride 2)");
+    DMB_REQUIRE(kind >= 0 && kind <= 5, "conv3d_tc: kind must be 0/3 (stride 1), 1/4 (stride 2) or 2/5 (transposed stride 2)");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc: Cin=%d must be a multiple of 32", Cin);
+    DMB_REQUIRE(kind != 5 || (Cin % 64 == 0 && Cout % 32 == 0), "conv3d_tc: kind 5 needs Cin %% 64 == 0 and Cout %% 32 == 0");
     DMB_REQUIRE(w_scale > 0.f, "conv3d_tc: w_scale must be positive");
     const bool scalar_out = (Cout == 1);
     DMB_REQUIRE(scalar_out || (Cout > 0 && Cout % 32 == 0), "conv3d_tc: Cout=%d must be 1 or a multiple of 32", Cout);
@@ -1126,8 +1175,8 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     const bool split = x_lo != nullptr;
     DMB_REQUIRE(head || scalar_out || split == (y_lo != nullptr), "conv3d_tc: x_lo and y_lo must both be given or both be NULL");
 
-    const int cbk = cbk_of(kind);
-    const int IB = Cin / (8 * cbk), OB = scalar_out ? 1 : Cout / 32;
+    const int cbk = cbk_of(kind), nbo = nbo_of(kind);
+    const int IB = Cin / (8 * cbk), OB = scalar_out ? 1 : Cout / nbo;
     const int CBS = Cin / 8;
 
     Params p;
@@ -1141,7 +1190,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     p.Do = same ? D : (s2 ? D / 2 : 2 * D);
     p.Ho = same ? H : (s2 ? H / 2 : 2 * H);
     p.Wo = same ? W : (s2 ? W / 2 : 2 * W);
-    p.n_valid_out = scalar_out ? 1 : 32;
+    p.n_valid_out = scalar_out ? 1 : nbo;
     p.acc_scale = 1.0f / w_scale;
     p.tiles_h = (int)cdiv(p.Hm, (kind == 3 || kind == 4) ? TH3 : TH);
     p.tiles_w = (int)cdiv(p.Wm, (kind == 3 || kind == 4) ? TWV : TW);
@@ -1161,7 +1210,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     p.nseg = (int)cdiv(p.Dm, p.seg_len);
     p.n_items = cols * p.nseg;
     const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-    const size_t blob = (size_t)TAPS * cbk * (split ? 64 : 32) * 16;
+    const size_t blob = (size_t)TAPS * cbk * (split ? 2 * nbo : nbo) * 16;
     const size_t in_batch_bytes = (size_t)CBS * D * H * W * 16;
     const size_t out_cbs = scalar_out ? 0 : Cout / 8;
 
@@ -1189,7 +1238,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
             if (rc) return rc;
             for (int i = 4; i < 8; ++i) maps.m[i] = maps.m[0];
         } else {
-            const int bh = kind == 2 ? 17 : (kind == 3 ? TH3 + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? TW3 : 9);
+            const int bh = (kind == 2 || kind == 5) ? 17 : (kind == 3 ? TH3 + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? TW3 : 9);
             rc = make_dense_map(&maps.m[0], xh, B, CBS, D, H, W, bh, bw, cbk, fp16);
             if (rc) return rc;
             rc = make_dense_map(&maps.m[1], xl, B, CBS, D, H, W, bh, bw, cbk, fp16);
@@ -1203,15 +1252,15 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
             for (int ib = 0; ib < IB; ++ib) {
                 const bool first = ib == 0, last = ib == IB - 1;
                 p.w_blob = reinterpret_cast<const unsigned char*>(w_blob) + (size_t)(ob * IB + ib) * blob;
-                p.bias = (first && bias) ? bias + ob * 32 : nullptr;
+                p.bias = (first && bias) ? bias + ob * nbo : nullptr;
                 p.in_cb0 = ib * cbk;
                 p.relu = (last && relu) ? 1 : 0;
                 p.y_hi = y_hi ? reinterpret_cast<uint4*>(y_hi) + yb : nullptr;
                 p.y_lo = y_lo ? reinterpret_cast<uint4*>(y_lo) + yb : nullptr;
-                p.y_cb0 = ob * 4;
+                p.y_cb0 = ob * (nbo / 8);
                 p.y_cbs = (int)out_cbs;
                 p.y_f32 = y_f32 ? y_f32 + (size_t)bo * out_plane : nullptr;
-                p.res_cb0 = ob * 4;
+                p.res_cb0 = ob * (nbo / 8);
                 p.res_cbs = p.y_cbs;
                 if (first) {                       // the external residual joins on the first pass
                     p.res_hi = res_hi ? reinterpret_cast<const uint4*>(res_hi) + yb : nullptr;
@@ -1231,6 +1280,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
                 else if (kind == 1) rc = launch_kind<1>(maps, p, grid, split, fp16, stream);
                 else if (kind == 2) rc = launch_kind<2>(maps, p, grid, split, fp16, stream);
                 else if (kind == 3) rc = launch_kind<3>(maps, p, grid, split, fp16, stream);
+                else if (kind == 5) rc = launch_kind<5>(maps, p, grid, split, fp16, stream);
                 else rc = launch_kind<4>(maps, p, grid, split, fp16, stream);
                 if (rc) return rc;
             }

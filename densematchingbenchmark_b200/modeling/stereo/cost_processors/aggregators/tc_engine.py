@@ -21,6 +21,16 @@ from ...layers.basic_layers import FusedConvUnit
 # stride-1 / stride-2 layers: kinds 3 / 4 (kw taps merged into the MMA N dimension, the fast kernels) or
 # kinds 0 / 1 (one MMA per tap; kept as the simpler reference implementations, DMB_B200_TC_KW_MERGE=0)
 KW_MERGE = os.environ.get("DMB_B200_TC_KW_MERGE", "1") != "0"
+# transposed layers with 64 input channels: kind 2 (two 32-input-channel passes, the second accumulating in place)
+# or kind 5 (one K=64 pass per 16 output channels, every output written once; DMB_B200_TC_DECONV_K64=1).
+# Measured (profiles/README.md): kind 5 is SLOWER (conv6: 2 x 141 us against 2 x 115 us) although it moves 40 %
+# fewer bytes -- a tcgen05.mma with M=128 costs ~110 cycles however small N is (its A tile streams from shared
+# memory), and kind 5 issues twice as many.  Kept, tested and off by default.
+DECONV_K64 = os.environ.get("DMB_B200_TC_DECONV_K64", "0") == "1"
+
+
+def _transposed_kind(cin, cout):
+    return 5 if (DECONV_K64 and cin % 64 == 0 and cout % 32 == 0) else 2
 
 PRECISIONS = {          # name -> (split, fp16)
     "fp16x3": (True, True),
@@ -88,14 +98,14 @@ def tc_shape_ok(trunk, channels, dhw):
 
 
 def _kind_of(layer):
-    """0: stride-1 conv, 1: stride-2 conv, 2: stride-2 transposed conv (k3, p1, op1)."""
+    """0/3: stride-1 conv, 1/4: stride-2 conv, 2/5: stride-2 transposed conv (k3, p1, op1)."""
     conv = layer.conv if isinstance(layer, FusedConvUnit) else layer
     if tuple(conv.kernel_size) != (3, 3, 3) or tuple(conv.padding) != (1, 1, 1) or tuple(conv.dilation) != (1, 1, 1):
         raise NotImplementedError("the tcgen05 path implements 3x3x3, padding 1, dilation 1 only")
     if isinstance(conv, torch.nn.ConvTranspose3d):
         if tuple(conv.stride) != (2, 2, 2) or tuple(conv.output_padding) != (1, 1, 1):
             raise NotImplementedError("transposed conv on tcgen05: stride 2, output_padding 1 only")
-        return 2
+        return _transposed_kind(conv.in_channels, conv.out_channels)
     if tuple(conv.stride) == (1, 1, 1):
         return 3 if KW_MERGE else 0
     if tuple(conv.stride) == (2, 2, 2):
@@ -182,7 +192,8 @@ def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=N
     NCDHW tensor on the tcgen05 kernels: layout conversion in, conv, layout conversion out.  Used by the training
     path (ops/autograd.py), whose weights change every step -- nothing is cached.  Returns float32 NCDHW."""
     split, fp16 = PRECISIONS[precision]
-    kind = 2 if transposed else ((3 if KW_MERGE else 0) if stride == 1 else (4 if KW_MERGE else 1))
+    kind = (_transposed_kind(w_packed.shape[1], w_packed.shape[2]) if transposed
+            else ((3 if KW_MERGE else 0) if stride == 1 else (4 if KW_MERGE else 1)))
     blob, Cin, Cout, scale = pack_blob(w_packed, kind, split, fp16)
     xb = Blocked.from_ncdhw(x, split, fp16)
     if Cout == 1:

@@ -491,6 +491,8 @@ TC_STRIDED_CASES = [
 def test_conv3d_tc_strided_vs_torch_cpu(P, case, precision, kw_merge, monkeypatch):
     tc = _tc_or_skip()
     monkeypatch.setattr(tc, "KW_MERGE", kw_merge)
+    # 64-input-channel transposed layers: kind 5 (K=64 passes, production) with kw_merge, kind 2 (in-place passes) without
+    monkeypatch.setattr(tc, "DECONV_K64", kw_merge)
     split, fp16 = tc.PRECISIONS[precision]
     dt = torch.float16 if fp16 else torch.bfloat16
     kind, cin, cout, dims, bias, residual, relu = case
