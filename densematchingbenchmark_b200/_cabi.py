@@ -11,7 +11,8 @@ from ctypes import c_double, c_float, c_int, c_int64, c_longlong, c_void_p, c_ch
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libdmb_b200.so")
+# DMB_B200_LIB: an alternative build of the same library (A/B timing of two builds on one GPU box)
+LIB_PATH = os.environ.get("DMB_B200_LIB") or os.path.join(_HERE, "csrc", "libdmb_b200.so")
 
 _P = c_void_p
 _I = c_int

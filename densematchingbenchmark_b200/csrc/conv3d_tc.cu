@@ -43,7 +43,9 @@ constexpr int NB = 32;                      // output channels per pass
 constexpr int TAPS = 27;
 // threads: warp 0 = TMA producer, warp 1 = MMA issuer, then 4 epilogue warps (8 for the transposed
 // kernel, whose tiles carry 8 output parity classes = 8x the epilogue work per MMA tile)
-__host__ __device__ constexpr int nthreads_of(int kind, bool head = false) { return (kind == 2 || kind == 5 || head) ? 320 : 192; }
+// (8 epilogue warps everywhere but the two reference kernels: the epilogue -- TMEM drain, shifted sums, bias /
+// residual / ReLU, 16-bit split, stores -- of a 4-warp kernel took longer per tile than the tile's MMAs)
+__host__ __device__ constexpr int nthreads_of(int kind, bool head = false) { return (kind >= 2 || head) ? 320 : 192; }
 // output channels per pass: 32, except KIND 5 (16: all 64 input channels of the layer fit one pass instead)
 __host__ __device__ constexpr int nbo_of(int kind) { return kind == 5 ? 16 : 32; }
 // depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
@@ -161,6 +163,35 @@ __device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t desc_
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Lean issue path (KIND 3): the leader lane is elected ONCE per output plane and issues all of the plane's MMAs
+// under a branch -- per MMA that leaves the descriptor adds, the 64-bit packs and the instruction itself
+// (the per-MMA elect.sync / vote / predicated-move sequence of the wrappers above measured ~97 cycles of issue
+// per MMA against 76 cycles of tensor-pipe time: the issuing warp, not the tensor core, bounded the kernel).
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t e;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
+    return e;
+}
+template <bool ACC>
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(ACC ? 1 : 0)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16_ss_rt(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void commit_one(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -174,6 +205,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor layout):
@@ -278,7 +318,7 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
 // bias + residual + ReLU + 16-bit (hi[,lo]) split + store of one output voxel's 32 channels
 template <bool FP16, int NCB = 4>
 __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], const float (&bias)[NB], int b, int d, int h,
-                                            int w) {
+                                            int w, int cb_off = 0) {
     const size_t plane_sz = (size_t)p.Ho * p.Wo;
     const size_t vox = (size_t)d * plane_sz + (size_t)h * p.Wo + w;
     if (p.y_f32) {
@@ -294,7 +334,7 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
     if (p.res_hi) {
 #pragma unroll
         for (int cb = 0; cb < NCB; ++cb) {
-            const size_t ri = ((size_t)(b * p.res_cbs + p.res_cb0 + cb) * p.Do) * plane_sz + vox;
+            const size_t ri = ((size_t)(b * p.res_cbs + p.res_cb0 + cb_off + cb) * p.Do) * plane_sz + vox;
             float f[8];
             unpack8<FP16>(__ldg(p.res_hi + ri), f);
 #pragma unroll
@@ -312,7 +352,7 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
     }
 #pragma unroll
     for (int cb = 0; cb < NCB; ++cb) {
-        const size_t yi = ((size_t)(b * p.y_cbs + p.y_cb0 + cb) * p.Do) * plane_sz + vox;
+        const size_t yi = ((size_t)(b * p.y_cbs + p.y_cb0 + cb_off + cb) * p.Do) * plane_sz + vox;
         float hi[8], lo[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -588,42 +628,54 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     constexpr uint32_t LBO_A = 10 * 16 * 16, SBO_A = 8 * 16;   // 10 rows of 256 bytes per channel block
                     constexpr uint32_t idesc_hi3 = make_idesc(3 * NB, FP16 ? 0u : 1u);     // A_lo x [Whi kw0..2]
                     constexpr uint32_t a_hiw = desc_hi(SBO_A);
+                    // ring slot of plane (n_base + od), kept as a wrapping counter (no modulo in the loop)
+                    uint32_t slot = n_base % NSTAGE, phase = (n_base / NSTAGE) & 1;
+                    uint32_t wslot = slot, wphase = phase;                     // next plane to wait for
                     int waited = 0;
                     for (int od = 0; od < nout; ++od) {
                         while (waited < od + 3) {
-                            const uint32_t n = n_base + waited;
-                            mbar_wait(&full[n % NSTAGE], (n / NSTAGE) & 1);
+                            mbar_wait(&full[wslot], wphase);
+                            if (++wslot == NSTAGE) { wslot = 0; wphase ^= 1; }
                             ++waited;
                         }
                         const uint32_t t = t_base + od;
                         const uint32_t buf = t & 1;
                         mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
                         tcgen05_fence_after();
-                        const uint32_t acc = tmem_base + buf * S::ACC_COLS;
+                        const uint32_t s1 = slot + 1 >= NSTAGE ? slot + 1 - NSTAGE : slot + 1;
+                        const uint32_t s2 = slot + 2 >= NSTAGE ? slot + 2 - NSTAGE : slot + 2;
+                        if (elect_one()) {
+                            const uint32_t acc = tmem_base + buf * S::ACC_COLS;
+                            const uint32_t a_lo_kd[3] = {desc_lo(planes_addr + slot * S::STAGE_BYTES, LBO_A),
+                                                         desc_lo(planes_addr + s1 * S::STAGE_BYTES, LBO_A),
+                                                         desc_lo(planes_addr + s2 * S::STAGE_BYTES, LBO_A)};
 #pragma unroll
-                        for (int kd = 0; kd < 3; ++kd) {
-                            const uint32_t a_hi = planes_addr + ((n_base + od + kd) % NSTAGE) * S::STAGE_BYTES;
-                            const uint32_t a_lo0 = desc_lo(a_hi, LBO_A);
+                            for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-                            for (int kh = 0; kh < 3; ++kh) {
+                                for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                                for (int kk = 0; kk < CBK / 2; ++kk) {
-                                    const bool first = (kd == 0 && kh == 0 && kk == 0);
-                                    const uint64_t db = desc_of(b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
-                                    const uint32_t a_off = kh * (TW3 * 16) + 2 * kk * LBO_A;
-                                    tcgen05_mma_bf16(acc, desc_of(a_lo0 + (a_off >> 4), a_hiw), db, idesc_main, first ? 0u : 1u);
-                                    if (SPLIT)   // lo*Whi of the three kw lands on the (small) hi*Wlo columns
-                                        tcgen05_mma_bf16(acc + 3 * NB, desc_of(a_lo0 + ((S::PLANE_BYTES + a_off) >> 4), a_hiw), db,
-                                                         idesc_hi3, 1u);
+                                    for (int kk = 0; kk < CBK / 2; ++kk) {
+                                        const uint32_t b_lo = b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4);
+                                        const uint32_t a_off = kh * (TW3 * 16) + 2 * kk * LBO_A;
+                                        if (kd == 0 && kh == 0 && kk == 0)
+                                            mma_f16_ss<false>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
+                                        else
+                                            mma_f16_ss<true>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
+                                        if (SPLIT)   // lo*Whi of the three kw lands on the (small) hi*Wlo columns
+                                            mma_f16_ss<true>(acc + 3 * NB, a_lo_kd[kd] + ((S::PLANE_BYTES + a_off) >> 4), a_hiw, b_lo, b_hi,
+                                                             idesc_hi3);
+                                    }
                                 }
                             }
+                            commit_one(&tfull[buf]);
+                            commit_one(&empty[slot]);
+                            if (od == nout - 1) {
+                                commit_one(&empty[s1]);
+                                commit_one(&empty[s2]);
+                            }
                         }
-                        tcgen05_commit(&tfull[buf]);
-                        tcgen05_commit(&empty[(n_base + od) % NSTAGE]);
-                        if (od == nout - 1) {
-                            tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
-                            tcgen05_commit(&empty[(n_base + od + 2) % NSTAGE]);
-                        }
+                        __syncwarp();
+                        if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
                     }
                     n_base += nout + 2;
                     t_base += nout;
@@ -633,7 +685,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     constexpr uint32_t a_hiw = desc_hi(8 * 16);
                     constexpr uint32_t LBO_E = 8 * 256, LBO_O = 9 * 256;
                     const int nplanes = 2 * nout + 1;
-                    auto issue_kd = [&](uint32_t a_stage, uint32_t t, int kd) {
+                    auto issue_kd = [&](uint32_t a_stage, uint32_t t, int kd) {      // called by the elected lane only
                         const uint32_t acc = tmem_base + (t & 1) * S::ACC_COLS;
                         const uint32_t e_lo0 = desc_lo(a_stage, LBO_E);
                         const uint32_t o_lo0 = desc_lo(a_stage + Geo<4>::EVEN_BYTES, LBO_O);
@@ -642,38 +694,42 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
 #pragma unroll
                             for (int kk = 0; kk < CBK / 2; ++kk) {
                                 const bool first = (kd == 0 && kh == 0 && kk == 0);
-                                const uint64_t db = desc_of(b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
+                                const uint32_t b_lo = b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4);
                                 // kh=1: even rows, local row = oh; kh=0: odd rows, row oh; kh=2: odd rows, row oh+1
                                 const uint32_t lo = kh == 1 ? e_lo0 + ((2 * kk * LBO_E) >> 4)
                                                             : o_lo0 + (((kh == 2 ? 256u : 0u) + 2 * kk * LBO_O) >> 4);
-                                tcgen05_mma_bf16(acc, desc_of(lo, a_hiw), db, idesc_main, first ? 0u : 1u);
+                                mma_f16_ss_rt(acc, lo, a_hiw, b_lo, b_hi, idesc_main, first ? 0u : 1u);
                                 if (SPLIT)
-                                    tcgen05_mma_bf16(acc + 3 * NB, desc_of(lo + (S::PLANE_BYTES >> 4), a_hiw), db, idesc_hi3, 1u);
+                                    mma_f16_ss<true>(acc + 3 * NB, lo + (S::PLANE_BYTES >> 4), a_hiw, b_lo, b_hi, idesc_hi3);
                             }
                         }
                     };
+                    uint32_t slot = n_base % NSTAGE, phase = (n_base / NSTAGE) & 1;
                     for (int j = 0; j < nplanes; ++j) {
-                        const uint32_t n = n_base + j;
-                        const uint32_t slot = n % NSTAGE;
-                        mbar_wait(&full[slot], (n / NSTAGE) & 1);
+                        mbar_wait(&full[slot], phase);
                         tcgen05_fence_after();
                         const uint32_t a_stage = planes_addr + slot * S::STAGE_BYTES;
-                        if (j & 1) {
-                            issue_kd(a_stage, t_base + ((j - 1) >> 1), 1);
-                        } else {
-                            if (j >= 2) {
-                                const uint32_t t = t_base + (j >> 1) - 1;
-                                issue_kd(a_stage, t, 2);
-                                tcgen05_commit(&tfull[t & 1]);
-                            }
-                            if ((j >> 1) < nout) {
-                                const uint32_t t = t_base + (j >> 1);
-                                mbar_wait(&tempty[t & 1], ((t >> 1) & 1) ^ 1);
-                                tcgen05_fence_after();
-                                issue_kd(a_stage, t, 0);
-                            }
+                        const bool opens = !(j & 1) && (j >> 1) < nout;          // this plane is kd=0 of a new output
+                        if (opens) {
+                            const uint32_t t = t_base + (j >> 1);
+                            mbar_wait(&tempty[t & 1], ((t >> 1) & 1) ^ 1);
+                            tcgen05_fence_after();
                         }
-                        tcgen05_commit(&empty[slot]);
+                        if (elect_one()) {
+                            if (j & 1) {
+                                issue_kd(a_stage, t_base + ((j - 1) >> 1), 1);
+                            } else {
+                                if (j >= 2) {
+                                    const uint32_t t = t_base + (j >> 1) - 1;
+                                    issue_kd(a_stage, t, 2);
+                                    commit_one(&tfull[t & 1]);
+                                }
+                                if (opens) issue_kd(a_stage, t_base + (j >> 1), 0);
+                            }
+                            commit_one(&empty[slot]);
+                        }
+                        __syncwarp();
+                        if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
                     }
                     n_base += nplanes;
                     t_base += nout;
@@ -733,7 +789,8 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 } else {
                     // transposed: per input depth qd two groups (output depth parity rd), 4 classes each
                     constexpr uint32_t LBO_A = 17 * 9 * 16, SBO_A = 9 * 16;
-                    auto issue_group = [&](uint32_t a_same, uint32_t a_next, int rd) {
+                    constexpr uint32_t a_hiw = desc_hi(SBO_A);
+                    auto issue_group = [&](uint32_t a_same, uint32_t a_next, int rd) {        // elected lane only
                         const uint32_t accg = tmem_base + rd * S::ACC_COLS;
 #pragma unroll
                         for (int cls = 0; cls < 4; ++cls) {
@@ -761,38 +818,48 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                                         const uint32_t a_off = (offh * 9 + offw) * 16;
 #pragma unroll
                                         for (int kk = 0; kk < CBK / 2; ++kk) {
-                                            const uint64_t db = bdesc(tap, kk);
-                                            tcgen05_mma_bf16(acc, desc_of(a_lo0 + ((a_off + 2 * kk * LBO_A) >> 4), desc_hi(SBO_A)), db,
-                                                             idesc_main, first ? 0u : 1u);
+                                            const uint32_t b_lo = b_lo0 + ((tap * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4);
+                                            mma_f16_ss_rt(acc, a_lo0 + ((a_off + 2 * kk * LBO_A) >> 4), a_hiw, b_lo, b_hi, idesc_main,
+                                                          first ? 0u : 1u);
                                             first = false;
                                             if (SPLIT)
-                                                tcgen05_mma_bf16(acc, desc_of(a_lo0 + ((S::PLANE_BYTES + a_off + 2 * kk * LBO_A) >> 4), desc_hi(SBO_A)),
-                                                                 db, idesc_lo, 1u);
+                                                mma_f16_ss<true>(acc, a_lo0 + ((S::PLANE_BYTES + a_off + 2 * kk * LBO_A) >> 4), a_hiw, b_lo,
+                                                                 b_hi, idesc_lo);
                                         }
                                     }
                                 }
                             }
                         }
                     };
+                    uint32_t slot = n_base % NSTAGE, phase = (n_base / NSTAGE) & 1;
+                    uint32_t wslot = slot, wphase = phase;
                     int waited = 0;
                     for (int od = 0; od < nout; ++od) {
                         while (waited < od + 2) {
-                            const uint32_t n = n_base + waited;
-                            mbar_wait(&full[n % NSTAGE], (n / NSTAGE) & 1);
+                            mbar_wait(&full[wslot], wphase);
+                            if (++wslot == NSTAGE) { wslot = 0; wphase ^= 1; }
                             ++waited;
                         }
-                        const uint32_t a_same = planes_addr + ((n_base + od) % NSTAGE) * S::STAGE_BYTES;
-                        const uint32_t a_next = planes_addr + ((n_base + od + 1) % NSTAGE) * S::STAGE_BYTES;
+                        const uint32_t s1 = slot + 1 >= NSTAGE ? slot + 1 - NSTAGE : slot + 1;
+                        const uint32_t a_same = planes_addr + slot * S::STAGE_BYTES;
+                        const uint32_t a_next = planes_addr + s1 * S::STAGE_BYTES;
 #pragma unroll 1
                         for (int rd = 0; rd < 2; ++rd) {
                             const uint32_t t = t_base + 2 * od + rd;          // t_base is even: buffer == rd
                             mbar_wait(&tempty[rd], ((t >> 1) & 1) ^ 1);
                             tcgen05_fence_after();
-                            issue_group(a_same, a_next, rd);
-                            tcgen05_commit(&tfull[rd]);
+                            if (elect_one()) {
+                                if (rd == 0) issue_group(a_same, a_next, 0);
+                                else issue_group(a_same, a_next, 1);
+                                commit_one(&tfull[rd]);
+                                if (rd == 1) {
+                                    commit_one(&empty[slot]);
+                                    if (od == nout - 1) commit_one(&empty[s1]);
+                                }
+                            }
+                            __syncwarp();
                         }
-                        tcgen05_commit(&empty[(n_base + od) % NSTAGE]);
-                        if (od == nout - 1) tcgen05_commit(&empty[(n_base + od + 1) % NSTAGE]);
+                        if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
                     }
                     n_base += nout + 1;
                     t_base += 2 * nout;
@@ -805,9 +872,15 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
         const int hl = (KIND == 3 || KIND == 4) ? (m >> 4) : (m >> 3), wl = (KIND == 3 || KIND == 4) ? (m & 15) : (m & 7);
+        // KIND 3/4 (not the fused-head variant): two warps per TMEM lane quarter, each owns 16 of the 32 channels
+        constexpr bool HALVES = (KIND == 3 || KIND == 4) && !HEAD;
+        const int half = HALVES ? ((warp - 2) >> 2) : 0;
         float bias[NB];
 #pragma unroll
-        for (int c = 0; c < NB; ++c) bias[c] = (p.bias && c < p.n_valid_out) ? __ldg(p.bias + c) : 0.f;
+        for (int c = 0; c < NB; ++c) {
+            const int cc = half * 16 + c;
+            bias[c] = (p.bias && cc < p.n_valid_out && (!HALVES || c < 16)) ? __ldg(p.bias + cc) : 0.f;
+        }
         uint32_t t = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
@@ -825,8 +898,8 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                         const size_t plane_sz = (size_t)p.Ho * p.Wo;
                         const size_t vox = (size_t)d * plane_sz + (size_t)h * p.Wo + w;
 #pragma unroll
-                        for (int cb = 0; cb < 4; ++cb) {
-                            const size_t ri = ((size_t)(it.b * p.res_cbs + p.res_cb0 + cb) * p.Do) * plane_sz + vox;
+                        for (int cb = 0; cb < 2; ++cb) {
+                            const size_t ri = ((size_t)(it.b * p.res_cbs + p.res_cb0 + half * 2 + cb) * p.Do) * plane_sz + vox;
                             prefetch_l1(p.res_hi + ri);
                             if (p.res_lo) prefetch_l1(p.res_lo + ri);
                         }
@@ -834,21 +907,41 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
                     tcgen05_fence_after();
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
-                    uint32_t r0[32], r1[32];
                     float v[NB];
                     // out(w) = D'[w-1][kw=0] + D'[w][kw=1] + D'[w+1][kw=2]; lanes of one tile row are adjacent
+                    if constexpr (HEAD) {
+                        uint32_t r0[32], r1[32];
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        tmem_ld32(taddr + kw * NB, r0);
-                        if (SPLIT) tmem_ld32(taddr + 3 * NB + kw * NB, r1);
-                        tmem_ld_wait();
+                        for (int kw = 0; kw < 3; ++kw) {
+                            tmem_ld32(taddr + kw * NB, r0);
+                            if (SPLIT) tmem_ld32(taddr + 3 * NB + kw * NB, r1);
+                            tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < NB; ++c) {
-                            float sv = __uint_as_float(r0[c]);
-                            if (SPLIT) sv += __uint_as_float(r1[c]);
-                            if (kw == 0) v[c] = __shfl_up_sync(0xffffffffu, sv, 1);
-                            else if (kw == 1) v[c] += sv;
-                            else v[c] = (v[c] + __shfl_down_sync(0xffffffffu, sv, 1)) * p.acc_scale;
+                            for (int c = 0; c < NB; ++c) {
+                                float sv = __uint_as_float(r0[c]);
+                                if (SPLIT) sv += __uint_as_float(r1[c]);
+                                if (kw == 0) v[c] = __shfl_up_sync(0xffffffffu, sv, 1);
+                                else if (kw == 1) v[c] += sv;
+                                else v[c] = (v[c] + __shfl_down_sync(0xffffffffu, sv, 1)) * p.acc_scale;
+                            }
+                        }
+                    } else {
+                        uint32_t r0[16], r1[16];
+#pragma unroll
+                        for (int c = 16; c < NB; ++c) v[c] = 0.f;
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            tmem_ld16(taddr + kw * NB + half * 16, r0);
+                            if (SPLIT) tmem_ld16(taddr + 3 * NB + kw * NB + half * 16, r1);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < 16; ++c) {
+                                float sv = __uint_as_float(r0[c]);
+                                if (SPLIT) sv += __uint_as_float(r1[c]);
+                                if (kw == 0) v[c] = __shfl_up_sync(0xffffffffu, sv, 1);
+                                else if (kw == 1) v[c] += sv;
+                                else v[c] = (v[c] + __shfl_down_sync(0xffffffffu, sv, 1)) * p.acc_scale;
+                            }
                         }
                     }
                     tcgen05_fence_before();
@@ -861,8 +954,9 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             const float4* hw4 = reinterpret_cast<const float4*>(smem + S::HEAD_OFF);
                             if (warp < 6) store_head<0, 14>(p, v, bias, hw4, it.b, d, h, w);
                             else store_head<14, TAPS>(p, v, bias, hw4, it.b, d, h, w);
-                        } else
-                            store_voxel<FP16>(p, v, bias, it.b, d, h, w);
+                        } else if (!(p.y_f32 && half)) {       // single-channel output: the first half's warp writes it
+                            store_voxel<FP16, 2>(p, v, bias, it.b, d, h, w, half * 2);
+                        }
                     }
                 } else if (KIND != 2 && KIND != 5) {
                     const uint32_t buf = t & 1;
