@@ -39,6 +39,7 @@ SIGNATURES = {
     "dmb_b200_conv3d_tc": [_P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_conv3d_tc_head": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_head_gather": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "dmb_b200_debug_set_trace": [_P],
     "dmb_b200_conv3d_tc_pack_weights": [_P, _P, _I, _I, _I, _I, _F, _I, _P],
     "dmb_b200_ncdhw_to_blocked": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_blocked_to_ncdhw": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
@@ -62,6 +63,9 @@ OTHER = {
     "dmb_b200_conv3d_tc_available": ([], c_int),
 }
 
+# debug-only entry points that an older build handed in through DMB_B200_LIB may lack
+OPTIONAL = {"dmb_b200_debug_set_trace"}
+
 _lib = None
 
 
@@ -80,6 +84,8 @@ def load():
             "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
+        if name in OPTIONAL and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = c_int

@@ -50,7 +50,7 @@ __host__ __device__ constexpr int nthreads_of(int kind, bool head = false) { ret
 __host__ __device__ constexpr int nbo_of(int kind) { return kind == 5 ? 16 : 32; }
 // depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
 // work-item boundaries)
-__host__ __device__ constexpr int nstage_of(int kind) { return kind == 3 ? 5 : ((kind == 4 || kind == 5) ? 3 : 4); }
+__host__ __device__ constexpr int nstage_of(int kind) { return (kind == 4 || kind == 5) ? 3 : 4; }
 constexpr int TMEM_COLS = 512;
 
 // KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane (reference kernel)
@@ -90,7 +90,7 @@ template <> struct Geo<5> {
 // group pitch because no w halo is stored): 14 of 16 columns carry outputs.
 template <> struct Geo<3> {
     static constexpr int CBK = 4;
-    static constexpr int PLANE_BYTES = 4 * 10 * 16 * 16;           // 10240: (8+2) rows x 16 columns x 32 channels
+    static constexpr int PLANE_BYTES = 4 * 6 * 32 * 16;            // 12288: (4+2) rows x 32 columns x 32 channels
 };
 // KIND 4: stride-2 conv on the kw-merged scheme.  The depth and height strides are taken by the loads
 // (plane index 2*od+kd-1; two row-parity boxes per plane through tensor maps with a doubled row pitch --
@@ -103,8 +103,18 @@ template <> struct Geo<4> {
     static constexpr int ODD_BYTES = 4 * 9 * 16 * 16;              // 9216: rows 2*oh-1 .. 2*oh+15
     static constexpr int PLANE_BYTES = EVEN_BYTES + ODD_BYTES;     // 17408
 };
-constexpr int TH3 = 8, TW3 = 16;            // KIND 3 / 4 tile
-constexpr int TWV = 14;                     // valid output columns per tile row in KIND 3
+constexpr int TH3 = 8, TW3 = 16;            // KIND 4 tile: 8 output rows x 16 input columns
+constexpr int TWV = 14;                     // KIND 4: columns of a tile row that are computed with both neighbours
+// KIND 3 tile: 4 rows x 32 columns, 30 of which produce outputs (the kw-merged scheme needs one halo column on
+// each side INSIDE the M tile).  8 x 16 with 14 valid columns wasted 12.5 % of every MMA plus the ragged last
+// tile column (240 = 17.1 x 14); 4 x 32 wastes 6.25 % and tiles the PSMNet grids exactly (136 = 34 x 4,
+// 240 = 8 x 30, 120 = 4 x 30, 60 = 2 x 30): 272 instead of 306 tiles at 1/4 resolution, 68 instead of 81 at 1/8,
+// 18 instead of 25 at 1/16.  The trunk is POWER bound (tools/tc_clock.py: the SM clock drops to 1.3-1.5 GHz under
+// this MMA stream), so MMAs not issued are the only time saved.
+constexpr int K3_TH = 4, K3_TW = 32, K3_TWV = 30;
+// per-KIND tile steps (M-space rows / output columns a tile advances by)
+__host__ __device__ constexpr int th_of(int kind) { return kind == 3 ? K3_TH : (kind == 4 ? TH3 : TH); }
+__host__ __device__ constexpr int twstep_of(int kind) { return kind == 3 ? K3_TWV : (kind == 4 ? TWV : TW); }
 
 struct Maps {
     CUtensorMap m[8];   // KIND 0/2: [0]=hi [1]=lo;  KIND 1: [(ph*2+pw)*2 + (0 hi | 1 lo)]
@@ -132,6 +142,7 @@ struct Params {
     // fused classifier head (KIND 3 only): instead of storing the 32-channel activation a, the epilogue
     // writes its 27 per-tap projections T[tap][voxel] = sum_c a[c] * head_w[tap][c]; the 32->1 3x3x3
     // convolution that follows is then a 27-term gather (head_gather_kernel)
+    long long* trace;          // debug timeline (dmb_b200_debug_set_trace) or null: CTA 0 records clock64() per role
     const float* head_w;       // [27][32] fp32 (device) or null
     float* head_t;             // [B][27][Do][Ho][Wo] fp32 (null: ordinary layer)
 };
@@ -171,6 +182,20 @@ __device__ __forceinline__ uint32_t elect_one() {
     uint32_t e;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(e));
     return e;
+}
+// both barrier polls are in flight together; returns 1 when both phases have completed
+__device__ __forceinline__ uint32_t mbar_try_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred pa, pb;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 pa, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 pb, [%3], %4;\n\t"
+        "and.pred pa, pa, pb;\n\t"
+        "selp.u32 %0, 1, 0, pa;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar_a)), "r"(parity_a), "r"(smem_u32(bar_b)), "r"(parity_b)
+        : "memory");
+    return ok;
 }
 template <bool ACC>
 __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -443,6 +468,11 @@ __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restric
     y[i] = o;
 }
 
+// timeline tracing (tools/tc_trace.py): role r of CTA 0 appends clock64() stamps to trace[r * 4096 ...]
+__device__ __forceinline__ void trace_stamp(const Params& p, int role, uint32_t& n) {
+    if (p.trace && blockIdx.x == 0 && n < 4096) p.trace[role * 4096 + n++] = clock64();
+}
+
 template <int KIND, bool SPLIT, bool FP16, bool HEAD>
 __global__ void __launch_bounds__(nthreads_of(KIND, HEAD), 1)
 conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
@@ -499,16 +529,19 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 bulk_g2s(w_smem + t * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
                          S::TAP_BYTES, wbar);
             uint32_t n = 0;
+            uint32_t ntrace_p = 0;
             const int in_cb0_k4 = p.in_cb0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
+                const Item it = decode_item<th_of(KIND), twstep_of(KIND)>(p, item);
                 const int nout = it.d1 - it.d0;
                 const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : ((KIND == 1 || KIND == 4) ? 2 * nout + 1 : nout + 1);   // KIND 2/5: nout + 1
                 const int pl0 = (KIND == 0 || KIND == 3) ? it.d0 - 1 : ((KIND == 1 || KIND == 4) ? 2 * it.d0 - 1 : it.d0);
                 for (int j = 0; j < nplanes; ++j, ++n) {
                     const int pl = pl0 + j;
                     const uint32_t slot = n % NSTAGE;
+                    trace_stamp(p, 2, ntrace_p);                               // [0] plane wanted
                     mbar_wait(&empty[slot], ((n / NSTAGE) & 1) ^ 1);
+                    trace_stamp(p, 2, ntrace_p);                               // [1] stage free, TMA issued next
                     unsigned char* dst = planes + slot * S::STAGE_BYTES;
                     if (KIND == 0) {
                         mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 18 * 10 * 16);
@@ -569,8 +602,9 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 return desc_of(b_lo0 + ((tap * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4), b_hi);
             };
             uint32_t n_base = 0, t_base = 0;
+            uint32_t ntrace = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
+                const Item it = decode_item<th_of(KIND), twstep_of(KIND)>(p, item);
                 const int nout = it.d1 - it.d0;
                 if (KIND == 0) {
                     constexpr uint32_t LBO_A = 18 * 10 * 16, SBO_A = 10 * 16;
@@ -625,56 +659,86 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     n_base += nout + 2;
                     t_base += nout;
                 } else if (KIND == 3) {
-                    constexpr uint32_t LBO_A = 10 * 16 * 16, SBO_A = 8 * 16;   // 10 rows of 256 bytes per channel block
+                    constexpr uint32_t LBO_A = (K3_TH + 2) * K3_TW * 16, SBO_A = 8 * 16;   // 6 rows of 512 bytes per channel block
                     constexpr uint32_t idesc_hi3 = make_idesc(3 * NB, FP16 ? 0u : 1u);     // A_lo x [Whi kw0..2]
                     constexpr uint32_t a_hiw = desc_hi(SBO_A);
                     // ring slot of plane (n_base + od), kept as a wrapping counter (no modulo in the loop)
                     uint32_t slot = n_base % NSTAGE, phase = (n_base / NSTAGE) & 1;
                     uint32_t wslot = slot, wphase = phase;                     // next plane to wait for
+                    // The barrier waits of plane od+1 (its newest input plane, its accumulator buffer) are taken in the
+                    // MIDDLE of issuing plane od -- after the kd = 0, 1 MMAs, before the kd = 2 ones -- so that the issue of
+                    // consecutive planes is back to back.  Measured (tools/tc_trace.py): tcgen05.mma issue is synchronous
+                    // with execution (issuing a plane's 36 MMAs takes the 2660 cycles they execute in), and the two
+                    // mbarrier waits between planes, although always satisfied, cost ~550 cycles of idle tensor pipe.
                     int waited = 0;
-                    for (int od = 0; od < nout; ++od) {
-                        while (waited < od + 3) {
+                    auto wait_inputs = [&](int upto) {                         // planes [.., upto) of this item present
+                        while (waited < upto) {
                             mbar_wait(&full[wslot], wphase);
                             if (++wslot == NSTAGE) { wslot = 0; wphase ^= 1; }
                             ++waited;
                         }
+                    };
+                    wait_inputs(3);
+                    mbar_wait(&tempty[t_base & 1], ((t_base >> 1) & 1) ^ 1);
+                    tcgen05_fence_after();
+                    for (int od = 0; od < nout; ++od) {
                         const uint32_t t = t_base + od;
                         const uint32_t buf = t & 1;
-                        mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
-                        tcgen05_fence_after();
                         const uint32_t s1 = slot + 1 >= NSTAGE ? slot + 1 - NSTAGE : slot + 1;
                         const uint32_t s2 = slot + 2 >= NSTAGE ? slot + 2 - NSTAGE : slot + 2;
-                        if (elect_one()) {
-                            const uint32_t acc = tmem_base + buf * S::ACC_COLS;
-                            const uint32_t a_lo_kd[3] = {desc_lo(planes_addr + slot * S::STAGE_BYTES, LBO_A),
-                                                         desc_lo(planes_addr + s1 * S::STAGE_BYTES, LBO_A),
-                                                         desc_lo(planes_addr + s2 * S::STAGE_BYTES, LBO_A)};
+                        const uint32_t acc = tmem_base + buf * S::ACC_COLS;
+                        const uint32_t a_lo_kd[3] = {desc_lo(planes_addr + slot * S::STAGE_BYTES, LBO_A),
+                                                     desc_lo(planes_addr + s1 * S::STAGE_BYTES, LBO_A),
+                                                     desc_lo(planes_addr + s2 * S::STAGE_BYTES, LBO_A)};
+                        auto issue_kd = [&](int kd) {
 #pragma unroll
-                            for (int kd = 0; kd < 3; ++kd) {
+                            for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                                for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                                    for (int kk = 0; kk < CBK / 2; ++kk) {
-                                        const uint32_t b_lo = b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4);
-                                        const uint32_t a_off = kh * (TW3 * 16) + 2 * kk * LBO_A;
-                                        if (kd == 0 && kh == 0 && kk == 0)
-                                            mma_f16_ss<false>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
-                                        else
-                                            mma_f16_ss<true>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
-                                        if (SPLIT)   // lo*Whi of the three kw lands on the (small) hi*Wlo columns
-                                            mma_f16_ss<true>(acc + 3 * NB, a_lo_kd[kd] + ((S::PLANE_BYTES + a_off) >> 4), a_hiw, b_lo, b_hi,
-                                                             idesc_hi3);
-                                    }
+                                for (int kk = 0; kk < CBK / 2; ++kk) {
+                                    const uint32_t b_lo = b_lo0 + (((kd * 3 + kh) * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4);
+                                    const uint32_t a_off = kh * (K3_TW * 16) + 2 * kk * LBO_A;
+                                    if (kd == 0 && kh == 0 && kk == 0)
+                                        mma_f16_ss<false>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
+                                    else
+                                        mma_f16_ss<true>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
+                                    if (SPLIT)   // lo*Whi of the three kw lands on the (small) hi*Wlo columns
+                                        mma_f16_ss<true>(acc + 3 * NB, a_lo_kd[kd] + ((S::PLANE_BYTES + a_off) >> 4), a_hiw, b_lo, b_hi,
+                                                         idesc_hi3);
                                 }
                             }
+                        };
+                        // one elected lane does everything for the plane: the issue stream must not pause (see above)
+                        const bool more = od + 1 < nout;
+                        if (elect_one()) {
+                            trace_stamp(p, 0, ntrace);                         // [0] plane start
+                            issue_kd(0);
+                            issue_kd(1);
+                            trace_stamp(p, 0, ntrace);                         // [1] kd 0,1 issued
+                            if (more) {                                        // barriers of the NEXT plane (already complete
+                                                                               // in steady state: one overlapped poll)
+                                uint64_t* bt = &tempty[buf ^ 1];
+                                const uint32_t pt = (((t + 1) >> 1) & 1) ^ 1;
+                                if (!mbar_try_wait2(&full[wslot], wphase, bt, pt)) {
+                                    mbar_wait(&full[wslot], wphase);
+                                    mbar_wait(bt, pt);
+                                }
+                                tcgen05_fence_after();
+                            }
+                            trace_stamp(p, 0, ntrace);                         // [2] next plane's barriers passed
+                            issue_kd(2);
                             commit_one(&tfull[buf]);
                             commit_one(&empty[slot]);
                             if (od == nout - 1) {
                                 commit_one(&empty[s1]);
                                 commit_one(&empty[s2]);
                             }
+                            trace_stamp(p, 0, ntrace);                         // [3] plane's MMAs issued
                         }
                         __syncwarp();
+                        if (more) {                                            // warp-uniform bookkeeping of the wait above
+                            if (++wslot == NSTAGE) { wslot = 0; wphase ^= 1; }
+                            ++waited;
+                        }
                         if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
                     }
                     n_base += nout + 2;
@@ -871,7 +935,9 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         // ================================ epilogue =====================================
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
-        const int hl = (KIND == 3 || KIND == 4) ? (m >> 4) : (m >> 3), wl = (KIND == 3 || KIND == 4) ? (m & 15) : (m & 7);
+        // row / column of this thread's accumulator row inside the M tile
+        const int hl = KIND == 3 ? (m >> 5) : (KIND == 4 ? (m >> 4) : (m >> 3));
+        const int wl = KIND == 3 ? (m & 31) : (KIND == 4 ? (m & 15) : (m & 7));
         // KIND 3/4 (not the fused-head variant): two warps per TMEM lane quarter, each owns 16 of the 32 channels
         constexpr bool HALVES = (KIND == 3 || KIND == 4) && !HEAD;
         const int half = HALVES ? ((warp - 2) >> 2) : 0;
@@ -882,13 +948,15 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             bias[c] = (p.bias && cc < p.n_valid_out && (!HALVES || c < 16)) ? __ldg(p.bias + cc) : 0.f;
         }
         uint32_t t = 0;
+        uint32_t ntrace = 0;
+        const bool tracer = (warp == 2 && lane == 0);
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const Item it = decode_item<((KIND == 3 || KIND == 4) ? TH3 : TH), ((KIND == 3 || KIND == 4) ? TWV : TW)>(p, item);
+            const Item it = decode_item<th_of(KIND), twstep_of(KIND)>(p, item);
             const int h = it.h0 + hl;
             // KIND 3/4: tile columns are input columns w0-1 .. w0+14; KIND 4 keeps the even centres (ow = w/2)
             const int win = it.w0 - 1 + wl;
             const int w = KIND == 3 ? win : (KIND == 4 ? (win >> 1) : it.w0 + wl);
-            const bool valid = KIND == 3 ? (h < p.Hm && wl >= 1 && wl <= TWV && w < p.Wm)
+            const bool valid = KIND == 3 ? (h < p.Hm && wl >= 1 && wl <= K3_TWV && w < p.Wm)
                              : KIND == 4 ? (h < p.Hm && wl >= 1 && wl <= TWV && (win & 1) == 0 && win < p.Wm)
                                          : (h < p.Hm && w < p.Wm);
             for (int d = it.d0; d < it.d1; ++d) {
@@ -904,8 +972,10 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             if (p.res_lo) prefetch_l1(p.res_lo + ri);
                         }
                     }
+                    if (tracer) trace_stamp(p, 1, ntrace);                     // [0] epilogue ready for the plane
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
                     tcgen05_fence_after();
+                    if (tracer) trace_stamp(p, 1, ntrace);                     // [1] accumulator complete
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
                     float v[NB];
                     // out(w) = D'[w-1][kw=0] + D'[w][kw=1] + D'[w+1][kw=2]; lanes of one tile row are adjacent
@@ -947,6 +1017,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
+                    if (tracer) trace_stamp(p, 1, ntrace);                     // [2] TMEM drained, buffer released
                     ++t;
                     if (valid) {
                         if constexpr (HEAD) {
@@ -958,6 +1029,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             store_voxel<FP16, 2>(p, v, bias, it.b, d, h, w, half * 2);
                         }
                     }
+                    if (tracer) trace_stamp(p, 1, ntrace);                     // [3] stores issued
                 } else if (KIND != 2 && KIND != 5) {
                     const uint32_t buf = t & 1;
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
@@ -1242,6 +1314,12 @@ extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_bl
     return check_launch("pack_weights_kernel");
 }
 
+static long long* g_trace = nullptr;
+extern "C" int dmb_b200_debug_set_trace(long long* device_buffer) {   // 3 roles x 4096 stamps, or NULL to stop
+    g_trace = device_buffer;
+    return DMB_OK;
+}
+
 static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
                           const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
                           int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind,
@@ -1274,6 +1352,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     const int CBS = Cin / 8;
 
     Params p;
+    p.trace = g_trace;
     p.head_w = head_w;
     p.head_t = head_t;
     p.B = (kind == 1) ? 1 : B;
@@ -1286,18 +1365,31 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     p.Wo = same ? W : (s2 ? W / 2 : 2 * W);
     p.n_valid_out = scalar_out ? 1 : nbo;
     p.acc_scale = 1.0f / w_scale;
-    p.tiles_h = (int)cdiv(p.Hm, (kind == 3 || kind == 4) ? TH3 : TH);
-    p.tiles_w = (int)cdiv(p.Wm, (kind == 3 || kind == 4) ? TWV : TW);
+    p.tiles_h = (int)cdiv(p.Hm, th_of(kind));
+    p.tiles_w = (int)cdiv(p.Wm, twstep_of(kind));
     // depth segments: ~8 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
     // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
     const int cols = p.tiles_h * p.tiles_w * p.B;
-    static int items_per_sm = 0;      // tuning knob (DMB_B200_TC_ITEMS_PER_SM); 8 measured best (2: 5.37 ms, 4: 4.83, 8: 4.60, 12: 4.58)
-    if (items_per_sm == 0) {
+    static int items_per_sm = -1;     // DMB_B200_TC_ITEMS_PER_SM > 0: the old fixed rule (~that many items per CTA)
+    if (items_per_sm < 0) {
         const char* e = getenv("DMB_B200_TC_ITEMS_PER_SM");
-        items_per_sm = e ? atoi(e) : 8;
-        if (items_per_sm < 1 || items_per_sm > 64) items_per_sm = 8;
+        items_per_sm = e ? atoi(e) : 0;
+        if (items_per_sm < 0 || items_per_sm > 64) items_per_sm = 0;
     }
-    int nseg = (int)cdiv((int64_t)sm_count() * items_per_sm, cols);
+    int nseg;
+    if (items_per_sm > 0) {
+        nseg = (int)cdiv((int64_t)sm_count() * items_per_sm, cols);
+    } else {
+        // static schedule: the slowest CTA runs ceil(items / SMs) items of seg_len planes each, every item costing
+        // about one extra plane (halo loads, pipeline restart).  Take the segment count that minimises that.
+        int64_t best = -1;
+        nseg = 1;
+        for (int c = 1; c <= (p.Dm + 1) / 2; ++c) {
+            const int sl = (int)cdiv(p.Dm, c), ns = (int)cdiv(p.Dm, sl);
+            const int64_t cost = cdiv((int64_t)cols * ns, sm_count()) * (sl + 1);
+            if (best < 0 || cost < best) { best = cost; nseg = ns; }
+        }
+    }
     if (nseg > p.Dm / 2) nseg = p.Dm / 2;
     if (nseg < 1) nseg = 1;
     p.seg_len = (int)cdiv(p.Dm, nseg);
@@ -1332,7 +1424,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
             if (rc) return rc;
             for (int i = 4; i < 8; ++i) maps.m[i] = maps.m[0];
         } else {
-            const int bh = (kind == 2 || kind == 5) ? 17 : (kind == 3 ? TH3 + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? TW3 : 9);
+            const int bh = (kind == 2 || kind == 5) ? 17 : (kind == 3 ? K3_TH + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? K3_TW : 9);
             rc = make_dense_map(&maps.m[0], xh, B, CBS, D, H, W, bh, bw, cbk, fp16);
             if (rc) return rc;
             rc = make_dense_map(&maps.m[1], xl, B, CBS, D, H, W, bh, bw, cbk, fp16);

@@ -186,6 +186,9 @@ int dmb_b200_conv3d_tc_head(const void* x_hi, const void* x_lo, const void* w_bl
                             const float* head_w, float* head_t, int B, int D, int H, int W, int relu, int fp16,
                             void* stream);
 int dmb_b200_head_gather(const float* head_t, const float* res, float* y, int B, int D, int H, int W, void* stream);
+/* Debug: device buffer of 3 x 4096 int64 that CTA 0 of every following conv3d_tc launch fills with clock64()
+ * stamps of its MMA-issue, epilogue and TMA-producer roles (tools/tc_trace.py); NULL switches tracing off. */
+int dmb_b200_debug_set_trace(long long* device_buffer);
 /* w_packed: [27][Cin][Cout] float32 (the conv3d_direct packing; for kind 2 the ConvTranspose3d
  * weight packed the same way, un-flipped) -> w_blob (16-bit), one [27][cbk][32|64][8] block per
  * (32 out, 8*cbk in) channel pair; split=1 stores hi rows then lo rows.  `scale` (a power of two)
