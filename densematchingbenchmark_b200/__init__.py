@@ -12,6 +12,7 @@ from .modeling.stereo.cost_processors import (  # noqa: F401
     DeferredCost,
 )
 from .modeling.stereo.disp_predictors import PREDICTORS, build_disp_predictor  # noqa: F401
+from .modeling.stereo.losses import StereoFocalLoss  # noqa: F401
 from .utils.config import ConfigDict, load_config  # noqa: F401
 from .dropin import install_into_dmb  # noqa: F401
 

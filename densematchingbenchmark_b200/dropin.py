@@ -35,4 +35,13 @@ def install_into_dmb(dmb_module_name="dmb"):
         replaced["ops"] = ["GateRecurrent2dnoind"]
     except Exception:   # the reference's dmb.ops import needs its compiled extension
         pass
+    # losses: the builder constructs `StereoFocalLoss` and dispatches on isinstance(..., StereoFocalLoss) through its
+    # module-level name (dmb/modeling/stereo/losses/builder.py:3,39,70) -- rebinding that name swaps both
+    try:
+        ref_loss = importlib.import_module(dmb_module_name + ".modeling.stereo.losses.builder")
+        from .modeling.stereo.losses import StereoFocalLoss
+        ref_loss.StereoFocalLoss = StereoFocalLoss
+        replaced["losses"] = ["StereoFocalLoss"]
+    except Exception:
+        pass
     return replaced

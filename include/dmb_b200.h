@@ -186,6 +186,27 @@ int dmb_b200_conv3d_tc_head(const void* x_hi, const void* x_lo, const void* w_bl
                             const float* head_w, float* head_t, int B, int D, int H, int W, int relu, int fp16,
                             void* stream);
 int dmb_b200_head_gather(const float* head_t, const float* res, float* y, int B, int D, int H, int W, void* stream);
+/* ------------------------------------------------------------------------------------------
+ * Stereo focal loss on a raw cost volume.  Replaces
+ * StereoFocalLoss.loss_per_level (losses/stereo_focal_loss.py:63-101) + LaplaceDisp2Prob (losses/utils/
+ * disp2prob.py:29-173) and their autograd: one pass over the volume per direction instead of five materialised
+ * [B,D,H,W] intermediates.  cost [B,D,H,W]; gt [B,1,H,W] already at the cost's resolution (the caller rescales /
+ * pools it, stereo_focal_loss.py:66-73); variance = var_map [B,1,H,W] or (NULL, var_scalar); the disparity samples
+ * are either shared (disp_values [D], device) or per pixel (disp_sample [B,D,H,W]) -- exactly one of the two.
+ * lower/upper: the outer validity mask lower < gt < upper (:78-81); inner_end = start + max_disp - 1 (disp2prob.py:60).
+ * forward : sums[0] += sum of the per-pixel losses, sums[1] += number of valid pixels (float64, zeroed by the
+ *           caller; loss = sums[0] / max(sums[1], 1)); stats [B,2,H,W] (log-partition, weight sum) for backward or NULL.
+ * backward: gscale = device pointer to (upstream gradient * level weight / max(#valid, 1)); writes dcost [B,D,H,W]
+ *           and, when dvar != NULL (needs var_map), d(loss)/d(variance) [B,1,H,W]. */
+int dmb_b200_focal_loss_forward(const float* cost, const float* gt, const float* var_map, float var_scalar,
+                                const float* disp_values, const float* disp_sample, int B, int D, int H, int W,
+                                float lower, float upper, float inner_end, float coefficient, double* sums, float* stats,
+                                void* stream);
+int dmb_b200_focal_loss_backward(const float* cost, const float* gt, const float* var_map, float var_scalar,
+                                 const float* disp_values, const float* disp_sample, const float* stats,
+                                 const float* gscale, int B, int D, int H, int W, float lower, float upper,
+                                 float inner_end, float coefficient, float* dcost, float* dvar, void* stream);
+
 /* Debug: device buffer of 3 x 4096 int64 that CTA 0 of every following conv3d_tc launch fills with clock64()
  * stamps of its MMA-issue, epilogue and TMA-producer roles (tools/tc_trace.py); NULL switches tracing off. */
 int dmb_b200_debug_set_trace(long long* device_buffer);

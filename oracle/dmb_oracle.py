@@ -28,6 +28,53 @@ BN_EPS = 1e-5  # nn.BatchNorm3d default, layers/basic_layers.py:74
 
 
 # --------------------------------------------------------------------------------------
+# stereo focal loss (the consumer of the raw cost volumes in AcfNet training)
+# --------------------------------------------------------------------------------------
+def laplace_disp2prob(gt, max_disp, variance=1.0, start_disp=0, dilation=1, disp_sample=None):
+    """losses/utils/disp2prob.py:29-173 (Disp2Prob.getProb + LaplaceDisp2Prob): ground-truth disparity map
+    [B,1,H,W] -> probability volume [B,n,H,W]: softmax over the samples of -|d - gt| / variance, zeroed where gt
+    is outside (start, start + max_disp - 1) (the INNER mask, with `end = start + max_disp - 1`, :60,:126-128),
+    plus eps = 1e-40 (:63,:137)."""
+    B, _, H, W = gt.shape
+    end = start_disp + max_disp - 1
+    if disp_sample is None:
+        n = (max_disp + dilation - 1) // dilation
+        disp_sample = torch.linspace(start_disp, end, n).view(1, n, 1, 1).expand(B, n, H, W)
+    mask = ((gt > start_disp) & (gt < end)).to(gt.dtype)
+    gt = gt * mask
+    cost = -torch.abs(disp_sample - gt) / variance
+    return F.softmax(cost, dim=1) * mask + 1e-40
+
+
+def stereo_focal_loss(est_cost, gt_disp, variance, max_disp, start_disp=0, dilation=1, focal_coefficient=0.0,
+                      sparse=False, disp_sample=None):
+    """StereoFocalLoss.loss_per_level (losses/stereo_focal_loss.py:63-101) for one cost volume [B,D,H,W]:
+    the ground truth is rescaled (and average- / max-pooled) to the cost's resolution (:66-73), masked to
+    (start, start + int(max_disp / scale)) (:78-81), turned into a Laplace distribution over the disparity samples,
+    and  loss = -sum(gtProb * log_softmax(cost) * (1 - gtProb)^(-coefficient) * mask) / max(#valid, 1)  (:95-99)."""
+    B, D, H, W = est_cost.shape
+    gt = gt_disp.clone()
+    scale = 1.0
+    if gt_disp.shape[-2] != H or gt_disp.shape[-1] != W:
+        scale = gt_disp.shape[-1] / (W * 1.0)
+        gt = gt / scale
+        gt = (F.adaptive_max_pool2d if sparse else F.adaptive_avg_pool2d)(gt, (H, W))
+    lower = start_disp
+    upper = lower + int(max_disp / scale)
+    mask = ((gt > lower) & (gt < upper)).to(gt.dtype)
+    if float(mask.sum()) < 1.0:
+        gt_prob = torch.zeros_like(est_cost)
+    else:
+        gt_prob = laplace_disp2prob(gt * mask, int(max_disp / scale), variance, start_disp, dilation, disp_sample)
+    valid = float(mask.sum())
+    if valid < 1.0:
+        valid = 1.0
+    log_prob = F.log_softmax(est_cost, dim=1)
+    weight = (1.0 - gt_prob).pow(-focal_coefficient)
+    return -((gt_prob * log_prob) * weight * mask).sum() / valid
+
+
+# --------------------------------------------------------------------------------------
 # disparity sampling
 # --------------------------------------------------------------------------------------
 def disp_count(max_disp, dilation=1):

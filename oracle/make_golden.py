@@ -221,6 +221,53 @@ def gen_hourglass():
     print("hourglass.pt")
 
 
+FOCAL_CASES = [
+    # name, B, D (= samples), cost H, W, gt H, W, max_disp, start_disp, dilation, coefficient, sparse, variance kind
+    ("full_res_fc0_scalar_var", 2, 24, 8, 16, 8, 16, 24, 0, 1, 0.0, False, "scalar"),
+    ("full_res_fc5_tensor_var", 2, 24, 8, 16, 8, 16, 24, 0, 1, 5.0, False, "tensor"),      # AcfNet adaptive
+    ("half_res_fc5_tensor_var", 2, 12, 8, 16, 16, 32, 24, 0, 1, 5.0, False, "tensor"),     # cost at 1/2 of the gt
+    ("sparse_fc2", 1, 16, 6, 10, 12, 20, 32, 0, 1, 2.0, True, "scalar"),                   # KITTI-style zeros
+    ("start_dilation", 1, 10, 5, 7, 5, 7, 20, -4, 2, 1.0, False, "tensor"),
+    ("all_invalid", 1, 8, 4, 5, 4, 5, 8, 0, 1, 5.0, False, "scalar"),
+]
+
+
+def focal_inputs(case):
+    name, B, D, H, W, Hg, Wg, max_disp, start, dil, fc, sparse, vkind = case
+    g = torch.Generator().manual_seed(len(name) * 7 + D)
+    cost = torch.randn(B, D, H, W, generator=g) * 3.0
+    gt = torch.rand(B, 1, Hg, Wg, generator=g) * (max_disp + 6) + start - 3        # some outside the range
+    if sparse:
+        gt = gt * (torch.rand(B, 1, Hg, Wg, generator=g) > 0.5)
+    if name == "all_invalid":
+        gt = torch.full((B, 1, Hg, Wg), 1000.0)
+    var = 1.2 if vkind == "scalar" else torch.rand(B, 1, H, W, generator=g) * 1.5 + 0.5
+    return cost, gt, var
+
+
+def gen_focal_loss():
+    """StereoFocalLoss of the reference (losses/stereo_focal_loss.py) on seeded inputs: loss, d/dcost, d/dvariance."""
+    ref_import.install()
+    from dmb.modeling.stereo.losses.stereo_focal_loss import StereoFocalLoss
+    out = {}
+    for case in FOCAL_CASES:
+        name, B, D, H, W, Hg, Wg, max_disp, start, dil, fc, sparse, vkind = case
+        cost, gt, var = focal_inputs(case)
+        cost = cost.clone().requires_grad_(True)
+        if torch.is_tensor(var):
+            var = var.clone().requires_grad_(True)
+        ev = StereoFocalLoss(max_disp=max_disp, start_disp=start, dilation=dil, weights=(0.7,), focal_coefficient=fc,
+                             sparse=sparse)
+        loss = ev(cost, gt, var)["stereo_focal_loss_lvl0"]
+        if loss.requires_grad:
+            loss.backward()
+        out[name] = dict(loss=float(loss), dcost=cost.grad.clone() if cost.grad is not None else torch.zeros_like(cost),
+                         dvar=(var.grad.clone() if torch.is_tensor(var) and var.grad is not None else None))
+        print("focal", name, float(loss))
+    torch.save(out, os.path.join(OUT, "focal_loss.pt"))
+    print("focal_loss.pt")
+
+
 def gen_epe():
     # the package __init__ chain pulls visualisation deps; load the single file instead
     import importlib.util
@@ -246,3 +293,4 @@ if __name__ == "__main__":
     gen_epe()
     gen_aggregators()
     gen_train_step()
+    gen_focal_loss()

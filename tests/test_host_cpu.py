@@ -189,3 +189,10 @@ def test_dropin_swaps_reference_tables(P):
     assert type(proc).__module__.startswith("densematchingbenchmark_b200")
     assert type(proc.aggregator).__module__.startswith("densematchingbenchmark_b200")
     assert type(build_disp_predictor(cfg)).__module__.startswith("densematchingbenchmark_b200")
+    # the loss builder of the AcfNet config now constructs (and dispatches on) our fused StereoFocalLoss
+    assert replaced.get("losses") == ["StereoFocalLoss"]
+    acf = ref_import.load_config("configs/AcfNet/scene_flow_adaptive.py")
+    from dmb.modeling.stereo.losses.builder import make_focal_loss_evaluator
+    ev = make_focal_loss_evaluator(acf)
+    assert type(ev).__module__.startswith("densematchingbenchmark_b200")
+    assert (ev.max_disp, ev.focal_coefficient, tuple(ev.weights)) == (192, 5.0, (1.0, 0.7, 0.5))

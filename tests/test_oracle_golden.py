@@ -171,3 +171,27 @@ def test_train_step_matches_reference(golden_dir, kind):
         check_grad_summary(got["grads"][k], want, what=k)
     for k, want in rec["running"].items():
         torch.testing.assert_close(got["running"][k].to(want.dtype), want, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------------------------------------------ stereo focal loss
+def test_focal_loss_oracle_vs_reference_golden(golden_dir):
+    """oracle.stereo_focal_loss (value and autograd) == the reference's StereoFocalLoss on the seeded cases of
+    oracle/make_golden.py:FOCAL_CASES (resolution change, sparse pooling, focal coefficient, tensor variance,
+    start / dilation, no valid pixel)."""
+    from make_golden import FOCAL_CASES, focal_inputs
+    rec = torch.load(os.path.join(golden_dir, "focal_loss.pt"), weights_only=False)
+    for case in FOCAL_CASES:
+        name, B, D, H, W, Hg, Wg, max_disp, start, dil, fc, sparse, vkind = case
+        cost, gt, var = focal_inputs(case)
+        cost = cost.clone().requires_grad_(True)
+        if torch.is_tensor(var):
+            var = var.clone().requires_grad_(True)
+        loss = 0.7 * O.stereo_focal_loss(cost, gt, var, max_disp, start, dil, fc, sparse)
+        if loss.requires_grad:
+            loss.backward()
+        want = rec[name]
+        assert abs(float(loss) - want["loss"]) <= 1e-6 * max(1.0, abs(want["loss"])), name
+        got_dc = cost.grad if cost.grad is not None else torch.zeros_like(cost)
+        torch.testing.assert_close(got_dc, want["dcost"], rtol=1e-5, atol=1e-7)
+        if want["dvar"] is not None:
+            torch.testing.assert_close(var.grad, want["dvar"], rtol=1e-5, atol=1e-7)
