@@ -138,16 +138,23 @@ def _blob(layer, split, fp16):
     return val
 
 
-def pack_blob(w, kind, split, fp16):
-    """w: packed fp32 weight [27,Cin,Cout] (ops.functional.pack_conv_weight) -> (tcgen05 blob, Cin, Cout, scale)."""
+def weight_scale(w):
+    """Power-of-two pre-scale of an fp16 weight blob: the largest |w| lands in [4, 8) so that the `lo` halves stay
+    normal.  Reads max|w| back to the host (one synchronisation)."""
+    import math
+    wmax = float(w.abs().max())
+    return 2.0 ** max(-14, min(14, math.floor(math.log2(8.0 / wmax)))) if wmax > 0 else 1.0
+
+
+def pack_blob(w, kind, split, fp16, scale=None):
+    """w: packed fp32 weight [27,Cin,Cout] (ops.functional.pack_conv_weight) -> (tcgen05 blob, Cin, Cout, scale).
+    `scale`: a pre-computed weight_scale() -- training re-packs every step and must not synchronise every time;
+    None computes it here.  bfloat16 blobs are never scaled (full fp32 exponent range)."""
     K3, Cin, Cout = w.shape
-    scale = 1.0
-    if fp16:
-        # power-of-two pre-scale: largest |w| lands in [4, 8) so that the `lo` halves stay normal
-        wmax = float(w.abs().max())
-        if wmax > 0:
-            import math
-            scale = 2.0 ** max(-14, min(14, math.floor(math.log2(8.0 / wmax))))
+    if not fp16:
+        scale = 1.0
+    elif scale is None:
+        scale = weight_scale(w)
     nbytes = C.load().dmb_b200_conv3d_tc_weight_bytes(Cin, Cout, 1 if split else 0, kind)
     blob = torch.empty(nbytes // 2, dtype=torch.float16 if fp16 else torch.bfloat16, device=w.device)
     C.call("dmb_b200_conv3d_tc_pack_weights", C.ptr(w), C.ptr(blob), Cin, Cout, 1 if split else 0,
@@ -187,14 +194,27 @@ def conv_tc_raw(x, blob, bias, Cin, Cout, scale, kind, residual=None, relu=False
     return y
 
 
-def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False):
+def cached_weight_scale(param, w_packed, refresh=64):
+    """weight_scale() of a trainable weight, cached on the Parameter and refreshed every `refresh` in-place updates
+    (optimizer steps): the scale only has to keep |w| * scale inside fp16's range with the `lo` halves normal, and
+    max|w| drifts slowly -- one host synchronisation per layer every `refresh` steps instead of every step."""
+    hit = param.__dict__.get("_dmb_b200_wscale")
+    ver = param._version
+    if hit is not None and 0 <= ver - hit[0] < refresh:
+        return hit[1]
+    sc = weight_scale(w_packed)
+    param.__dict__["_dmb_b200_wscale"] = (ver, sc)
+    return sc
+
+
+def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False, scale=None):
     """One 3x3x3 / pad 1 convolution (stride 1 | stride 2 | transposed stride 2 with output_padding 1) of a float32
     NCDHW tensor on the tcgen05 kernels: layout conversion in, conv, layout conversion out.  Used by the training
     path (ops/autograd.py), whose weights change every step -- nothing is cached.  Returns float32 NCDHW."""
     split, fp16 = PRECISIONS[precision]
     kind = (_transposed_kind(w_packed.shape[1], w_packed.shape[2]) if transposed
             else ((3 if KW_MERGE else 0) if stride == 1 else (4 if KW_MERGE else 1)))
-    blob, Cin, Cout, scale = pack_blob(w_packed, kind, split, fp16)
+    blob, Cin, Cout, scale = pack_blob(w_packed, kind, split, fp16, scale)
     xb = Blocked.from_ncdhw(x, split, fp16)
     if Cout == 1:
         return conv_tc_raw(xb, blob, bias, Cin, Cout, scale, kind, None, relu, residual)

@@ -27,18 +27,23 @@ TRAIN_TC_FWD = "fp16x3"
 TRAIN_TC_BWD = "bf16x3"
 
 
-def _conv(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, relu, out_dims=None, precision=None):
-    """y = act(conv(x) + bias + residual) for the training path: tcgen05 if eligible, else conv3d_direct."""
+def _conv(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, relu, out_dims=None, precision=None,
+          param=None):
+    """y = act(conv(x) + bias + residual) for the training path: tcgen05 if eligible, else conv3d_direct.
+    `param`: the weight Parameter the packed weight was made from (cache key of its fp16 pre-scale)."""
     if TRAIN_TC and precision is not None:
         from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
         K3, Cin, Cout = w_packed.shape
+        scale = None
+        if param is not None and T.PRECISIONS[precision][1]:
+            scale = T.cached_weight_scale(param, w_packed)
         if transposed and stride == 1 and tuple(ksize) == (3, 3, 3) and pad == 1 and \
                 (out_dims is None or tuple(int(v) for v in out_dims) == tuple(x.shape[2:])):
             # a stride-1 transposed convolution is the plain convolution with the taps mirrored
             if T.conv3d_tc_eligible(x, Cin, Cout, ksize, 1, pad, False, 0):
-                return T.conv3d_ncdhw_tc(x, w_packed.flip(0).contiguous(), bias, 1, False, precision, residual, relu)
+                return T.conv3d_ncdhw_tc(x, w_packed.flip(0).contiguous(), bias, 1, False, precision, residual, relu, scale)
         elif T.conv3d_tc_eligible(x, Cin, Cout, ksize, stride, pad, transposed, opad, out_dims):
-            return T.conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual, relu)
+            return T.conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual, relu, scale)
     return F_.conv3d_fused(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, relu=relu,
                            out_dims=out_dims)
 
@@ -91,10 +96,10 @@ class ConvUnitFn(torch.autograd.Function):
         ctx.has_res = residual is not None
         ctx.x_dims = tuple(x.shape[2:])
         if bn is None:
-            y = _conv(x, w_packed, b, ksize, stride, pad, transposed, opad, res, relu, precision=TRAIN_TC_FWD)
+            y = _conv(x, w_packed, b, ksize, stride, pad, transposed, opad, res, relu, precision=TRAIN_TC_FWD, param=weight)
             ctx.save_for_backward(x, weight, y if relu else None, None, None, None, None)
             return y
-        z = _conv(x, w_packed, b, ksize, stride, pad, transposed, opad, None, False, precision=TRAIN_TC_FWD)
+        z = _conv(x, w_packed, b, ksize, stride, pad, transposed, opad, None, False, precision=TRAIN_TC_FWD, param=weight)
         B, Co = z.shape[:2]
         S = z.numel() // (B * Co)
         dev = z.device

@@ -273,9 +273,9 @@ def test_training_convs_run_on_tcgen05(P, monkeypatch):
     calls = []
     real = T.conv3d_ncdhw_tc
 
-    def counting(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False):
+    def counting(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False, scale=None):
         calls.append((tuple(w_packed.shape[1:]), stride, transposed, precision))
-        return real(x, w_packed, bias, stride, transposed, precision, residual, relu)
+        return real(x, w_packed, bias, stride, transposed, precision, residual, relu, scale)
 
     monkeypatch.setattr(T, "conv3d_ncdhw_tc", counting)
     from make_golden import TRAIN_CASE
