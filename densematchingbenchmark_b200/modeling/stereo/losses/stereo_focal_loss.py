@@ -94,23 +94,22 @@ class StereoFocalLoss(object):
         return _FocalLossFn.apply(estCost, gt, var_map, var_scalar, disp_values, disp_sample, lower, upper, inner_end,
                                   self.focal_coefficient)
 
+    @staticmethod
+    def _per_level(value, levels):
+        """A per-level list stays as it is; anything else is shared by all levels."""
+        return list(value) if isinstance(value, (list, tuple)) else [value] * levels
+
     def __call__(self, estCost, gtDisp, variance, disp_sample=None):
-        if not isinstance(estCost, (list, tuple)):
-            estCost = [estCost]
-        if self.weights is None:
-            self.weights = 1.0
-        if not isinstance(self.weights, (list, tuple)):
-            self.weights = [self.weights] * len(estCost)
-        if not isinstance(self.dilation, (list, tuple)):
-            self.dilation = [self.dilation] * len(estCost)
-        if not isinstance(variance, (list, tuple)):
-            variance = [variance] * len(estCost)
-        if disp_sample is None or not isinstance(disp_sample, (list, tuple)):
-            disp_sample = [disp_sample] * len(estCost)
-        out = dict()
-        for i, (cost, var, dt, ds) in enumerate(zip(estCost, variance, self.dilation, disp_sample)):
-            out["stereo_focal_loss_lvl{}".format(i)] = self.weights[i] * self.loss_per_level(cost, gtDisp, var, dt, ds)
-        return out
+        volumes = self._per_level(estCost, 1) if not isinstance(estCost, (list, tuple)) else list(estCost)
+        levels = len(volumes)
+        # like the reference, the broadcast settings are written back to the evaluator on first use (:104-113)
+        self.weights = self._per_level(1.0 if self.weights is None else self.weights, levels)
+        self.dilation = self._per_level(self.dilation, levels)
+        result = {}
+        for lvl, (volume, var, step, samples) in enumerate(zip(volumes, self._per_level(variance, levels), self.dilation,
+                                                               self._per_level(disp_sample, levels))):
+            result["stereo_focal_loss_lvl%d" % lvl] = self.weights[lvl] * self.loss_per_level(volume, gtDisp, var, step, samples)
+        return result
 
     def __repr__(self):
         return ("{}(max_disp={}, start_disp={}, dilation={}, weights={}, focal_coefficient={}, sparse={})"
