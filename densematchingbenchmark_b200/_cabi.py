@@ -40,6 +40,7 @@ SIGNATURES = {
     "dmb_b200_conv3d_tc_head": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_head_gather": [_P, _P, _P, _I, _I, _I, _I, _P],
     "dmb_b200_debug_set_trace": [_P],
+    "dmb_b200_conv3d_tc_schedule": [_I, _I, _I, _I, _I, _IP],
     "dmb_b200_focal_loss_forward": [_P, _P, _P, _F, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P],
     "dmb_b200_focal_loss_backward": [_P, _P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _P, _P, _P],
     "dmb_b200_conv3d_tc_pack_weights": [_P, _P, _I, _I, _I, _I, _F, _I, _P],

@@ -1314,6 +1314,51 @@ extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_bl
     return check_launch("pack_weights_kernel");
 }
 
+// Geometry and static schedule of one launch: M-space / output extents, tile counts, depth segmentation.
+// Returns the grid size (persistent CTAs).  Pure host arithmetic (dmb_b200_conv3d_tc_schedule exposes it to the
+// CPU tests).
+static int plan_schedule(Params& p, int kind, int B, int D, int H, int W) {
+    p.B = (kind == 1) ? 1 : B;
+    const bool s2 = (kind == 1 || kind == 4);
+    // KIND 4 tiles W in INPUT columns (every column is computed, even centres are kept)
+    p.Dm = s2 ? D / 2 : D; p.Hm = s2 ? H / 2 : H; p.Wm = kind == 1 ? W / 2 : W;
+    const bool same = (kind == 0 || kind == 3);
+    p.Do = same ? D : (s2 ? D / 2 : 2 * D);
+    p.Ho = same ? H : (s2 ? H / 2 : 2 * H);
+    p.Wo = same ? W : (s2 ? W / 2 : 2 * W);
+    p.tiles_h = (int)cdiv(p.Hm, th_of(kind));
+    p.tiles_w = (int)cdiv(p.Wm, twstep_of(kind));
+    // depth segments: ~8 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
+    // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
+    const int cols = p.tiles_h * p.tiles_w * p.B;
+    static int items_per_sm = -1;     // DMB_B200_TC_ITEMS_PER_SM > 0: the old fixed rule (~that many items per CTA)
+    if (items_per_sm < 0) {
+        const char* e = getenv("DMB_B200_TC_ITEMS_PER_SM");
+        items_per_sm = e ? atoi(e) : 0;
+        if (items_per_sm < 0 || items_per_sm > 64) items_per_sm = 0;
+    }
+    int nseg;
+    if (items_per_sm > 0) {
+        nseg = (int)cdiv((int64_t)sm_count() * items_per_sm, cols);
+    } else {
+        // static schedule: the slowest CTA runs ceil(items / SMs) items of seg_len planes each, every item costing
+        // about one extra plane (halo loads, pipeline restart).  Take the segment count that minimises that.
+        int64_t best = -1;
+        nseg = 1;
+        for (int c = 1; c <= (p.Dm + 1) / 2; ++c) {
+            const int sl = (int)cdiv(p.Dm, c), ns = (int)cdiv(p.Dm, sl);
+            const int64_t cost = cdiv((int64_t)cols * ns, sm_count()) * (sl + 1);
+            if (best < 0 || cost < best) { best = cost; nseg = ns; }
+        }
+    }
+    if (nseg > p.Dm / 2) nseg = p.Dm / 2;
+    if (nseg < 1) nseg = 1;
+    p.seg_len = (int)cdiv(p.Dm, nseg);
+    p.nseg = (int)cdiv(p.Dm, p.seg_len);
+    p.n_items = cols * p.nseg;
+    return p.n_items < sm_count() ? p.n_items : sm_count();
+}
+
 static long long* g_trace = nullptr;
 extern "C" int dmb_b200_debug_set_trace(long long* device_buffer) {   // 3 roles x 4096 stamps, or NULL to stop
     g_trace = device_buffer;
@@ -1355,47 +1400,9 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     p.trace = g_trace;
     p.head_w = head_w;
     p.head_t = head_t;
-    p.B = (kind == 1) ? 1 : B;
-    const bool s2 = (kind == 1 || kind == 4);
-    // KIND 4 tiles W in INPUT columns (every column is computed, even centres are kept)
-    p.Dm = s2 ? D / 2 : D; p.Hm = s2 ? H / 2 : H; p.Wm = kind == 1 ? W / 2 : W;
-    const bool same = (kind == 0 || kind == 3);
-    p.Do = same ? D : (s2 ? D / 2 : 2 * D);
-    p.Ho = same ? H : (s2 ? H / 2 : 2 * H);
-    p.Wo = same ? W : (s2 ? W / 2 : 2 * W);
+    const int grid = plan_schedule(p, kind, B, D, H, W);
     p.n_valid_out = scalar_out ? 1 : nbo;
     p.acc_scale = 1.0f / w_scale;
-    p.tiles_h = (int)cdiv(p.Hm, th_of(kind));
-    p.tiles_w = (int)cdiv(p.Wm, twstep_of(kind));
-    // depth segments: ~8 work items per persistent CTA; small grids (the 1/8 and 1/16 levels of the
-    // hourglass) are cut down to 2-plane segments so that every SM gets work (halo planes are L2 hits)
-    const int cols = p.tiles_h * p.tiles_w * p.B;
-    static int items_per_sm = -1;     // DMB_B200_TC_ITEMS_PER_SM > 0: the old fixed rule (~that many items per CTA)
-    if (items_per_sm < 0) {
-        const char* e = getenv("DMB_B200_TC_ITEMS_PER_SM");
-        items_per_sm = e ? atoi(e) : 0;
-        if (items_per_sm < 0 || items_per_sm > 64) items_per_sm = 0;
-    }
-    int nseg;
-    if (items_per_sm > 0) {
-        nseg = (int)cdiv((int64_t)sm_count() * items_per_sm, cols);
-    } else {
-        // static schedule: the slowest CTA runs ceil(items / SMs) items of seg_len planes each, every item costing
-        // about one extra plane (halo loads, pipeline restart).  Take the segment count that minimises that.
-        int64_t best = -1;
-        nseg = 1;
-        for (int c = 1; c <= (p.Dm + 1) / 2; ++c) {
-            const int sl = (int)cdiv(p.Dm, c), ns = (int)cdiv(p.Dm, sl);
-            const int64_t cost = cdiv((int64_t)cols * ns, sm_count()) * (sl + 1);
-            if (best < 0 || cost < best) { best = cost; nseg = ns; }
-        }
-    }
-    if (nseg > p.Dm / 2) nseg = p.Dm / 2;
-    if (nseg < 1) nseg = 1;
-    p.seg_len = (int)cdiv(p.Dm, nseg);
-    p.nseg = (int)cdiv(p.Dm, p.seg_len);
-    p.n_items = cols * p.nseg;
-    const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
     const size_t blob = (size_t)TAPS * cbk * (split ? 2 * nbo : nbo) * 16;
     const size_t in_batch_bytes = (size_t)CBS * D * H * W * 16;
     const size_t out_cbs = scalar_out ? 0 : Cout / 8;
@@ -1481,6 +1488,16 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                                   int relu, int fp16, void* stream) {
     return conv3d_tc_impl(x_hi, x_lo, Cin, w_blob, w_scale, bias, res_hi, res_lo, y_hi, y_lo, Cout, y_f32, res_f32, B, D, H,
                           W, kind, relu, fp16, nullptr, nullptr, stream);
+}
+
+extern "C" int dmb_b200_conv3d_tc_schedule(int kind, int B, int D, int H, int W, int* out) {
+    DMB_REQUIRE(out, "conv3d_tc_schedule: null output");
+    DMB_REQUIRE(kind >= 0 && kind <= 5 && B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc_schedule: bad arguments");
+    Params p;
+    const int grid = plan_schedule(p, kind, B, D, H, W);
+    out[0] = p.tiles_h; out[1] = p.tiles_w; out[2] = p.nseg; out[3] = p.seg_len; out[4] = p.n_items; out[5] = grid;
+    out[6] = th_of(kind); out[7] = twstep_of(kind);
+    return DMB_OK;
 }
 
 extern "C" int dmb_b200_conv3d_tc_head(const void* x_hi, const void* x_lo, const void* w_blob, float w_scale,

@@ -207,6 +207,9 @@ int dmb_b200_focal_loss_backward(const float* cost, const float* gt, const float
                                  const float* gscale, int B, int D, int H, int W, float lower, float upper,
                                  float inner_end, float coefficient, float* dcost, float* dvar, void* stream);
 
+/* The static schedule dmb_b200_conv3d_tc would use for input extents B,D,H,W (host arithmetic only; no launch):
+ * out[8] = {tiles_h, tiles_w, depth segments, planes per segment, work items, grid, tile rows, tile column step}. */
+int dmb_b200_conv3d_tc_schedule(int kind, int B, int D, int H, int W, int* out);
 /* Debug: device buffer of 3 x 4096 int64 that CTA 0 of every following conv3d_tc launch fills with clock64()
  * stamps of its MMA-issue, epilogue and TMA-producer roles (tools/tc_trace.py); NULL switches tracing off. */
 int dmb_b200_debug_set_trace(long long* device_buffer);

@@ -196,3 +196,55 @@ def test_dropin_swaps_reference_tables(P):
     ev = make_focal_loss_evaluator(acf)
     assert type(ev).__module__.startswith("densematchingbenchmark_b200")
     assert (ev.max_disp, ev.focal_coefficient, tuple(ev.weights)) == (192, 5.0, (1.0, 0.7, 0.5))
+
+
+def test_tc_schedule_tiles_and_depth_segments(P):
+    """Host arithmetic of the tcgen05 launches (no GPU): the 4x32 stride-1 tile (30 output columns per step) tiles
+    the PSMNet grids exactly, depth segments cover every output plane exactly once, and the slowest persistent CTA
+    of the static schedule stays close to the average load at the config-2 sizes."""
+    import ctypes
+    from densematchingbenchmark_b200 import _cabi as C
+
+    def sched(kind, B, D, H, W):
+        out = (ctypes.c_int * 8)()
+        C.call("dmb_b200_conv3d_tc_schedule", kind, B, D, H, W, out)
+        return dict(zip(("tiles_h", "tiles_w", "nseg", "seg_len", "items", "grid", "th", "tw"), list(out)))
+
+    # exact tiling of the 1/4, 1/8, 1/16 grids of a 544x960 image by the stride-1 kernel (kind 3)
+    for (D, H, W), tiles in (((48, 136, 240), (34, 8)), ((24, 68, 120), (17, 4)), ((12, 34, 60), (9, 2))):
+        s3 = sched(3, 1, D, H, W)
+        assert (s3["th"], s3["tw"]) == (4, 30)
+        assert (s3["tiles_h"], s3["tiles_w"]) == tiles
+        assert s3["tiles_w"] * 30 == W                                  # no ragged last tile column
+    for kind in (0, 1, 2, 3, 4, 5):
+        for B in (1, 2, 3):
+            for (D, H, W) in ((48, 136, 240), (24, 68, 120), (12, 34, 60), (6, 10, 14), (2, 4, 8), (16, 32, 64)):
+                s_ = sched(kind, B, D, H, W)
+                Dm = D // 2 if kind in (1, 4) else D
+                assert s_["nseg"] >= 1 and s_["seg_len"] >= 1
+                assert s_["nseg"] * s_["seg_len"] >= Dm > (s_["nseg"] - 1) * s_["seg_len"]      # a partition of the planes
+                nb = 1 if kind == 1 else B
+                assert s_["items"] == s_["tiles_h"] * s_["tiles_w"] * nb * s_["nseg"]
+                assert 1 <= s_["grid"] <= 148 and s_["grid"] == min(s_["items"], 148)
+    # load balance of the static schedule where it matters (the 1/4-resolution layers, batch 1 and 2)
+    for B in (1, 2):
+        s3 = sched(3, B, 48, 136, 240)
+        slowest = -(-s3["items"] // s3["grid"]) * s3["seg_len"]
+        average = s3["tiles_h"] * s3["tiles_w"] * B * 48 / 148.0
+        assert slowest <= 1.10 * average, (slowest, average)
+
+
+def test_cached_weight_scale_refreshes_with_parameter_updates(P):
+    """The fp16 weight pre-scale of the training path is a power of two, cached on the Parameter and recomputed only
+    after `refresh` in-place updates (no per-step host synchronisation)."""
+    import torch
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators import tc_engine as T
+    w = torch.nn.Parameter(torch.full((4, 4), 0.3))
+    s0 = T.cached_weight_scale(w, w.detach(), refresh=3)
+    assert s0 == 16.0                                                   # 0.3 * 16 = 4.8 in [4, 8)
+    with torch.no_grad():
+        w.mul_(100.0)                                                   # one update: still the cached value
+    assert T.cached_weight_scale(w, w.detach(), refresh=3) == s0
+    with torch.no_grad():
+        w.add_(0.0); w.add_(0.0)                                        # third update since the scale was taken
+    assert T.cached_weight_scale(w, w.detach(), refresh=3) == 0.25      # 30 * 0.25 = 7.5 in [4, 8)
