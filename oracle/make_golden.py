@@ -245,6 +245,20 @@ def focal_inputs(case):
     return cost, gt, var
 
 
+def focal_ref_test_inputs(which):
+    """The reference's own test parameterisations (tests/modeling/stereo/losses/test_stereo_focal_loss.py:17-63 and
+    :65-110): max_disp 5, start -2, h x w = 3 x 4, variance 2, coefficient 5, an all-ones cost volume; case 1 enumerates
+    the samples with dilation 2, case 2 hands them in per pixel as disp_sample = [-2, 0, 2].  (The reference draws its
+    ground truth with the global RNG; seeded here.)"""
+    g = torch.Generator().manual_seed(40 + which)
+    gt = torch.rand(1, 1, 3, 4, generator=g) * 5 - 2
+    cost = torch.ones(1, 3, 3, 4)
+    ds = None
+    if which == 2:
+        ds = torch.tensor([-2.0, 0.0, 2.0]).repeat(1, 3, 4, 1).permute(0, 3, 1, 2).contiguous()
+    return cost, gt, ds
+
+
 def gen_focal_loss():
     """StereoFocalLoss of the reference (losses/stereo_focal_loss.py) on seeded inputs: loss, d/dcost, d/dvariance."""
     ref_import.install()
@@ -264,6 +278,22 @@ def gen_focal_loss():
         out[name] = dict(loss=float(loss), dcost=cost.grad.clone() if cost.grad is not None else torch.zeros_like(cost),
                          dvar=(var.grad.clone() if torch.is_tensor(var) and var.grad is not None else None))
         print("focal", name, float(loss))
+    for which in (1, 2):
+        cost, gt, ds = focal_ref_test_inputs(which)
+        cost = cost.clone().requires_grad_(True)
+        ev = StereoFocalLoss(max_disp=5, start_disp=-2, dilation=2 if which == 1 else 1, weights=(1.0), focal_coefficient=5.0,
+                             sparse=False)
+        loss = ev(estCost=cost, gtDisp=gt, variance=2, disp_sample=ds)["stereo_focal_loss_lvl0"]
+        loss.backward()
+        out["ref_test_case%d" % which] = dict(loss=float(loss), dcost=cost.grad.clone(), dvar=None)
+        print("focal ref_test_case%d" % which, float(loss))
+    # the probability volumes of tests/modeling/stereo/losses/utils/test_disp2prob.py:13-62 (same two cases)
+    from dmb.modeling.stereo.losses.utils.disp2prob import LaplaceDisp2Prob
+    for which in (1, 2):
+        _, gt, ds = focal_ref_test_inputs(which)
+        prob = LaplaceDisp2Prob(gt.clone(), max_disp=5, variance=2, start_disp=-2, dilation=2 if which == 1 else 1,
+                                disp_sample=ds).getProb()
+        out["disp2prob_case%d" % which] = prob.clone()
     torch.save(out, os.path.join(OUT, "focal_loss.pt"))
     print("focal_loss.pt")
 

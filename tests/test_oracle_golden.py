@@ -195,3 +195,37 @@ def test_focal_loss_oracle_vs_reference_golden(golden_dir):
         torch.testing.assert_close(got_dc, want["dcost"], rtol=1e-5, atol=1e-7)
         if want["dvar"] is not None:
             torch.testing.assert_close(var.grad, want["dvar"], rtol=1e-5, atol=1e-7)
+
+
+def test_focal_loss_oracle_on_the_reference_tests_own_cases(golden_dir):
+    """tests/modeling/stereo/losses/test_stereo_focal_loss.py of the reference prints its results without asserting
+    them; the same two parameterisations (dilated enumeration, per-pixel disp_sample), run through the reference in
+    the build container, pin the oracle here."""
+    from make_golden import focal_ref_test_inputs
+    rec = torch.load(os.path.join(golden_dir, "focal_loss.pt"), weights_only=False)
+    for which in (1, 2):
+        cost, gt, ds = focal_ref_test_inputs(which)
+        cost = cost.clone().requires_grad_(True)
+        loss = O.stereo_focal_loss(cost, gt, 2, 5, start_disp=-2, dilation=2 if which == 1 else 1, focal_coefficient=5.0,
+                                   disp_sample=ds)
+        loss.backward()
+        want = rec["ref_test_case%d" % which]
+        assert abs(float(loss) - want["loss"]) <= 1e-6 * max(1.0, abs(want["loss"]))
+        torch.testing.assert_close(cost.grad, want["dcost"], rtol=1e-5, atol=1e-7)
+
+
+def test_laplace_disp2prob_oracle_vs_reference(golden_dir):
+    """LaplaceDisp2Prob.getProb on the reference's own test cases (tests/modeling/stereo/losses/utils/
+    test_disp2prob.py:13-62): dilated enumeration and per-pixel samples; probabilities sum to 1 where the ground truth
+    is inside (start, start + max - 1) and are exactly the 1e-40 floor elsewhere."""
+    from make_golden import focal_ref_test_inputs
+    rec = torch.load(os.path.join(golden_dir, "focal_loss.pt"), weights_only=False)
+    for which in (1, 2):
+        _, gt, ds = focal_ref_test_inputs(which)
+        got = O.laplace_disp2prob(gt.clone(), 5, variance=2, start_disp=-2, dilation=2 if which == 1 else 1, disp_sample=ds)
+        want = rec["disp2prob_case%d" % which]
+        assert got.shape == want.shape == (1, 3, 3, 4)
+        torch.testing.assert_close(got, want, rtol=1e-6, atol=0)
+        inside = ((gt > -2) & (gt < 2)).expand_as(got)
+        torch.testing.assert_close(got.sum(1)[inside[:, 0]], torch.ones(int(inside[:, 0].sum())), rtol=1e-6, atol=1e-6)
+        assert bool((got[~inside] < 1e-39).all())
