@@ -1,23 +1,16 @@
-"""AGGREGATORS + build_cost_aggregator (reference: cost_processors/aggregators/builder.py:8-29)."""
+"""Cost aggregators by config key (the names of dmb/modeling/stereo/cost_processors/aggregators/builder.py:8-15; the
+staged, model-specific 'DeepPruner' / 'AnyNet' processors are outside this path's scope).  As in the reference
+(:23-27) the model-level `batch_norm` switch is injected into the constructor arguments."""
+from .....utils.registry import ctor_kwargs, lookup
+from .AcfNet import AcfAggregator
 from .GCNet import GCAggregator
 from .PSMNet import PSMAggregator
-from .AcfNet import AcfAggregator
 from .StereoNet import StereoNetAggregator
 
-AGGREGATORS = {
-    "GCNet": GCAggregator,
-    "PSMNet": PSMAggregator,
-    "AcfNet": AcfAggregator,
-    "StereoNet": StereoNetAggregator,
-    # 'DeepPruner' / 'AnyNet' (staged, model-specific processors) are outside this path's scope
-}
+AGGREGATORS = dict(GCNet=GCAggregator, PSMNet=PSMAggregator, AcfNet=AcfAggregator, StereoNet=StereoNetAggregator)
 
 
 def build_cost_aggregator(cfg):
-    agg_type = cfg.model.cost_processor.cost_aggregator.type
-    assert agg_type in AGGREGATORS, "cost_aggregator type not found, excepted: {}," \
-                                    "but got {}".format(AGGREGATORS.keys(), agg_type)
-    default_args = cfg.model.cost_processor.cost_aggregator.copy()
-    default_args.pop('type')
-    default_args.update(batch_norm=cfg.model.batch_norm)
-    return AGGREGATORS[agg_type](**default_args)
+    section = cfg.model.cost_processor.cost_aggregator
+    cls = lookup(AGGREGATORS, "cost_aggregator", section.type)
+    return cls(**ctor_kwargs(section, batch_norm=cfg.model.batch_norm))

@@ -80,7 +80,5 @@ PROCESSORS = {
 
 
 def build_cost_processor(cfg):
-    proc_type = cfg.model.cost_processor.type
-    assert proc_type in PROCESSORS, "cost_processor type not found, excepted: {}," \
-                                    "but got {}".format(PROCESSORS.keys(), proc_type)
-    return PROCESSORS[proc_type](cfg=cfg)
+    from ....utils.registry import lookup
+    return lookup(PROCESSORS, "cost_processor", cfg.model.cost_processor.type)(cfg=cfg)
