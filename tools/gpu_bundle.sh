@@ -5,7 +5,6 @@
 # Everything lands in gpurun_out/ (merged back by gpurun); numbers printed under ncu are never bench values.
 set -u
 mkdir -p gpurun_out
-want() { [[ " $* " == *" all "* ]] && return 0; for s in "${SECTIONS[@]}"; do [[ "$s" == "$1" ]] && return 0; done; return 1; }
 SECTIONS=("$@")
 [[ ${#SECTIONS[@]} -eq 0 ]] && SECTIONS=(tests smoke bench)
 has() { for s in "${SECTIONS[@]}"; do [[ "$s" == "$1" || "$s" == "all" ]] && return 0; done; return 1; }
@@ -42,6 +41,7 @@ fi
 if has probes; then        # micro-benchmarks behind DESIGN.md section 5 (binaries built by the nvcc lines in their headers)
     [[ -x tools/_build/mma_probe ]] && timeout 60 tools/_build/mma_probe | head -8
     [[ -x tools/_build/mma_mn_probe ]] && timeout 60 tools/_build/mma_mn_probe
+    [[ -x tools/_build/wgrad_tc_proto ]] && { timeout 60 tools/_build/wgrad_tc_proto 0 1; timeout 60 tools/_build/wgrad_tc_proto 1 1; }
     timeout 120 python tools/tc_trace.py | head -8
     timeout 200 python tools/tc_clock.py
 fi
