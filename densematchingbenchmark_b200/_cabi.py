@@ -6,6 +6,7 @@ There is NO fallback: if `csrc/libdmb_b200.so` is missing or an entry point fail
 """
 import ctypes
 import os
+import threading
 from ctypes import c_double, c_float, c_int, c_int64, c_longlong, c_void_p, c_char_p, POINTER
 
 import torch
@@ -56,6 +57,7 @@ SIGNATURES = {
     "dmb_b200_upsample_trilinear_backward": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_soft_argmin_backward": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _F, _F, _P, _P],
     "dmb_b200_cat_volume_backward": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
+    "dmb_b200_dif_volume_backward": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
 }
 # entry points that do not return a status code
 OTHER = {
@@ -100,9 +102,28 @@ def load():
     return lib
 
 
+# devices of the tensors whose pointers were taken (ptr()) since the last call(): the launch, the
+# cudaFuncSetAttribute, the SM count and the TMA descriptors inside the library all act on the calling thread's
+# CURRENT device, so call() makes the tensors' device current for the duration of the entry point
+_tls = threading.local()
+
+
 def call(name, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    devs = getattr(_tls, "devs", None)
+    _tls.devs = None
+    fn = getattr(lib, name)
+    if devs:
+        if len(devs) > 1:
+            raise DmbB200Error("%s: tensor arguments live on different CUDA devices %s" % (name, sorted(devs)))
+        dev = next(iter(devs))
+        if dev != torch.cuda.current_device():
+            with torch.cuda.device(dev):
+                rc = fn(*args)
+        else:
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
     if rc != 0:
         msg = lib.dmb_b200_last_error()
         raise DmbB200Error("%s failed (%d): %s" % (name, rc, msg.decode() if msg else "?"))
@@ -120,6 +141,10 @@ def ptr(t):
         raise DmbB200Error("dmb_b200 kernels need CUDA tensors (got %s); there is no CPU path" % t.device)
     if not t.is_contiguous():
         raise DmbB200Error("dmb_b200 kernels need contiguous tensors")
+    devs = getattr(_tls, "devs", None)
+    if devs is None:
+        devs = _tls.devs = set()
+    devs.add(t.device.index if t.device.index is not None else torch.cuda.current_device())
     return c_void_p(t.data_ptr())
 
 

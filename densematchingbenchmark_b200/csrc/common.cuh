@@ -39,7 +39,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-int sm_count();   // cached per process (current device)
+int sm_count();   // of the calling thread's current device (cached per device)
 
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -1233,17 +1233,12 @@ static int make_parity_map(CUtensorMap* map, const void* base_b, int CBS, int D,
     return encode(map, base, dims, strides, box, fp16);
 }
 
-static int device_ok() {
-    static int cached = -1;
-    if (cached < 0) {
-        int dev = 0, major = 0;
-        cached = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
-            encode_fn() != nullptr)
-            cached = 1;
-    }
-    return cached;
+static int device_ok() {          // of the calling thread's current device
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess)
+        return 0;
+    return (major == 10 && encode_fn() != nullptr) ? 1 : 0;
 }
 
 template <int KIND, bool SPLIT, bool FP16>

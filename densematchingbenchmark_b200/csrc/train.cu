@@ -502,6 +502,9 @@ constexpr int kMaxDispBwd = 256;
 struct DispListBwd {
     int d[kMaxDispBwd];
 };
+// DIF = false: backward of cat_fms (dvol [B,2C,D,H,W]: left half -> dleft, right half -> dright);
+// DIF = true : backward of dif_fms (dvol [B,C,D,H,W] = d(ref - tgt): dleft = +sum, dright = -sum over the same channels)
+template <bool DIF>
 __global__ void __launch_bounds__(128) cat_volume_bwd_kernel(const float* __restrict__ dvol, float* __restrict__ dleft,
                                                              float* __restrict__ dright, int C, int H, int W, int D,
                                                              DispListBwd dl) {
@@ -511,7 +514,8 @@ __global__ void __launch_bounds__(128) cat_volume_bwd_kernel(const float* __rest
     const int b = blockIdx.z;
     if (xw >= W) return;
     const size_t plane = (size_t)H * W;
-    const float* v = dvol + (((size_t)b * 2 * C + c2) * D) * plane + (size_t)y * W;
+    const float* v = DIF ? dvol + (((size_t)b * C + (c2 % C)) * D) * plane + (size_t)y * W
+                         : dvol + (((size_t)b * 2 * C + c2) * D) * plane + (size_t)y * W;
     float acc = 0.f;
     if (c2 < C) {
         for (int k = 0; k < D; ++k) {
@@ -524,7 +528,7 @@ __global__ void __launch_bounds__(128) cat_volume_bwd_kernel(const float* __rest
             const int xo = xw + dl.d[k];
             if (xo >= 0 && xo < W) acc += __ldg(v + (size_t)k * plane + xo);
         }
-        dright[(((size_t)b * C + (c2 - C)) * H + y) * W + xw] = acc;
+        dright[(((size_t)b * C + (c2 - C)) * H + y) * W + xw] = DIF ? -acc : acc;
     }
 }
 
@@ -678,8 +682,8 @@ extern "C" int dmb_b200_soft_argmin_backward(const float* cost, const float* gra
     return check_launch("soft_argmin_bwd_kernel");
 }
 
-extern "C" int dmb_b200_cat_volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
-                                            const int* disp_idx_host, int D, void* stream) {
+static int volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
+                           const int* disp_idx_host, int D, bool dif, void* stream) {
     DMB_REQUIRE(dvol && dleft && dright && disp_idx_host, "cat_volume_backward: null pointer");
     DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && D > 0, "cat_volume_backward: non-positive dimension");
     DMB_REQUIRE(D <= kMaxDispBwd, "cat_volume_backward: at most %d disparity samples", kMaxDispBwd);
@@ -690,6 +694,17 @@ extern "C" int dmb_b200_cat_volume_backward(const float* dvol, float* dleft, flo
         dl.d[i] = d >= W ? W : (d <= -W ? -W : d);
     }
     dim3 grid((unsigned)cdiv(W, 128), (unsigned)(H * 2 * C), B);
-    cat_volume_bwd_kernel<<<grid, 128, 0, as_stream(stream)>>>(dvol, dleft, dright, C, H, W, D, dl);
+    if (dif) cat_volume_bwd_kernel<true><<<grid, 128, 0, as_stream(stream)>>>(dvol, dleft, dright, C, H, W, D, dl);
+    else cat_volume_bwd_kernel<false><<<grid, 128, 0, as_stream(stream)>>>(dvol, dleft, dright, C, H, W, D, dl);
     return check_launch("cat_volume_bwd_kernel");
+}
+
+extern "C" int dmb_b200_cat_volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
+                                            const int* disp_idx_host, int D, void* stream) {
+    return volume_backward(dvol, dleft, dright, B, C, H, W, disp_idx_host, D, false, stream);
+}
+
+extern "C" int dmb_b200_dif_volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
+                                            const int* disp_idx_host, int D, void* stream) {
+    return volume_backward(dvol, dleft, dright, B, C, H, W, disp_idx_host, D, true, stream);
 }

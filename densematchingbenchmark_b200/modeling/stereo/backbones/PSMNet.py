@@ -88,7 +88,12 @@ class PSMNetBackbone(nn.Module):
         if len(input) != 2:
             raise ValueError('expected input length 2 (got {} length input)'.format(len(input)))
         l_img, r_img = input
-        # one batched pass over both views instead of two (reference: PSMNet.py:126-127)
+        if self.training and any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) and m.training
+                                 for m in self.modules()):
+            # batch statistics: two passes like the reference (backbones/PSMNet.py:126-127) -- one joint pass would
+            # normalise with the statistics of the 2N-image batch and update the running statistics once, not twice
+            return self._forward(l_img), self._forward(r_img)
+        # eval / frozen BatchNorm: one batched pass over both views instead of two (same result, half the launches)
         both = self._forward(torch.cat([l_img, r_img], 0))
         n = l_img.shape[0]
         return both[:n], both[n:]

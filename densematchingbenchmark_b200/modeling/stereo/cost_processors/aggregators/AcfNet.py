@@ -25,8 +25,9 @@ class AcfAggregator(PSMTrunk):
             raise ValueError("AcfAggregator: max_disp (%d) must be 4x the raw cost depth (%d), as the reference's "
                              "ConvTranspose3d(output_size=...) requires" % (self.max_disp, D))
         pairs = ((cost3, self.deconv3), (cost2, self.deconv2), (cost1, self.deconv1))
-        if self.defer_upsample and not self.training:
+        diff = self.differentiable(raw_cost)
+        if self.defer_upsample and not diff:
             return [DeferredCost(c[:, 0].contiguous(), size, "deconv", up.weight.detach()) for c, up in pairs]
-        if self.training:
+        if diff:
             return [UpsampleDeconvFn.apply(c, up.weight, size) for c, up in pairs]
         return [F_.upsample_regress(c, size, "deconv", up.weight.detach())[0] for c, up in pairs]

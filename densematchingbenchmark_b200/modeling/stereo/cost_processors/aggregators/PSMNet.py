@@ -6,7 +6,7 @@ from ...layers.basic_layers import conv3d_bn, conv3d_bn_relu, fused_plain_conv3d
 from ..utils.hourglass import Hourglass
 from .deferred import DeferredCost
 from .....ops import functional as F_
-from .....ops.autograd import UpsampleTrilinearFn
+from .....ops.autograd import UpsampleTrilinearFn, wants_grad
 
 
 class PSMTrunk(nn.Module):
@@ -60,8 +60,8 @@ class PSMTrunk(nn.Module):
         """Fast path used by CatCostProcessor: when the trunk will run on tcgen05, build the
         concatenation volume directly in the trunk's blocked 16-bit layout.  Returns None when
         the trunk is not going to use the tensor-core engine for this shape."""
-        if self.engine == "direct" or self.training or not ref_fms.is_cuda:
-            return None
+        if self.engine == "direct" or self.training or not ref_fms.is_cuda or wants_grad(ref_fms, tgt_fms):
+            return None                                   # (the blocked volume and the tcgen05 trunk have no backward)
         from . import tc_engine
         D = (max_disp + dilation - 1) // dilation
         dhw = (D, ref_fms.shape[2], ref_fms.shape[3])
@@ -69,8 +69,13 @@ class PSMTrunk(nn.Module):
             return None
         return tc_engine.cat_volume_blocked(ref_fms, tgt_fms, max_disp, start_disp, dilation, self.precision)
 
+    def differentiable(self, raw_cost):
+        """True when the forward must build an autograd graph: training mode, or an eval-mode call whose input
+        carries a gradient (inference without torch.no_grad() on top of a trainable backbone)."""
+        return self.training or (not hasattr(raw_cost, "dims") and wants_grad(raw_cost))
+
     def _use_tc(self, raw_cost):
-        if self.engine == "direct" or self.training:      # training runs the fp32 autograd path
+        if self.engine == "direct" or self.differentiable(raw_cost):      # training runs the autograd path
             return False
         from .tc_engine import tc_supported
         ok = tc_supported(self, raw_cost)
@@ -91,8 +96,9 @@ class PSMAggregator(PSMTrunk):
         D, H, W = raw_cost.dims if hasattr(raw_cost, "dims") else raw_cost.shape[2:]
         cost1, cost2, cost3 = self.trunk(raw_cost)
         size = (self.max_disp, H * 4, W * 4)
-        if self.defer_upsample and not self.training:
+        diff = self.differentiable(raw_cost)
+        if self.defer_upsample and not diff:
             return [DeferredCost(c[:, 0].contiguous(), size, "trilinear") for c in (cost3, cost2, cost1)]
-        if self.training:
+        if diff:
             return [UpsampleTrilinearFn.apply(c, size) for c in (cost3, cost2, cost1)]
         return [F_.upsample_regress(c, size, "trilinear")[0] for c in (cost3, cost2, cost1)]

@@ -1,6 +1,6 @@
 """CAT_FUNCS -- concatenation cost volumes (reference: cost_processors/utils/cat_fms.py:7-88)."""
 from .....ops import functional as F_
-from .....ops.autograd import CatVolumeFn, wants_grad
+from .....ops.autograd import CatVolumeFn, forbid_grad, wants_grad
 
 
 def cat_fms(reference_fm, target_fm, max_disp=192, start_disp=0, dilation=1, disp_sample=None):
@@ -15,6 +15,7 @@ def cat_fms(reference_fm, target_fm, max_disp=192, start_disp=0, dilation=1, dis
 def fast_cat_fms(reference_fm, target_fm, max_disp=192, start_disp=0, dilation=1, disp_sample=None):
     """grid_sample-warped variant with per-pixel `disp_sample` [B,D,H,W] (cat_fms.py:51-82),
     reproducing the reference's align_corners mismatch and `(target > 0)` masking."""
+    forbid_grad("fast_cat_fms", reference_fm, target_fm, disp_sample)
     if disp_sample is None:
         disp_sample = _ramp_sample(reference_fm, max_disp, start_disp, dilation)
     return F_.warp_volume(reference_fm, target_fm, disp_sample, mode=0)

@@ -2,6 +2,7 @@
 import torch.nn as nn
 
 from ....ops import functional as F_
+from ....ops.autograd import forbid_grad
 
 
 class LocalSoftArgmin(nn.Module):
@@ -22,6 +23,7 @@ class LocalSoftArgmin(nn.Module):
         D = cost_volume.size()[1]
         assert D == self.disp_sample_number, 'Number of disparity sample should be same' \
                                              'with predicted disparity number in cost volume!'
+        forbid_grad("LocalSoftArgmin", cost_volume)
         return F_.local_soft_argmin(cost_volume, self.radius, self.radius_dilation, self.alpha,
                                     self.start_disp, self.dilation)
 

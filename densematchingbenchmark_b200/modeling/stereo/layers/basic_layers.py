@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from ....ops import functional as F_
-from ....ops.autograd import ConvUnitFn
+from ....ops.autograd import ConvUnitFn, wants_grad
 
 
 def consistent_padding_with_dilation(padding, dilation):
@@ -96,17 +96,25 @@ class FusedConvUnit(nn.Sequential):
         the unit's own ReLU (conv3d_bn_relu) cannot be combined with a residual."""
         if self._has_relu and residual is not None:
             raise ValueError("conv+bn+relu unit cannot take a fused residual")
-        if self.training:
+        bn = self.bn
+        if self.training and (bn is None or bn.training):
             return self._forward_train(x, residual, relu_after)
+        if self.training or wants_grad(x, residual):
+            # frozen BatchNorm (`model.train()` followed by `bn.eval()`), or an eval-mode unit whose INPUT carries
+            # a gradient: running statistics are folded with differentiable torch ops and the convolution runs
+            # through the autograd Function, so input / weight / affine gradients flow like through
+            # nn.Sequential(Conv3d, BatchNorm3d.eval()) and no running statistic is touched
+            return self._forward_frozen(x, residual, relu_after)
         w, b = self.folded()
         ksize, stride, pad, opad = self.geometry()
         return F_.conv3d_fused(x, w, b, ksize, stride, pad, self.transposed, opad, residual,
                                relu=self._has_relu or relu_after)
 
 
-def _unit_forward_train(conv, bn, x, residual, relu, sync_group=None):
+def _unit_forward_train(conv, bn, x, residual, relu, sync_group=None, weight=None, bias=None):
     """Training-mode forward of one conv(+bn)(+relu) unit through the autograd Function whose forward and
-    backward are the library's kernels (batch statistics, running-stat update as nn.BatchNorm3d)."""
+    backward are the library's kernels (batch statistics, running-stat update as nn.BatchNorm3d).
+    `weight` / `bias`: differentiable replacements of the conv's own parameters (frozen-BatchNorm folding)."""
     transposed = isinstance(conv, nn.ConvTranspose3d)
     for name in ("stride", "padding", "dilation"):
         if len(set(getattr(conv, name))) != 1:
@@ -117,14 +125,35 @@ def _unit_forward_train(conv, bn, x, residual, relu, sync_group=None):
                opad=conv.output_padding[0] if transposed else 0, relu=relu, bn=bn, sync_group=sync_group)
     gamma = bn.weight if bn is not None else None
     beta = bn.bias if bn is not None else None
-    return ConvUnitFn.apply(x, conv.weight, conv.bias, gamma, beta, residual, cfg)
+    if weight is None:
+        weight, bias = conv.weight, conv.bias
+    return ConvUnitFn.apply(x, weight, bias, gamma, beta, residual, cfg)
 
 
 def _ff_train(self, x, residual=None, relu_after=False):
     return _unit_forward_train(self.conv, self.bn, x, residual, self._has_relu or relu_after, self.sync_group)
 
 
+def _ff_frozen(self, x, residual=None, relu_after=False):
+    conv, bn = self.conv, self.bn
+    w, b = conv.weight, conv.bias
+    if bn is not None:
+        if bn.running_var is None:
+            raise NotImplementedError("BatchNorm3d without running statistics cannot run in eval mode on the CUDA path")
+        scale = torch.rsqrt(bn.running_var.float() + bn.eps)
+        if bn.weight is not None:
+            scale = bn.weight * scale
+        # Conv3d weight [Cout,Cin,k,k,k]; ConvTranspose3d weight [Cin,Cout,k,k,k]
+        w = w * (scale.view(1, -1, 1, 1, 1) if self.transposed else scale.view(-1, 1, 1, 1, 1))
+        shift = -bn.running_mean.float() * scale
+        if bn.bias is not None:
+            shift = shift + bn.bias
+        b = shift if b is None else b * scale + shift
+    return _unit_forward_train(conv, None, x, residual, self._has_relu or relu_after, None, weight=w, bias=b)
+
+
 FusedConvUnit._forward_train = _ff_train
+FusedConvUnit._forward_frozen = _ff_frozen
 
 
 def conv3d_bn(batchNorm, in_planes, out_planes, kernel_size=3, stride=1, padding=1, dilation=1, bias=True):
@@ -161,7 +190,7 @@ class _PlainCache(object):
 def fused_plain_conv3d(conv, x, residual=None, relu=False):
     """Run a bare nn.Conv3d / nn.ConvTranspose3d (e.g. the 32->1 classifier heads,
     aggregators/PSMNet.py:41-52) through the fused kernel, with an optional residual."""
-    if conv.training:
+    if conv.training or wants_grad(x, residual):
         return _unit_forward_train(conv, None, x, residual, relu)
     cache = conv.__dict__.setdefault("_dmb_b200_cache", _PlainCache())
     tensors = [conv.weight, conv.bias]

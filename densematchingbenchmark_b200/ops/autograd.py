@@ -195,6 +195,28 @@ class CatVolumeFn(torch.autograd.Function):
         return dl, dr, None, None, None
 
 
+class DifVolumeFn(torch.autograd.Function):
+    """dif_fms forward + backward (cost_processors/utils/dif_fms.py:7-46): out = ref - shifted tgt, so the
+    backward is the cat-volume gather with both halves reading the same channels and the target half negated."""
+
+    @staticmethod
+    def forward(ctx, left, right, max_disp, start_disp, dilation):
+        ctx.args = (max_disp, start_disp, dilation)
+        ctx.shape = tuple(left.shape)
+        return F_.dif_volume(left, right, max_disp, start_disp, dilation)
+
+    @staticmethod
+    def backward(ctx, dvol):
+        dvol = C.f32(dvol)
+        B, Ch, H, W = ctx.shape
+        idx = F_.disp_indices(*ctx.args)
+        dl = torch.empty(ctx.shape, device=dvol.device, dtype=torch.float32)
+        dr = torch.empty_like(dl)
+        C.call("dmb_b200_dif_volume_backward", C.ptr(dvol), C.ptr(dl), C.ptr(dr), B, Ch, H, W, C.int_array(idx),
+               len(idx), C.stream(dvol.device))
+        return dl, dr, None, None, None
+
+
 class UpsampleTrilinearFn(torch.autograd.Function):
     """[B,1,Dl,Hl,Wl] -> [B,D,H,W] (F.interpolate trilinear align_corners=True + squeeze, PSMNet.py:75-88)."""
 
@@ -271,3 +293,12 @@ class SoftArgminFn(torch.autograd.Function):
 
 def wants_grad(*tensors):
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def forbid_grad(op, *tensors):
+    """Ops whose backward is not built: fail loudly instead of returning a tensor without grad_fn (which would
+    train the layers in front of it with a silent zero gradient)."""
+    if wants_grad(*tensors):
+        raise NotImplementedError(
+            "%s has no backward on the CUDA path: call it under torch.no_grad() / on detached inputs, or use the "
+            "differentiable variants (cat_fms / dif_fms 'default', SoftArgmin / FasterSoftArgmin)" % op)

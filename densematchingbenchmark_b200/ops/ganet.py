@@ -3,12 +3,14 @@ SURVEY.md section 0.1; semantics are fixed by oracle/dmb_oracle.py:sga / lga).""
 import torch.nn as nn
 
 from . import functional as F_
+from .autograd import forbid_grad
 
 
 class SGA(nn.Module):
     """Semi-global aggregation: forward(x [B,C,D,H,W], guidance [B,4*5*C,H,W]) -> [B,C,D,H,W]."""
 
     def forward(self, x, guidance):
+        forbid_grad("SGA", x, guidance)
         return F_.sga(x, guidance)
 
 
@@ -20,4 +22,5 @@ class LGA(nn.Module):
         self.radius = radius
 
     def forward(self, x, guidance):
+        forbid_grad("LGA", x, guidance)
         return F_.lga(x, guidance, self.radius)

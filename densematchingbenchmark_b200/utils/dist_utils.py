@@ -86,6 +86,7 @@ class GradReducer(object):
         self._pending = [len(b) for b in self.buckets]
         self._work = [None] * len(self.buckets)
         self._seen = set()
+        self._next = 0                             # first bucket whose all-reduce has not been issued yet
         self._handles = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self.launched_early = 0                    # buckets whose all-reduce started inside backward()
 
@@ -96,8 +97,13 @@ class GradReducer(object):
         bi, off = self.slot[id(p)]
         self.flat[bi][off:off + p.numel()].copy_(p.grad.reshape(-1))
         self._pending[bi] -= 1
-        if self._pending[bi] == 0:
-            self._work[bi] = dist.all_reduce(self.flat[bi], group=self.group, async_op=True)
+        # Collectives are issued STRICTLY in bucket order (bucket i only after buckets 0..i-1): a parameter that
+        # gets no gradient on one rank only (a data-dependent branch) then delays that rank's remaining buckets to
+        # finish() instead of re-ordering them -- every rank issues the same sequence of all-reduces, whatever
+        # order its gradients arrive in (NCCL pairs collectives by issue order).
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            self._work[self._next] = dist.all_reduce(self.flat[self._next], group=self.group, async_op=True)
+            self._next += 1
             self.launched_early += 1
 
     def finish(self):
@@ -129,6 +135,7 @@ class GradReducer(object):
         self._pending = [len(b) for b in self.buckets]
         self._work = [None] * len(self.buckets)
         self._seen = set()
+        self._next = 0
 
     def remove(self):
         for h in self._handles:

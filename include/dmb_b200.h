@@ -275,6 +275,10 @@ int dmb_b200_soft_argmin_backward(const float* cost, const float* grad_disp, flo
 /* backward of dmb_b200_cat_volume: dvol [B,2C,D,H,W] -> dleft, dright [B,C,H,W]; D <= 256 */
 int dmb_b200_cat_volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
                                  const int* disp_idx_host, int D, void* stream);
+/* backward of dmb_b200_dif_volume (dif_fms.py:7-46, out = ref - shifted tgt): dvol [B,C,D,H,W] -> dleft = +sum over
+   the valid disparities, dright = -sum at the shifted columns; D <= 256 */
+int dmb_b200_dif_volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
+                                 const int* disp_idx_host, int D, void* stream);
 
 #ifdef __cplusplus
 }

@@ -94,7 +94,29 @@ def _reducer_worker(rank, world, port, q):
         red.finish()
         ok3 = m[4].weight.grad is not None and float(m[4].weight.grad.abs().max()) == 0.0
         t = m[0].weight.grad.clone()
-        q.put((rank, bool(ok1), bool(ok2), bool(ok3), len(red.buckets), float(t.abs().sum())))
+        # (3) round-2 advisor finding: a parameter without gradient on ONE rank only (a data-dependent branch).
+        # Rank 1 skips the last two layers, so its early buckets never fill; the reducer issues collectives strictly
+        # in bucket order, so both ranks still pair bucket i with bucket i and the means are exact.
+        for p in m.parameters():
+            p.grad = None
+        if rank == 1:
+            m[3](m[2](m[1](m[0](x)))).square().mean().backward()
+        else:
+            m(x).square().mean().backward()
+        red.finish()
+        ref2 = make(); ref2[5].weight.requires_grad_(False)
+        if rank == 1:
+            ref2[3](ref2[2](ref2[1](ref2[0](x)))).square().mean().backward()
+        else:
+            ref2(x).square().mean().backward()
+        ok4 = True
+        for p, pr in zip(m.parameters(), ref2.parameters()):
+            if not pr.requires_grad:
+                continue
+            w = pr.grad.clone() if pr.grad is not None else torch.zeros_like(pr)
+            dist.all_reduce(w)
+            ok4 = ok4 and torch.allclose(p.grad, w / world, atol=1e-6)
+        q.put((rank, bool(ok1), bool(ok2), bool(ok3 and ok4), len(red.buckets), float(t.abs().sum())))
     finally:
         dist.destroy_process_group()
 

@@ -580,53 +580,84 @@ def test_acfnet_tc_engine_vs_reference_golden(P, golden_dir):
 
 
 # ------------------------------------------------------------------------------- BASELINE config sizes
-def test_config2_full_size_psm_hot_path(P):
-    """BASELINE config 2 at FULL size (features [1,32,136,240], D=192 -> 3x [1,1,544,960]) on the
-    tensor-core engine against the float32 CPU oracle.  Per-pixel agreement is bounded by the float32
-    noise floor measured at medium size (see test_medium_size...); the mean deviation and the EPE
-    difference must be far below 1e-3 px."""
+@pytest.mark.parametrize("sharpen", [1.0, 4.0])
+def test_config2_full_size_psm_hot_path(P, sharpen):
+    """BASELINE config 2 at FULL size (features [1,32,136,240], D=192 -> 3x [1,1,544,960]) on the tensor-core
+    engine, fp16x3 -- with sharpen=4.0 and seed 0 these are exactly the weights bench.py times.
+
+    The stated tolerance is per-pixel |d_disp| < 1e-3 px against the fp32 reference.  At D=192 the reference's OWN
+    float32 rounding noise exceeds that at the worst pixels (test_medium_size... docstring), so, as there, both
+    implementations are compared with the float64 evaluation of the same arithmetic: our worst error may exceed the
+    float32 CPU oracle's worst error by at most 1.5x + 2e-4, the mean deviation must stay below 1e-4 * sharpen, and
+    |dEPE| below 1e-3.  The maxima are printed (pytest -s)."""
     _tc_or_skip()
     cfg = _cfg(P, "PSMNet", feat_disp=48, max_disp=192)
     proc = P.build_cost_processor(cfg)
     pred = P.build_disp_predictor(cfg)
-    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=0, sharpen=1.0)
+    sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=0, sharpen=sharpen)
     proc.aggregator.load_state_dict(sd)
     proc = proc.to(DEV).eval(); pred = pred.to(DEV).eval()
+    assert proc.aggregator.precision == "fp16x3"
     l, r = seeded.feature_pair(1, 32, 136, 240, seed=5, scale=0.5, shift=6)
     disps = [pred(c).cpu() for c in proc(l.to(DEV), r.to(DEV))]
     assert all(tuple(d.shape) == (1, 1, 544, 960) for d in disps)
     torch.set_num_threads(min(32, max(1, os.cpu_count() or 1)))
-    _, want = O.psm_hot_path(sd, l, r, 192, prefix="")
-    for got, w in zip(disps, want):
-        diff = (got - w).abs()
-        print("config 2 full size: max |d_disp| %.2e mean %.2e" % (float(diff.max()), float(diff.mean())))
-        assert float(diff.max()) < 5e-3 and float(diff.mean()) < 1e-4
-        gt = w + 1.0
-        assert abs(O.epe(got, gt, 0, 1e9) - 1.0) < 1e-3
+    _, f32 = O.psm_hot_path(sd, l, r, 192, prefix="")
+    _, f64 = O.psm_hot_path(sd, l, r, 192, prefix="", dtype=torch.float64)
+    for got, w32, w64 in zip(disps, f32, f64):
+        ours = float((got.double() - w64).abs().max())
+        theirs = float((w32.double() - w64).abs().max())
+        mean = float((got.double() - w64).abs().mean())
+        print("config 2 full size, sharpen %.0f: ours-vs-f64 max %.2e mean %.2e | f32 oracle-vs-f64 max %.2e | "
+              "ours-vs-f32 oracle max %.2e" % (sharpen, ours, mean, theirs, float((got - w32).abs().max())))
+        assert ours < 1.5 * theirs + 2e-4
+        assert mean < 1e-4 * sharpen
+        gt = w64.float() + 1.0                                  # pseudo ground truth
+        assert abs(O.epe(got, gt, 0, 1e9) - O.epe(w32, gt, 0, 1e9)) < 1e-3
 
 
-def test_config3_gwc_full_size_properties(P):
-    """BASELINE config 3: 320-channel features, 40 groups, D4=48 at 136x240."""
+def test_config3_gwc_full_size_vs_oracle(P):
+    """BASELINE config 3 at full size: 320-channel features, 40 groups, D4=48 at 136x240 -- EVERY disparity plane
+    against the CPU oracle (fp32 products, mean over 8 channels: rounding-order level), plus linearity."""
     l, r = seeded.feature_pair(1, 320, 136, 240, seed=9)
     lg, rg = l.to(DEV), r.to(DEV)
     vol = P.GWC_FUNCS["default"](lg, rg, max_disp=48, num_groups=40)
     assert tuple(vol.shape) == (1, 40, 48, 136, 240)
-    for d in (0, 3, 47):
-        want = (lg[0, :, :, d:] * rg[0, :, :, :240 - d]).view(40, 8, 136, 240 - d).mean(1)
-        torch.testing.assert_close(vol[0, :, d, :, d:], want, atol=1e-5, rtol=1e-5)
+    want = O.gwc_volume(l, r, 40, 48)
+    torch.testing.assert_close(vol.cpu(), want, atol=2e-6, rtol=1e-5)
+    for d in (1, 47):                                          # left of the first valid column: exact zeros
         assert float(vol[0, :, d, :, :d].abs().sum()) == 0.0
-    # linearity in the left features
     vol2 = P.GWC_FUNCS["default"](2.0 * lg, rg, max_disp=48, num_groups=40)
-    torch.testing.assert_close(vol2, 2.0 * vol, atol=1e-5, rtol=1e-5)
+    assert torch.equal(vol2, 2.0 * vol)                        # scaling by a power of two is exact
+    # dilation / negative start at full size (disparities -8, -4, ..., 36)
+    vol3 = P.GWC_FUNCS["default"](lg, rg, max_disp=48, start_disp=-8, dilation=4, num_groups=40)
+    torch.testing.assert_close(vol3.cpu(), O.gwc_volume(l, r, 40, 48, -8, 4), atol=2e-6, rtol=1e-5)
 
 
-def test_config4_ganet_full_size_properties(P):
-    """BASELINE config 4 sizes (1248x384 padded from 1242x375): identity guidance reproduces the input."""
+def test_config4_ganet_full_size_vs_oracle(P):
+    """BASELINE config 4 at FULL size (1248x384 padded from 1242x375, GANet-deep): SGA on all 32 channels of
+    [1,32,64,128,416] with random (signed) guidance that the op L1-normalises, LGA on [1,192,384,1248] with random
+    guidance -- both against the CPU oracle, every element; then the identity-guidance property."""
     from densematchingbenchmark_b200.ops import SGA, LGA
+    torch.set_num_threads(min(32, max(1, os.cpu_count() or 1)))
     g = torch.Generator().manual_seed(4)
-    x = torch.randn(1, 8, 64, 128, 416, generator=g).to(DEV)          # 8 of the 32 channels (memory of the test box)
-    gd = torch.zeros(1, 4, 5, 8, 128, 416, device=DEV); gd[:, :, 0] = 1.7
-    torch.testing.assert_close(SGA()(x, gd.view(1, 160, 128, 416)), x)
-    c = torch.randn(1, 192, 384, 1248, generator=g).to(DEV)
-    gl = torch.zeros(1, 3, 5, 5, 384, 1248, device=DEV); gl[:, 0, 2, 2] = 0.3
-    torch.testing.assert_close(LGA(2)(c, gl.view(1, 75, 384, 1248)), c)
+    x = torch.randn(1, 32, 64, 128, 416, generator=g)
+    gd = torch.randn(1, 4 * 5 * 32, 128, 416, generator=g)
+    xg = x.to(DEV)
+    got = SGA()(xg, gd.to(DEV)).cpu()
+    want = O.sga(x, gd)
+    err = float((got - want).abs().max())
+    print("config 4 SGA full size: max |d| %.2e on a scale of %.2f" % (err, float(want.abs().max())))
+    torch.testing.assert_close(got, want, atol=2e-5, rtol=1e-4)
+    ident = torch.zeros(1, 4, 5, 32, 128, 416, device=DEV); ident[:, :, 0] = 1.7
+    torch.testing.assert_close(SGA()(xg, ident.view(1, 640, 128, 416)), xg)
+    del xg, got, want, ident
+    c = torch.randn(1, 192, 384, 1248, generator=g)
+    gl = torch.randn(1, 75, 384, 1248, generator=g)
+    cg = c.to(DEV)
+    got = LGA(2)(cg, gl.to(DEV)).cpu()
+    want = O.lga(c, gl)
+    print("config 4 LGA full size: max |d| %.2e" % float((got - want).abs().max()))
+    torch.testing.assert_close(got, want, atol=2e-5, rtol=1e-4)
+    gi = torch.zeros(1, 3, 5, 5, 384, 1248, device=DEV); gi[:, 0, 2, 2] = 0.3
+    torch.testing.assert_close(LGA(2)(cg, gi.view(1, 75, 384, 1248)), cg)

@@ -248,3 +248,38 @@ def test_cached_weight_scale_refreshes_with_parameter_updates(P):
     with torch.no_grad():
         w.add_(0.0); w.add_(0.0)                                        # third update since the scale was taken
     assert T.cached_weight_scale(w, w.detach(), refresh=3) == 0.25      # 30 * 0.25 = 7.5 in [4, 8)
+
+
+@pytest.mark.ref
+def test_reference_spn_kernel_compiles_into_oracle_ref():
+    """oracle/build_ref.py compiles the reference's own SPN CUDA file from where it lies (build container only);
+    the resulting test-only library exports the two C entry points tests/test_gpu_spn_ref.py binds."""
+    import ctypes
+    import build_ref
+    lib = build_ref.build_ref()
+    assert lib is not None and os.path.exists(lib)
+    assert os.path.realpath(lib).startswith(os.path.realpath(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref")))
+    h = ctypes.CDLL(lib)
+    assert hasattr(h, "spn_ref_forward") and hasattr(h, "spn_ref_backward")
+
+
+def test_backbone_train_mode_runs_the_two_views_separately():
+    """Reference backbones/PSMNet.py:126-127 runs `_forward` once per view: in train() the BatchNorm statistics are
+    per view and the running statistics get two updates.  Eval mode may batch the views (same result)."""
+    from densematchingbenchmark_b200.modeling.stereo.backbones.PSMNet import PSMNetBackbone
+    torch.manual_seed(0)
+    bb = PSMNetBackbone(3, True)
+    l, r = torch.randn(2, 3, 256, 256), torch.randn(2, 3, 256, 256)     # branch1 pools 64x64 windows of the 1/4 map
+    import copy
+    twin = copy.deepcopy(bb)
+    bb.train(); twin.train()
+    fl, fr = bb(l, r)
+    wl, wr = twin._forward(l), twin._forward(r)
+    assert torch.equal(fl, wl) and torch.equal(fr, wr)
+    bns = [m for m in bb.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    assert all(int(m.num_batches_tracked) == 2 for m in bns)
+    bb.eval(); twin.eval()
+    with torch.no_grad():
+        el, er = bb(l, r)
+        torch.testing.assert_close(el, twin._forward(l), atol=1e-5, rtol=1e-5)
+        torch.testing.assert_close(er, twin._forward(r), atol=1e-5, rtol=1e-5)
