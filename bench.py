@@ -25,6 +25,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 H_IMG, W_IMG, H_PAD, MAX_DISP = 540, 960, 544, 192
 H4, W4, D4 = H_PAD // 4, W_IMG // 4, MAX_DISP // 4
@@ -182,7 +183,15 @@ def build_model(device, engine, precision):
     return backbone.to(device).eval(), proc.to(device).eval(), pred.to(device).eval(), sd
 
 
-CPU_BAND = 256   # image rows of the CPU sample (the SPP branch's 64x64 pooling needs >= 256)
+CPU_BAND = 256   # image rows of the reduced CPU sample (the SPP branch's 64x64 pooling needs >= 256)
+
+
+def cpu_sample_rows(sd, threads, steps, budget_s=150.0):
+    """Rows of the CPU sample: the FULL padded image (544 rows = one whole pair per step) when `steps` of them fit
+    the time budget on this host, else a 256-row band (throughput then extrapolated by rows, and said so)."""
+    t_band = cpu_forward_sample(sd, threads, CPU_BAND)          # doubles as the warm-up
+    t_full_est = t_band * H_PAD / float(CPU_BAND)
+    return (H_PAD if t_full_est * (steps + 1) <= budget_s else CPU_BAND), t_band
 
 
 def best_cpu_threads():
@@ -234,22 +243,23 @@ def run_reference(args, rank, world):
     import seeded
     threads = best_cpu_threads()
     sd = seeded.seeded_state_dict(seeded.aggregator_entries("PSMNet", 64), seed=0, sharpen=4.0)
-    frac = CPU_BAND / float(H_PAD)
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_forward_sample(sd, threads)
-    times = [cpu_forward_sample(sd, threads) for _ in range(args.steps)]
+    rows, _ = cpu_sample_rows(sd, threads, args.steps)
+    frac = rows / float(H_PAD)
+    times = [cpu_forward_sample(sd, threads, rows) for _ in range(args.steps)]
     ms = 1e3 * sum(times) / len(times)
-    value = frac / (ms / 1e3)                   # pairs per second, extrapolated from the band by rows
+    value = frac / (ms / 1e3)                   # pairs per second (extrapolated by rows only when rows < 544)
+    kind = "port" if rows == H_PAD else "port, row-band extrapolated"
+    sample = ("one whole pair per step (all %d rows)" % H_PAD) if rows == H_PAD else \
+             ("%d of %d image rows per step, throughput extrapolated by rows" % (rows, H_PAD))
     line = {
         "impl": "reference", "metric": "disparity maps/sec (PSMNet, 960x540, D=192)", "value": value,
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "PSMNet full forward (backbone + cat volume + PSMAggregator + 3x soft-argmin), 544x960 "
-                               "D=192, CPU fp32, each step = a %d-of-%d image-row band, throughput extrapolated by rows"
-                               % (CPU_BAND, H_PAD)},
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
-                         "sample": "%d of %d image rows, full width/disparity, backbone + hot path; %d threads = fastest of a "
-                                   "thread-count probe on this %d-core host" % (CPU_BAND, H_PAD, threads, os.cpu_count() or 1)},
+                               "D=192, CPU fp32 (oracle port of the reference, torch CPU kernels); " + sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": kind,
+                         "sample": sample + ", full width/disparity, backbone + hot path; %d threads = fastest of a "
+                                   "thread-count probe on this %d-core host" % (threads, os.cpu_count() or 1)},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -331,9 +341,9 @@ def run_ours(args, rank, world, local_rank):
         pool = graph.pool()
         g0, g1, g2, g3 = [torch.cuda.CUDAGraph() for _ in range(4)]
         with torch.cuda.graph(g0, pool=pool):
-            feats = seg_backbone()
+            feats_g = seg_backbone()
         with torch.cuda.graph(g1, pool=pool):
-            raw_s = seg_cat(*feats)
+            raw_s = seg_cat(*feats_g)
         with torch.cuda.graph(g2, pool=pool):
             costs_s = seg_agg(raw_s)
         with torch.cuda.graph(g3, pool=pool):
@@ -430,12 +440,12 @@ def run_ours(args, rank, world, local_rank):
             static_l.copy_(left_h, non_blocking=True)
             static_r.copy_(right_h, non_blocking=True)
             graph.replay()
-            out_h = static_out[0].cpu()
+            out_h = torch.stack(static_out, 0).cpu()         # all three disparity maps, like the reference returns
         else:
             l = left_h.to(device, non_blocking=True)
             r = right_h.to(device, non_blocking=True)
             disps = forward(l, r)
-            out_h = disps[0].cpu()                           # D2H of the step's result (forces completion)
+            out_h = torch.stack(disps, 0).cpu()              # D2H of the step's result (forces completion)
     torch.cuda.synchronize()
     e2e_sync_ms = 1e3 * (time.perf_counter() - t0) / args.steps
     e2e_ms = e2e_sync_ms
@@ -448,8 +458,9 @@ def run_ours(args, rank, world, local_rank):
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         stage_l = [torch.empty_like(static_l) for _ in range(2)]
         stage_r = [torch.empty_like(static_r) for _ in range(2)]
-        out_d = [torch.empty_like(static_out[0]) for _ in range(2)]
-        out_hs = [torch.empty(static_out[0].shape, dtype=static_out[0].dtype).pin_memory() for _ in range(2)]
+        out_shape = (len(static_out),) + tuple(static_out[0].shape)
+        out_d = [torch.empty(out_shape, dtype=static_out[0].dtype, device=device) for _ in range(2)]
+        out_hs = [torch.empty(out_shape, dtype=static_out[0].dtype).pin_memory() for _ in range(2)]
         in_ready = [torch.cuda.Event() for _ in range(2)]
         in_free = [torch.cuda.Event() for _ in range(2)]
         out_ready = [torch.cuda.Event() for _ in range(2)]
@@ -471,7 +482,8 @@ def run_ours(args, rank, world, local_rank):
                 graph.replay()
                 if i >= 2:
                     main.wait_event(out_free[s])
-                out_d[s].copy_(static_out[0])
+                for k, d_k in enumerate(static_out):
+                    out_d[s][k].copy_(d_k)
                 out_ready[s].record(main)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(out_ready[s])
@@ -488,10 +500,44 @@ def run_ours(args, rank, world, local_rank):
             raise RuntimeError("streamed end-to-end result differs from the synchronous one")
 
     ms, e2e_ms, e2e_sync_ms = max_over_ranks([ms, e2e_ms, e2e_sync_ms], device, world)
+
+    # ---- round-2 blocks: (a) the one path with a collective -- the config-5 training step -- at every N;
+    # (b) N=1 only: configs 3 / 4 ops at full size, and the reference's own PyTorch arithmetic on this GPU
+    extra = {}
+    hot_ms = seg[1] + seg[2] + seg[3]
+    feats = None
+    if rank == 0 and world == 1 and args.gpu_torch_baseline:
+        with torch.no_grad():
+            feats = [t.clone() for t in run_backbone(backbone, left, right, args.backbone_dtype)]
+    # free the inference working set (the graphs' private pool holds the activations) before the training step
+    used_graph = graph is not None
+    out_elems = int(out_h.numel())
+    graph = seg_graphs = static_out = out_h = None
+    if used_graph:
+        feats_g = raw_s = costs_s = disps_s = g0 = g1 = g2 = g3 = None
+        static_l = static_r = stage_l = stage_r = out_d = out_hs = None
+    torch.cuda.empty_cache()
+    if args.train:
+        from train_step import run_train_bench
+        extra["train"] = run_train_bench("AcfNet", 4, 256, 512, MAX_DISP, steps=max(2, min(args.steps, 5)), warmup=2,
+                                         sync_bn=True, backbone=True, bucket_mb=4.0, loss="config", rank=rank, world=world,
+                                         device=device)
+        torch.cuda.empty_cache()
     if rank != 0:
         return
+    if world == 1 and args.ops:
+        from bench_blocks import ops_block
+        extra["ops"] = ops_block(device, peaks()["hbm_gbs"])
+    if feats is not None:
+        from bench_blocks import gpu_torch_baseline_block
+        extra["gpu_torch_baseline"] = gpu_torch_baseline_block(sd, feats[0], feats[1], MAX_DISP, hot_ms)
 
     pk = peaks()
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["conv3d_tc_kernel<3>"]
+    except Exception:
+        pass
     macs = trunk_macs(B)
     agg_ms = seg[2]
     on_tc = proc.aggregator._use_tc(torch.empty(B, 64, D4, H4, W4, device=device))
@@ -504,9 +550,10 @@ def run_ours(args, rank, world, local_rank):
                 "achieved": achieved_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tflops / pk["tflops_sustained"], "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "algorithmic_flops_per_step": 2.0 * macs, "mma_passes": passes,
-                # dram__bytes_read+write of ONE launch of the dominant kernel (32->32 layer at 48x136x240, ncu --set
-                # full, profiles/r1_ncu_full_conv3d_tc_k3_n4_s2.txt) against 401 MB algorithmic
-                "traffic": 365.1e6, "traffic_scope": "one launch of conv3d_tc_kernel<3> (32->32 @ 48x136x240)",
+                # dram__bytes_read+write of ONE launch of the dominant kernel (32->32 layer at 48x136x240) from the
+                # committed ncu --set full capture named in profiles/traffic.json (401 MB algorithmic per launch)
+                "traffic": traffic.get("dram_bytes"), "traffic_scope": traffic.get("scope"),
+                "traffic_source": traffic.get("source"),
                 "note": "power bound: the SM clock falls to 1.3-1.5 GHz under the trunk's MMA stream (tools/tc_clock.py); "
                         "tensor pipe active 68 % of elapsed cycles in the dominant kernel"}
     roofline_cat = {"bound": "hbm", "kernel": "cat_volume (blocked 16-bit hi/lo)" if on_tc else "cat_volume (fp32 NCDHW)", "achieved": cat_bytes / (seg[1] * 1e-3) / 1e9,
@@ -516,11 +563,14 @@ def run_ours(args, rank, world, local_rank):
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         threads = best_cpu_threads()
-        cpu_forward_sample(sd, threads)                      # warm-up
-        dt = min(cpu_forward_sample(sd, threads) for _ in range(2))
-        cpu_base = {"value": (CPU_BAND / float(H_PAD)) / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
-                    "sample": "backbone + hot path on %d of %d image rows (full width/disparity), best of 2, %.1f s each"
-                              % (CPU_BAND, H_PAD, dt)}
+        rows, _ = cpu_sample_rows(sd, threads, 2, budget_s=30.0)
+        dt = min(cpu_forward_sample(sd, threads, rows) for _ in range(2))
+        cpu_base = {"value": (rows / float(H_PAD)) / dt, "unit": "pairs/s", "cores": threads,
+                    "kind": "port" if rows == H_PAD else "port, row-band extrapolated",
+                    "sample": ("backbone + hot path on one whole pair (all %d rows), best of 2, %.1f s each" % (H_PAD, dt))
+                    if rows == H_PAD else
+                    ("backbone + hot path on %d of %d image rows (full width/disparity), throughput extrapolated by "
+                     "rows, best of 2, %.1f s each" % (rows, H_PAD, dt))}
 
     pairs = B * world
     line = {
@@ -536,15 +586,18 @@ def run_ours(args, rank, world, local_rank):
                    "engine": args.engine, "precision": args.precision, "backbone": "torch/cuDNN " + args.backbone_dtype + ", BatchNorm folded",
                    "l2": "intermediates (401 MB cat volume, 200 MB activations) exceed the 126 MB L2; no explicit flush"},
         "segments_ms": {"backbone": seg[0], "cat_volume": seg[1], "aggregator": seg[2], "regress": seg[3]},
-        "cuda_graph": bool(graph is not None), "eager_ms_per_step": eager_ms,
+        "cuda_graph": used_graph, "eager_ms_per_step": eager_ms,
         "hot_path": {"ms": seg[1] + seg[2] + seg[3], "pairs_per_s": B / ((seg[1] + seg[2] + seg[3]) * 1e-3)},
         "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms,
-                "mode": "streamed (copy streams overlap H2D/D2H of neighbouring steps with the kernels)" if graph is not None else "synchronous",
+                "mode": "streamed (copy streams overlap H2D/D2H of neighbouring steps with the kernels)" if used_graph else "synchronous",
                 "synchronous_ms_per_step": e2e_sync_ms,
-                "h2d_bytes_per_step": int(2 * left_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4)},
+                "h2d_bytes_per_step": int(2 * left_h.numel() * 4), "d2h_bytes_per_step": out_elems * 4,
+                "result": "all three disparity maps [3,B,1,544,960] fp32 (what the reference's forward returns); the "
+                          "[B,192,544,960] cost volumes are not materialised in eval mode"},
         "gpu_launches": int(launches),
         "roofline": roofline, "roofline_cat_volume": roofline_cat, "clocks": clocks,
     }
+    line.update(extra)
     if alt:
         line["alt_precisions"] = dict(alt, note="single-plane 16-bit trunk (1 MMA per product), eager launches; hot path = cat volume + "
                                                 "aggregator + 3x soft-argmin; headline precision is " + args.precision)
@@ -568,6 +621,10 @@ def main():
     ap.add_argument("--graph", type=int, default=1, help="1: time the forward replayed from a CUDA graph (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--alt-precisions", type=int, default=1, help="1: also time the hot path at single-plane fp16 / bf16")
+    ap.add_argument("--train", type=int, default=1, help="1: add the config-5 training step (`train` block) at every N")
+    ap.add_argument("--ops", type=int, default=1, help="1 (N=1 only): add the config 3 / 4 ops at full size (`ops` block)")
+    ap.add_argument("--gpu-torch-baseline", type=int, default=1,
+                    help="1 (N=1 only): time the reference's own PyTorch arithmetic for the hot path on this GPU")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -579,7 +636,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL_DEBUG=VERSION/INFO prints its banner on stdout: ONE JSON line only
+        # NCCL_DEBUG (whatever the launcher set: INFO shows the communicator / NVLS lines) stays as it is; its log
+        # goes to stderr so that stdout carries the ONE JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
         run_ours(args, rank, world, local_rank)

@@ -114,7 +114,7 @@ def cat_volume(left, right, max_disp=192, start_disp=0, dilation=1):
     """cat_fms (cost_processors/utils/cat_fms.py:7-48) -> [B,2C,D,H,W] float32."""
     B, C, H, W = left.shape
     idx = disp_indices(max_disp, start_disp, dilation)
-    out = torch.zeros(B, 2 * C, len(idx), H, W, dtype=torch.float32)
+    out = torch.zeros(B, 2 * C, len(idx), H, W, dtype=torch.float32, device=left.device)
     for k, d in enumerate(idx):
         if abs(d) >= W:
             continue  # empty slice in the reference
@@ -368,7 +368,7 @@ def soft_argmin(cost, max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=T
     if disp_sample is None:
         s = disp_samples(max_disp, start_disp, dilation)
         assert s.numel() == cost.shape[1]
-        disp_sample = s.view(1, -1, 1, 1)
+        disp_sample = s.view(1, -1, 1, 1).to(cost.device)
     return (p * disp_sample).sum(dim=1, keepdim=True)
 
 
