@@ -207,7 +207,8 @@ def cached_weight_scale(param, w_packed, refresh=64):
     return sc
 
 
-def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False, scale=None):
+def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False, scale=None,
+                    x_blocked=None):
     """One 3x3x3 / pad 1 convolution (stride 1 | stride 2 | transposed stride 2 with output_padding 1) of a float32
     NCDHW tensor on the tcgen05 kernels: layout conversion in, conv, layout conversion out.  Used by the training
     path (ops/autograd.py), whose weights change every step -- nothing is cached.  Returns float32 NCDHW."""
@@ -215,11 +216,33 @@ def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=N
     kind = (_transposed_kind(w_packed.shape[1], w_packed.shape[2]) if transposed
             else ((3 if KW_MERGE else 0) if stride == 1 else (4 if KW_MERGE else 1)))
     blob, Cin, Cout, scale = pack_blob(w_packed, kind, split, fp16, scale)
-    xb = Blocked.from_ncdhw(x, split, fp16)
+    xb = x_blocked if x_blocked is not None else Blocked.from_ncdhw(x, split, fp16)   # (a conversion the caller shares)
     if Cout == 1:
         return conv_tc_raw(xb, blob, bias, Cin, Cout, scale, kind, None, relu, residual)
     rb = Blocked.from_ncdhw(residual, split, fp16) if residual is not None else None
     return conv_tc_raw(xb, blob, bias, Cin, Cout, scale, kind, rb, relu).to_ncdhw()
+
+
+def wgrad_tc(a, g, a_blocked=None, g_blocked=None):
+    """Weight gradient of a 3x3x3 / stride 1 / pad 1 convolution on tcgen05 (csrc/wgrad_tc.cu): a = layer input,
+    g = gradient w.r.t. the layer output, float32 NCDHW (or already Blocked bf16 split pairs) -> [27, Ca, Cg] float32.
+    bfloat16 split pairs: gradients can be arbitrarily small, so the fp32 exponent range matters more than the three
+    extra mantissa bits of IEEE half."""
+    ab = a_blocked if a_blocked is not None else Blocked.from_ncdhw(a, True, False)
+    gb = g_blocked if g_blocked is not None else Blocked.from_ncdhw(g, True, False)
+    if ab.dims != gb.dims or ab.B != gb.B or ab.fp16 or gb.fp16 or not (ab.split and gb.split):
+        raise ValueError("wgrad_tc: input and output gradient must be bf16 split pairs of one geometry")
+    D, H, W = ab.dims
+    dw = torch.zeros(27, ab.C, gb.C, device=ab.hi.device, dtype=torch.float32)
+    C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), ab.B, ab.C, gb.C,
+           D, H, W, 0, C.stream(dw.device))
+    return dw
+
+
+def wgrad_tc_eligible(a, g, ksize, stride, pad, transposed):
+    return (not transposed and stride == 1 and pad == 1 and tuple(ksize) == (3, 3, 3) and a.is_cuda
+            and a.shape[1] % 32 == 0 and g.shape[1] % 32 == 0 and tuple(a.shape[2:]) == tuple(g.shape[2:])
+            and tc_available())
 
 
 def conv3d_tc_eligible(x, Cin, Cout, ksize, stride, pad, transposed, opad, out_dims=None):

@@ -28,7 +28,7 @@ TRAIN_TC_BWD = "bf16x3"
 
 
 def _conv(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, relu, out_dims=None, precision=None,
-          param=None):
+          param=None, x_blocked=None):
     """y = act(conv(x) + bias + residual) for the training path: tcgen05 if eligible, else conv3d_direct.
     `param`: the weight Parameter the packed weight was made from (cache key of its fp16 pre-scale)."""
     if TRAIN_TC and precision is not None:
@@ -41,9 +41,10 @@ def _conv(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, rel
                 (out_dims is None or tuple(int(v) for v in out_dims) == tuple(x.shape[2:])):
             # a stride-1 transposed convolution is the plain convolution with the taps mirrored
             if T.conv3d_tc_eligible(x, Cin, Cout, ksize, 1, pad, False, 0):
-                return T.conv3d_ncdhw_tc(x, w_packed.flip(0).contiguous(), bias, 1, False, precision, residual, relu, scale)
+                return T.conv3d_ncdhw_tc(x, w_packed.flip(0).contiguous(), bias, 1, False, precision, residual, relu, scale,
+                                         x_blocked)
         elif T.conv3d_tc_eligible(x, Cin, Cout, ksize, stride, pad, transposed, opad, out_dims):
-            return T.conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual, relu, scale)
+            return T.conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual, relu, scale, x_blocked)
     return F_.conv3d_fused(x, w_packed, bias, ksize, stride, pad, transposed, opad, residual, relu=relu,
                            out_dims=out_dims)
 
@@ -58,20 +59,35 @@ def _all_reduce_sums(sums, group):
     dist.all_reduce(sums, group=None if group is True else group)
 
 
-def _dgrad(dz, weight, transposed, ksize, stride, pad, x_dims):
+def _dgrad(dz, weight, transposed, ksize, stride, pad, x_dims, dz_blocked=None):
     """Gradient w.r.t. the conv input = the forward kernel with the weight's roles swapped:
     Conv3d weight [Cout,Cin,k] read as a ConvTranspose3d weight (in=Cout, out=Cin), and vice versa."""
     w = F_.pack_conv_weight(weight.detach(), transposed=not transposed)
     return _conv(dz, w, None, ksize, stride, pad, not transposed, 0, None, False, out_dims=x_dims,
-                 precision=TRAIN_TC_BWD)
+                 precision=TRAIN_TC_BWD, x_blocked=dz_blocked)
 
 
-def _wgrad(x, dz, transposed, ksize, stride, pad, weight_shape):
+# weight gradients of the stride-1 layers on tcgen05 (csrc/wgrad_tc.cu); DMB_B200_TRAIN_TC_WGRAD=0: the SIMT kernel
+TRAIN_TC_WGRAD = os.environ.get("DMB_B200_TRAIN_TC_WGRAD", "1") != "0"
+
+
+def _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
+    if not (TRAIN_TC and TRAIN_TC_WGRAD):
+        return False
+    from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
+    return T.wgrad_tc_eligible(x, dz, ksize, stride, pad, transposed)
+
+
+def _wgrad(x, dz, transposed, ksize, stride, pad, weight_shape, dz_blocked=None):
     if tuple(ksize) != (3, 3, 3):
         raise NotImplementedError("conv weight gradient: only 3x3x3 kernels are on the training path")
     a, g = (dz, x) if transposed else (x, dz)          # transposed: the roles of input and output swap
     B, Ca = a.shape[:2]
     Cg = g.shape[1]
+    if _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
+        from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
+        dw = T.wgrad_tc(a, g, g_blocked=dz_blocked)
+        return dw.permute(2, 1, 0).reshape(weight_shape).contiguous()
     dw = torch.zeros(27, Ca, Cg, device=x.device, dtype=torch.float32)
     C.call("dmb_b200_conv3d_wgrad", C.ptr(a), C.ptr(g), C.ptr(dw), B, Ca, Cg, C.int_array(list(a.shape[2:])),
            C.int_array(list(g.shape[2:])), stride, pad, C.stream(x.device))
@@ -169,8 +185,14 @@ class ConvUnitFn(torch.autograd.Function):
                 C.call("dmb_b200_bn_backward_reduce", C.ptr(dz), None, None, None, None, C.ptr(sums), B, Co, S,
                        C.stream(dev))
                 dbias = sums[:Co].float()
-        dx = _dgrad(dz, weight, transposed, ksize, stride, pad, ctx.x_dims) if need_x else None
-        dw = _wgrad(x, dz, transposed, ksize, stride, pad, weight.shape) if need_w else None
+        dz_blocked = None
+        if need_x and need_w and _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
+            # one bf16 split-pair conversion of dz shared by the input-gradient and the weight-gradient kernels
+            from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
+            if T.PRECISIONS[TRAIN_TC_BWD] == (True, False):
+                dz_blocked = T.Blocked.from_ncdhw(dz, True, False)
+        dx = _dgrad(dz, weight, transposed, ksize, stride, pad, ctx.x_dims, dz_blocked) if need_x else None
+        dw = _wgrad(x, dz, transposed, ksize, stride, pad, weight.shape, dz_blocked) if need_w else None
         return dx, dw, dbias, (dgamma if need_g else None), (dbeta if need_bt else None), dres, None
 
 

@@ -133,6 +133,72 @@ def test_conv_wgrad_multi_tile_and_segments(P):
                C.int_array([3, 4, 100]), C.int_array([3, 4, 99]), 1, 1, C.stream(torch.device(DEV)))
 
 
+WGRAD_TC_CASES = [
+    # B, Ca, Cg, D, H, W: ragged rows / columns against the 4 x 64 tile, single plane, several channel passes
+    (1, 32, 32, 4, 6, 32), (2, 32, 32, 3, 9, 70), (1, 64, 32, 2, 4, 64), (1, 64, 64, 3, 5, 20), (3, 32, 64, 1, 3, 130),
+    (1, 32, 32, 12, 16, 128),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_CASES, ids=["x".join(map(str, c)) for c in WGRAD_TC_CASES])
+def test_conv_wgrad_tcgen05(P, case):
+    """csrc/wgrad_tc.cu (MN-major tcgen05 operands over the blocked layout, three CTA populations by depth tap) against
+    torch autograd's Conv3d weight gradient on the CPU (what the reference's backward computes).  bf16 split pairs
+    carry ~16 bits per operand: agreement at the 1e-4 level of the tensor's scale; the SIMT fp32 kernel agrees with it
+    at the same level."""
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators import tc_engine as T
+    if not T.tc_available():
+        pytest.skip("tcgen05 path unavailable on this device")
+    B, Ca, Cg, D, H, W = case
+    g = torch.Generator().manual_seed(B * 7 + W)
+    x = torch.randn(B, Ca, D, H, W, generator=g)
+    w = (torch.randn(Cg, Ca, 3, 3, 3, generator=g) * 0.05).requires_grad_(True)
+    y = F.conv3d(x, w, padding=1)
+    gy = torch.randn(y.shape, generator=g) * 0.01              # small gradients: the reason for bfloat16's exponent range
+    y.backward(gy)
+    xg, gg = x.to(DEV), gy.to(DEV)
+    assert T.wgrad_tc_eligible(xg, gg, (3, 3, 3), 1, 1, False)
+    dw = T.wgrad_tc(xg, gg)
+    got = dw.permute(2, 1, 0).reshape(Cg, Ca, 3, 3, 3)
+    close(got, w.grad, 2e-4, "dw tcgen05")
+    # accumulation semantics of the raw entry point: a second call adds onto the first
+    from densematchingbenchmark_b200 import _cabi as C
+    ab, gb = T.Blocked.from_ncdhw(xg, True, False), T.Blocked.from_ncdhw(gg, True, False)
+    C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), B, Ca, Cg, D, H, W, 0,
+           C.stream(torch.device(DEV)))
+    close(dw.permute(2, 1, 0).reshape(Cg, Ca, 3, 3, 3), 2.0 * w.grad, 2e-4, "dw accumulated twice")
+    with pytest.raises(C.DmbB200Error):
+        C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), B, Ca, 48, D, H, W, 0,
+               C.stream(torch.device(DEV)))
+
+
+def test_conv_wgrad_tcgen05_long_accumulation(P):
+    """Config-5 sized layer (32->32 at 4 x 48 x 64 x 128 voxels: ~2000 MMAs chained into every TMEM accumulator, which
+    adds with truncation) against the SIMT fp32 kernel and, on a sub-sampled set of taps, float64."""
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators import tc_engine as T
+    from densematchingbenchmark_b200 import _cabi as C
+    if not T.tc_available():
+        pytest.skip("tcgen05 path unavailable on this device")
+    B, Cc, D, H, W = 4, 32, 48, 64, 128
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(B, Cc, D, H, W, generator=g, device=DEV).relu_()        # post-ReLU activations: positive mean
+    gy = torch.randn(B, Cc, D, H, W, generator=g, device=DEV) * 1e-3 + 2e-4
+    dw_tc = T.wgrad_tc(x, gy)
+    dw_simt = torch.zeros(27, Cc, Cc, device=DEV)
+    C.call("dmb_b200_conv3d_wgrad", C.ptr(x), C.ptr(gy), C.ptr(dw_simt), B, Cc, Cc, C.int_array([D, H, W]),
+           C.int_array([D, H, W]), 1, 1, C.stream(torch.device(DEV)))
+    # float64 truth of the centre tap and one corner tap
+    xd, gd = x.double(), gy.double()
+    centre = torch.einsum("bcdhw,bkdhw->ck", xd, gd)
+    corner = torch.einsum("bcdhw,bkdhw->ck", xd[:, :, :-1, :-1, :-1], gd[:, :, 1:, 1:, 1:])      # tap (0,0,0)
+    for name, tap, want in (("centre", 13, centre), ("corner", 0, corner)):
+        e_tc = float((dw_tc[tap].double() - want).abs().max() / want.abs().max())
+        e_simt = float((dw_simt[tap].double() - want).abs().max() / want.abs().max())
+        print("wgrad %s tap: tcgen05 rel err %.2e, SIMT fp32 rel err %.2e" % (name, e_tc, e_simt))
+        assert e_tc < 5e-4
+    close(dw_tc, dw_simt.cpu(), 1e-3, "tcgen05 vs SIMT")
+
+
 # ---------------------------------------------------------------------------- upsampling / regression / volume
 @pytest.mark.parametrize("shape", [(2, 3, 5, 7, 12, 20, 28), (1, 6, 4, 9, 24, 16, 36), (1, 2, 2, 3, 5, 7, 11)])
 def test_upsample_trilinear_backward(P, shape):
@@ -273,9 +339,9 @@ def test_training_convs_run_on_tcgen05(P, monkeypatch):
     calls = []
     real = T.conv3d_ncdhw_tc
 
-    def counting(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False, scale=None):
+    def counting(x, w_packed, bias, stride, transposed, precision, residual=None, relu=False, scale=None, x_blocked=None):
         calls.append((tuple(w_packed.shape[1:]), stride, transposed, precision))
-        return real(x, w_packed, bias, stride, transposed, precision, residual, relu, scale)
+        return real(x, w_packed, bias, stride, transposed, precision, residual, relu, scale, x_blocked)
 
     monkeypatch.setattr(T, "conv3d_ncdhw_tc", counting)
     from make_golden import TRAIN_CASE
