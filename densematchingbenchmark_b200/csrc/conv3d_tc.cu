@@ -51,7 +51,35 @@ __host__ __device__ constexpr int nthreads_of(int kind, bool head = false) { ret
 __host__ __device__ constexpr int nbo_of(int kind) { return kind == 5 ? 16 : 32; }
 // depth-plane ring: the kw-merged kernel's planes are small enough for 6 stages (prefetch across
 // work-item boundaries)
-__host__ __device__ constexpr int nstage_of(int kind) { return (kind == 4 || kind == 5) ? 3 : 4; }
+__host__ __device__ constexpr int nstage_of(int kind) { return (kind == 4 || kind >= 5) ? 3 : 4; }
+// KIND 6, 7, 8: the transposed conv with K = 64 (all input channels of a 64-channel layer in one pass, 32 output
+// channels) run as three CLASS-GROUP launches.  Every tap of the 3x3x3 kernel belongs to exactly one of the 8 output
+// parity classes (rd, rh, rw), so the 27 x 8 KB of (hi, lo) weights -- too much for shared memory next to the plane
+// ring -- split by class: group 0 = classes (1,1,*) (12 taps), group 1 = (0,1,*) + (1,0,*) (12 taps), group 2 =
+// (0,0,*) (3 taps).  Each launch writes ITS output voxels exactly once, residual and ReLU included, with the same
+// number of MMAs as KIND 2's two input-channel passes -- which write, re-read and re-write the whole output
+// (Hourglass conv6: 850 MB moved for 450 MB algorithmic).  The input (1/8 resolution, 50 MB) is re-read from L2.
+__host__ __device__ constexpr bool is_t64(int kind) { return kind >= 6; }
+__host__ __device__ constexpr bool is_transposed(int kind) { return kind == 2 || kind >= 5; }
+__host__ __device__ constexpr int t64_ntaps(int grp) { return grp == 2 ? 3 : 12; }
+__host__ __device__ constexpr int t64_nphases(int grp) { return grp == 1 ? 2 : 1; }
+// phase pi of group grp handles the two classes (rd, rh, 0) and (rd, rh, 1)
+__host__ __device__ constexpr int t64_rd(int grp, int pi) { return grp == 0 ? 1 : (grp == 1 ? pi : 0); }
+__host__ __device__ constexpr int t64_rh(int grp, int pi) { return grp == 0 ? 1 : (grp == 1 ? 1 - pi : 0); }
+// taps of an output parity r along one axis: r = 0 -> {1}, r = 1 -> {0, 2}
+__host__ __device__ constexpr bool t64_uses(int r, int k) { return r == 0 ? k == 1 : k != 1; }
+// shared-memory slot of tap (kd, kh, kw) in group grp (-1: not in the group): phases in order, then kd, kh, kw
+__host__ __device__ constexpr int t64_slot(int grp, int kd, int kh, int kw) {
+    int slot = 0;
+    for (int pi = 0; pi < t64_nphases(grp); ++pi)
+        for (int d = 0; d < 3; ++d)
+            for (int h = 0; h < 3; ++h) {
+                if (!t64_uses(t64_rd(grp, pi), d) || !t64_uses(t64_rh(grp, pi), h)) continue;
+                if (d == kd && h == kh) return slot + kw;
+                slot += 3;
+            }
+    return -1;
+}
 constexpr int TMEM_COLS = 512;
 
 // KIND 0: stride-1 conv          M space = output = input grid; halo box 18x10 per plane (reference kernel)
@@ -82,6 +110,9 @@ template <> struct Geo<5> {
     static constexpr int CBK = 8;
     static constexpr int PLANE_BYTES = 8 * 17 * 9 * 16;            // 19584 = 153 * 128
 };
+template <> struct Geo<6> : Geo<5> {};
+template <> struct Geo<7> : Geo<5> {};
+template <> struct Geo<8> : Geo<5> {};
 // KIND 3: stride-1 conv with the three kw taps merged into the MMA's N dimension.  The 8 tile columns
 // are w0-1 .. w0+6; every MMA multiplies the UNSHIFTED column block with [W(kw=0)|W(kw=1)|W(kw=2)], the
 // epilogue adds the three partial results of neighbouring columns (warp shuffles).  6 of 8 columns
@@ -186,7 +217,7 @@ struct Smem {
     static constexpr int NBO = nbo_of(KIND);                       // output channels per pass
     static constexpr int ROWS = (SPLIT ? 2 * NBO : NBO) * NKW;     // B-operand rows per channel block
     static constexpr int TAP_BYTES = CBK * ROWS * 16;              // one B block (a tap, or a (kd,kh) tap row)
-    static constexpr int W_BYTES = (TAPS / NKW) * TAP_BYTES;
+    static constexpr int W_BYTES = (is_t64(KIND) ? t64_ntaps(KIND - 6) : TAPS / NKW) * TAP_BYTES;
     static constexpr int PLANE_BYTES = G::PLANE_BYTES;
     static constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * PLANE_BYTES;
     static constexpr int NST = nstage_of(KIND);
@@ -205,7 +236,8 @@ struct Smem {
     // KIND 2: one accumulator per output parity class (chains are <= 32 MMAs by construction)
     static constexpr int CLS_COLS = SPLIT ? 2 * NBO : NBO;
     static constexpr int ACC_COLS =
-        (KIND == 2 || KIND == 5) ? 4 * CLS_COLS : ((KIND == 3 || KIND == 4) ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32));
+        is_t64(KIND) ? 2 * CLS_COLS
+                     : ((KIND == 2 || KIND == 5) ? 4 * CLS_COLS : ((KIND == 3 || KIND == 4) ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32)));
     static_assert(2 * ACC_COLS <= TMEM_COLS, "accumulators exceed TMEM");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
 };
@@ -414,9 +446,18 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             mbar_expect_tx(wbar, S::W_BYTES);      // weights: packed in global exactly as they sit in smem
-            for (int t = 0; t < TAPS / S::NKW; ++t)
-                bulk_g2s(w_smem + t * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
-                         S::TAP_BYTES, wbar);
+            if (is_t64(KIND)) {                    // only this class group's taps, in slot order
+                for (int t = 0; t < TAPS; ++t) {
+                    const int slot = t64_slot(KIND - 6, t / 9, (t / 3) % 3, t % 3);
+                    if (slot >= 0)
+                        bulk_g2s(w_smem + slot * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
+                                 S::TAP_BYTES, wbar);
+                }
+            } else {
+                for (int t = 0; t < TAPS / S::NKW; ++t)
+                    bulk_g2s(w_smem + t * S::TAP_BYTES, reinterpret_cast<const unsigned char*>(p.w_blob) + t * S::TAP_BYTES,
+                             S::TAP_BYTES, wbar);
+            }
             uint32_t n = 0;
             uint32_t ntrace_p = 0;
             const int in_cb0_k4 = p.in_cb0;
@@ -454,7 +495,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             tma_load_5d(dst + S::PLANE_BYTES + Geo<4>::EVEN_BYTES, &maps.m[3], &full[slot], 8 * (it.w0 - 1),
                                         it.h0 - 1, pl, in_cb0_k4, it.b);
                         }
-                    } else if (KIND == 2 || KIND == 5) {
+                    } else if (is_transposed(KIND)) {
                         mbar_expect_tx(&full[slot], (SPLIT ? 2 : 1) * CBK * 17 * 9 * 16);
                         tma_load_5d(dst, &maps.m[0], &full[slot], 8 * it.w0, it.h0, pl, p.in_cb0, it.b);
                         if (SPLIT)
@@ -739,6 +780,83 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     }
                     n_base += nplanes;
                     t_base += nout;
+                } else if (is_t64(KIND)) {
+                    // transposed, K = 64, one class group per launch: per input depth plane NPH phases, each the two
+                    // classes (rd, rh, rw = 0 | 1) accumulated in their own TMEM columns (double buffered over phases)
+                    constexpr int GRP = KIND - 6;
+                    constexpr int NPH = t64_nphases(GRP);
+                    constexpr uint32_t LBO_A = 17 * 9 * 16, SBO_A = 9 * 16;
+                    constexpr uint32_t a_hiw = desc_hi(SBO_A);
+                    auto issue_phase = [&](uint32_t a_same, uint32_t a_next, int rd, int rh, uint32_t accp) {   // elected lane only
+#pragma unroll
+                        for (int rw = 0; rw < 2; ++rw) {
+                            const uint32_t acc = accp + rw * S::CLS_COLS;
+                            bool first = true;
+#pragma unroll
+                            for (int id = 0; id < 2; ++id) {
+                                if (id > rd) continue;
+                                // rd=0: (kd=1, this plane); rd=1: id0 = (kd=0, next plane), id1 = (kd=2, this plane)
+                                const int kd = rd == 0 ? 1 : (id == 0 ? 0 : 2);
+                                const uint32_t a_lo0 = desc_lo((rd == 1 && id == 0) ? a_next : a_same, LBO_A);
+#pragma unroll
+                                for (int ih = 0; ih < 2; ++ih) {
+                                    if (ih > rh) continue;
+                                    const int kh = rh == 0 ? 1 : (ih == 0 ? 0 : 2);
+                                    const int offh = (rh == 1 && ih == 0) ? 1 : 0;
+#pragma unroll
+                                    for (int iw = 0; iw < 2; ++iw) {
+                                        if (iw > rw) continue;
+                                        const int kw = rw == 0 ? 1 : (iw == 0 ? 0 : 2);
+                                        const int offw = (rw == 1 && iw == 0) ? 1 : 0;
+                                        const int wslot_ = t64_slot(GRP, kd, kh, kw);
+                                        const uint32_t a_off = (offh * 9 + offw) * 16;
+#pragma unroll
+                                        for (int kk = 0; kk < CBK / 2; ++kk) {
+                                            const uint32_t b_lo = b_lo0 + ((wslot_ * S::TAP_BYTES + 2 * kk * (int)S::LBO_B) >> 4);
+                                            mma_f16_ss_rt(acc, a_lo0 + ((a_off + 2 * kk * LBO_A) >> 4), a_hiw, b_lo, b_hi, idesc_main,
+                                                          first ? 0u : 1u);
+                                            first = false;
+                                            if (SPLIT)
+                                                mma_f16_ss<true>(acc, a_lo0 + ((S::PLANE_BYTES + a_off + 2 * kk * LBO_A) >> 4), a_hiw, b_lo,
+                                                                 b_hi, idesc_lo);
+                                        }
+                                    }
+                                }
+                            }
+                        }
+                    };
+                    uint32_t slot = n_base % NSTAGE, phase = (n_base / NSTAGE) & 1;
+                    uint32_t wslot = slot, wphase = phase;
+                    int waited = 0;
+                    for (int od = 0; od < nout; ++od) {
+                        while (waited < od + 2) {
+                            mbar_wait(&full[wslot], wphase);
+                            if (++wslot == NSTAGE) { wslot = 0; wphase ^= 1; }
+                            ++waited;
+                        }
+                        const uint32_t s1 = slot + 1 >= NSTAGE ? slot + 1 - NSTAGE : slot + 1;
+                        const uint32_t a_same = planes_addr + slot * S::STAGE_BYTES;
+                        const uint32_t a_next = planes_addr + s1 * S::STAGE_BYTES;
+#pragma unroll
+                        for (int pi = 0; pi < NPH; ++pi) {
+                            const uint32_t t = t_base + NPH * od + pi;
+                            const uint32_t buf = t & 1;
+                            mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);
+                            tcgen05_fence_after();
+                            if (elect_one()) {
+                                issue_phase(a_same, a_next, t64_rd(GRP, pi), t64_rh(GRP, pi), tmem_base + buf * S::ACC_COLS);
+                                commit_one(&tfull[buf]);
+                                if (pi == NPH - 1) {
+                                    commit_one(&empty[slot]);
+                                    if (od == nout - 1) commit_one(&empty[s1]);
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+                    }
+                    n_base += nout + 1;
+                    t_base += NPH * nout;
                 } else {
                     // transposed: per input depth qd two groups (output depth parity rd), 4 classes each
                     constexpr uint32_t LBO_A = 17 * 9 * 16, SBO_A = 9 * 16;
@@ -919,6 +1037,45 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                         }
                     }
                     if (tracer) trace_stamp(p, 1, ntrace);                     // [3] stores issued
+                } else if (is_t64(KIND)) {
+                    constexpr int GRP = KIND - 6;
+                    const int rw = (warp - 2) >> 2;            // warps 2..5: class rw = 0; warps 6..9: rw = 1
+#pragma unroll
+                    for (int pi = 0; pi < t64_nphases(GRP); ++pi, ++t) {
+                        const int rd = t64_rd(GRP, pi), rh = t64_rh(GRP, pi);
+                        const uint32_t buf = t & 1;
+                        if (p.res_hi && valid) {               // residual lines into L1 while the phase's MMAs run
+                            const size_t plane_sz = (size_t)p.Ho * p.Wo;
+                            const size_t vox = (size_t)(2 * d + rd) * plane_sz + (size_t)(2 * h + rh) * p.Wo + 2 * w + rw;
+#pragma unroll
+                            for (int cb = 0; cb < 4; ++cb) {
+                                const size_t ri = ((size_t)(it.b * p.res_cbs + p.res_cb0 + cb) * p.Do) * plane_sz + vox;
+                                prefetch_l1(p.res_hi + ri);
+                                if (p.res_lo) prefetch_l1(p.res_lo + ri);
+                            }
+                        }
+                        mbar_wait(&tfull[buf], (t >> 1) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS + rw * S::CLS_COLS;
+                        uint32_t r0[32];
+                        float v[NB];
+                        tmem_ld32(taddr, r0);
+                        if (SPLIT) {
+                            uint32_t r1[32];
+                            tmem_ld32(taddr + 32, r1);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) v[c] = (__uint_as_float(r0[c]) + __uint_as_float(r1[c])) * p.acc_scale;
+                        } else {
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) v[c] = __uint_as_float(r0[c]) * p.acc_scale;
+                        }
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[buf]);
+                        if (valid) store_voxel<FP16, 4>(p, v, bias, it.b, 2 * d + rd, 2 * h + rh, 2 * w + rw);
+                    }
                 } else if (KIND != 2 && KIND != 5) {
                     const uint32_t buf = t & 1;
                     mbar_wait(&tfull[buf], (t >> 1) & 1);
@@ -1115,7 +1272,7 @@ static int launch_kind(const Maps& maps, const Params& p, int grid, bool split, 
     return fp16 ? launch_pass<KIND, false, true>(maps, p, grid, stream) : launch_pass<KIND, false, false>(maps, p, grid, stream);
 }
 
-static int cbk_of(int kind) { return kind == 1 ? Geo<1>::CBK : (kind == 5 ? Geo<5>::CBK : 4); }
+static int cbk_of(int kind) { return kind == 1 ? Geo<1>::CBK : (kind >= 5 ? Geo<5>::CBK : 4); }
 static int nkw_of(int kind) { return (kind == 3 || kind == 4) ? 3 : 1; }
 
 // row-parity map (ph) over the whole batch: dims (w*8, H/2, D, cb, b); row h2 of parity ph is input row 2*h2+ph
@@ -1138,7 +1295,7 @@ using namespace dmb::tc;
 extern "C" int dmb_b200_conv3d_tc_available(void) { return device_ok(); }
 
 extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split, int kind) {
-    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 5) return 0;
+    if (Cin <= 0 || Cout <= 0 || Cin % 32 || kind < 0 || kind > 6) return 0;
     const int cbk = cbk_of(kind), nb = nbo_of(kind);
     if (Cin % (8 * cbk)) return 0;
     const int64_t blob = (int64_t)TAPS * cbk * (split ? 2 * nb : nb) * 16;
@@ -1148,8 +1305,9 @@ extern "C" int64_t dmb_b200_conv3d_tc_weight_bytes(int Cin, int Cout, int split,
 extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_blob, int Cin, int Cout, int split,
                                                int fp16, float scale, int kind, void* stream) {
     DMB_REQUIRE(w_packed && w_blob, "conv3d_tc_pack_weights: null pointer");
-    DMB_REQUIRE(kind >= 0 && kind <= 5, "conv3d_tc_pack_weights: kind must be 0..5");
+    DMB_REQUIRE(kind >= 0 && kind <= 6, "conv3d_tc_pack_weights: kind must be 0..6");
     DMB_REQUIRE(kind != 5 || (Cin % 64 == 0 && Cout % 16 == 0), "conv3d_tc_pack_weights: kind 5 needs Cin %% 64 == 0 and Cout %% 16 == 0");
+    DMB_REQUIRE(kind != 6 || (Cin == 64 && Cout % 32 == 0), "conv3d_tc_pack_weights: kind 6 needs Cin == 64 and Cout %% 32 == 0");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc_pack_weights: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(Cout > 0 && (Cout % 32 == 0 || Cout < 32), "conv3d_tc_pack_weights: Cout=%d must be <32 or a multiple of 32", Cout);
     DMB_REQUIRE(scale > 0.f, "conv3d_tc_pack_weights: scale must be positive");
@@ -1217,7 +1375,8 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
                           int relu, int fp16, const float* head_w, float* head_t, void* stream) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
-    DMB_REQUIRE(kind >= 0 && kind <= 5, "conv3d_tc: kind must be 0/3 (stride 1), 1/4 (stride 2) or 2/5 (transposed stride 2)");
+    DMB_REQUIRE(kind >= 0 && kind <= 6, "conv3d_tc: kind must be 0/3 (stride 1), 1/4 (stride 2) or 2/5/6 (transposed stride 2)");
+    DMB_REQUIRE(kind != 6 || (Cin == 64 && Cout % 32 == 0), "conv3d_tc: kind 6 needs Cin == 64 and Cout %% 32 == 0");
     DMB_REQUIRE(Cin > 0 && Cin % 32 == 0, "conv3d_tc: Cin=%d must be a multiple of 32", Cin);
     DMB_REQUIRE(kind != 5 || (Cin % 64 == 0 && Cout % 32 == 0), "conv3d_tc: kind 5 needs Cin %% 64 == 0 and Cout %% 32 == 0");
     DMB_REQUIRE(w_scale > 0.f, "conv3d_tc: w_scale must be positive");
@@ -1277,7 +1436,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
             if (rc) return rc;
             for (int i = 4; i < 8; ++i) maps.m[i] = maps.m[0];
         } else {
-            const int bh = (kind == 2 || kind == 5) ? 17 : (kind == 3 ? K3_TH + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? K3_TW : 9);
+            const int bh = is_transposed(kind) ? 17 : (kind == 3 ? K3_TH + 2 : 18), bw = kind == 0 ? 10 : (kind == 3 ? K3_TW : 9);
             rc = make_dense_map(&maps.m[0], xh, B, CBS, D, H, W, bh, bw, cbk, fp16);
             if (rc) return rc;
             rc = make_dense_map(&maps.m[1], xl, B, CBS, D, H, W, bh, bw, cbk, fp16);
@@ -1320,7 +1479,11 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
                 else if (kind == 2) rc = launch_kind<2>(maps, p, grid, split, fp16, stream);
                 else if (kind == 3) rc = launch_kind<3>(maps, p, grid, split, fp16, stream);
                 else if (kind == 5) rc = launch_kind<5>(maps, p, grid, split, fp16, stream);
-                else rc = launch_kind<4>(maps, p, grid, split, fp16, stream);
+                else if (kind == 6) {              // three class-group launches, each writing its own output voxels once
+                    rc = launch_kind<6>(maps, p, grid, split, fp16, stream);
+                    if (!rc) rc = launch_kind<7>(maps, p, grid, split, fp16, stream);
+                    if (!rc) rc = launch_kind<8>(maps, p, grid, split, fp16, stream);
+                } else rc = launch_kind<4>(maps, p, grid, split, fp16, stream);
                 if (rc) return rc;
             }
         }
@@ -1338,7 +1501,7 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
 
 extern "C" int dmb_b200_conv3d_tc_schedule(int kind, int B, int D, int H, int W, int* out) {
     DMB_REQUIRE(out, "conv3d_tc_schedule: null output");
-    DMB_REQUIRE(kind >= 0 && kind <= 5 && B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc_schedule: bad arguments");
+    DMB_REQUIRE(kind >= 0 && kind <= 6 && B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc_schedule: bad arguments");
     Params p;
     const int grid = plan_schedule(p, kind, B, D, H, W);
     out[0] = p.tiles_h; out[1] = p.tiles_w; out[2] = p.nseg; out[3] = p.seg_len; out[4] = p.n_items; out[5] = grid;

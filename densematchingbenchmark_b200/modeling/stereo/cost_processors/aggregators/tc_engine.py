@@ -27,9 +27,15 @@ KW_MERGE = os.environ.get("DMB_B200_TC_KW_MERGE", "1") != "0"
 # fewer bytes -- a tcgen05.mma with M=128 costs ~110 cycles however small N is (its A tile streams from shared
 # memory), and kind 5 issues twice as many.  Kept, tested and off by default.
 DECONV_K64 = os.environ.get("DMB_B200_TC_DECONV_K64", "0") == "1"
+# kind 6 (default for 64-input-channel transposed layers): one K = 64 pass per 32 output channels, run as three
+# class-group launches that each write their output parity classes once (csrc/conv3d_tc.cu, KIND 6..8) -- the MMA
+# count of kind 2 with half its output traffic.  DMB_B200_TC_DECONV_GROUPS=0 falls back to kind 2.
+DECONV_GROUPS = os.environ.get("DMB_B200_TC_DECONV_GROUPS", "1") != "0"
 
 
 def _transposed_kind(cin, cout):
+    if DECONV_GROUPS and cin == 64 and cout % 32 == 0:
+        return 6
     return 5 if (DECONV_K64 and cin % 64 == 0 and cout % 32 == 0) else 2
 
 PRECISIONS = {          # name -> (split, fp16)
@@ -174,7 +180,7 @@ def conv_tc_raw(x, blob, bias, Cin, Cout, scale, kind, residual=None, relu=False
     D, H, W = x.dims
     if kind in (1, 4) and (D % 2 or H % 2 or W % 2):
         raise ValueError("stride-2 convolution on tcgen05 needs even extents, got %s" % (x.dims,))
-    odims = x.dims if kind in (0, 3) else (tuple(n // 2 for n in x.dims) if kind in (1, 4) else tuple(2 * n for n in x.dims))
+    odims = x.dims if kind in (0, 3) else (tuple(n // 2 for n in x.dims) if kind in (1, 4) else tuple(2 * n for n in x.dims))   # 2, 5, 6: transposed
     dev = x.hi.device
     fp16 = 1 if x.fp16 else 0
     if Cout == 1:

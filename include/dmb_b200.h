@@ -161,7 +161,11 @@ int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out
  *   kind 2: transposed, stride 2, pad 1, output_padding 1 (Hourglass conv5/conv6, :53-60)
  *   kind 5: the same transposed convolution for Cin % 64 == 0: one pass = all 64 input channels x 16 output
  *           channels, so every output element is written once (kind 2 accumulates two 32-input-channel
- *           passes in place); the production kernel for the hourglass' 64-channel transposed layers
+ *           passes in place); measured slower than kind 2 (twice the MMAs), kept for A/B
+ *   kind 6: the same transposed convolution for Cin == 64: one pass = all 64 input channels x 32 output channels,
+ *           run as three class-group launches (every 3x3x3 tap belongs to exactly one output parity class, so
+ *           the weights split by class: 12 + 12 + 3 taps); every output element is written once with kind 2's MMA
+ *           count; the production kernel for the hourglass' 64-channel transposed layers
  * x_hi/x_lo: [B][Cin/8][D][H][W][8] (x_lo NULL => single plane, else the (hi,lo) split pair);
  * B,D,H,W are the INPUT extents; the output grid is the same / halved / doubled.
  * w_blob: packed by dmb_b200_conv3d_tc_pack_weights with the same split / fp16 / kind; w_scale its

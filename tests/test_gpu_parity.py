@@ -482,17 +482,25 @@ TC_STRIDED_CASES = [
     ("tr", 32, 32, (3, 16, 8), False, False, False),          # one tile
     ("tr", 64, 32, (4, 19, 11), True, True, False),           # ragged, residual at output resolution
     ("tr", 64, 64, (5, 17, 18), False, True, True),
+    ("tr", 64, 32, (5, 21, 27), True, True, True),            # several tiles in both directions, ragged, B = 2
 ]
 
 
-@pytest.mark.parametrize("kw_merge", [True, False])
+@pytest.mark.parametrize("kw_merge", [True, False, "k64"])
 @pytest.mark.parametrize("precision", ["fp16x3", "bf16"])
 @pytest.mark.parametrize("case", TC_STRIDED_CASES)
 def test_conv3d_tc_strided_vs_torch_cpu(P, case, precision, kw_merge, monkeypatch):
     tc = _tc_or_skip()
-    monkeypatch.setattr(tc, "KW_MERGE", kw_merge)
-    # 64-input-channel transposed layers: kind 5 (K=64 passes, production) with kw_merge, kind 2 (in-place passes) without
-    monkeypatch.setattr(tc, "DECONV_K64", kw_merge)
+    if kw_merge == "k64" and not (case[0] == "tr" and case[1] == 64):
+        pytest.skip("the K=64 / 16-output-channel variant exists for 64-channel transposed layers only")
+    monkeypatch.setattr(tc, "KW_MERGE", bool(kw_merge))
+    # 64-input-channel transposed layers: kind 6 (class-group launches, production) with kw_merge, kind 2 (in-place
+    # input-channel passes) without, kind 5 (K = 64, 16 output channels per pass) with 'k64'
+    monkeypatch.setattr(tc, "DECONV_GROUPS", kw_merge is True)
+    monkeypatch.setattr(tc, "DECONV_K64", kw_merge == "k64")
+    if case[0] == "tr":
+        want_kind = {True: 6, False: 2, "k64": 5}[kw_merge] if case[1] == 64 else 2
+        assert tc._transposed_kind(case[1], case[2]) == want_kind
     split, fp16 = tc.PRECISIONS[precision]
     dt = torch.float16 if fp16 else torch.bfloat16
     kind, cin, cout, dims, bias, residual, relu = case

@@ -27,7 +27,8 @@ if ROOT not in sys.path:
 
 
 def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192, steps=3, warmup=2, sync_bn=True,
-                    backbone=True, bucket_mb=4.0, loss="config", rank=0, world=1, device=None, sync_backbone_bn=True):
+                    backbone=True, bucket_mb=4.0, loss="config", rank=0, world=1, device=None, sync_backbone_bn=True,
+                    channels_last_backbone=True):
     """Times `steps` training steps after `warmup`.  The process group (NCCL) must already be initialised when
     world > 1.  Returns the result dict on every rank (times are the max over ranks)."""
     import torch.distributed as dist
@@ -48,6 +49,10 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
         disp_predictor=dict(type="FASTER", max_disp=max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=True)))
     torch.manual_seed(0)                                             # identical replicas
     bb = PSMNetBackbone(3).to(device).train() if backbone else None
+    if bb is not None and channels_last_backbone:
+        # cuDNN's fastest 2-D kernels are NHWC: with NCHW tensors every convolution of the (torch) backbone is wrapped
+        # in a pair of layout-conversion kernels (~1400 launches, ~10 ms of the step: profiles/r2_launches_train*.csv)
+        bb = bb.to(memory_format=torch.channels_last)
     proc = P.build_cost_processor(cfg).to(device).train()
     pred = P.build_disp_predictor(cfg).to(device).train()
     synced = bool(sync_bn and world > 1)
@@ -68,6 +73,9 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
     if bb is not None:
         left = torch.rand(B, 3, H, W, generator=g).to(device)
         right = torch.rand(B, 3, H, W, generator=g).to(device)
+        if channels_last_backbone:
+            left = left.contiguous(memory_format=torch.channels_last)
+            right = right.contiguous(memory_format=torch.channels_last)
     else:
         left = (torch.randn(B, 32, H // 4, W // 4, generator=g) * 0.5).to(device).requires_grad_(True)
         right = (torch.randn(B, 32, H // 4, W // 4, generator=g) * 0.5).to(device).requires_grad_(True)
@@ -159,6 +167,7 @@ def main():
     ap.add_argument("--no-backbone", action="store_true", help="feed synthetic features (hot path only)")
     ap.add_argument("--bucket-mb", type=float, default=4.0)
     ap.add_argument("--local-backbone-bn", action="store_true", help="keep the torch backbone's BatchNorm per rank")
+    ap.add_argument("--nchw-backbone", action="store_true", help="torch backbone in NCHW (default: channels_last)")
     ap.add_argument("--loss", default="config", choices=["config", "l1"],
                     help="config: the losses of the reference configuration; l1: smooth-L1 only")
     args = ap.parse_args()
@@ -173,7 +182,7 @@ def main():
     try:
         res = run_train_bench(args.kind, args.batch, args.height, args.width, args.max_disp, args.steps, args.warmup,
                               args.sync_bn, not args.no_backbone, args.bucket_mb, args.loss, rank, world, device,
-                              not args.local_backbone_bn)
+                              not args.local_backbone_bn, not args.nchw_backbone)
         if rank == 0:
             print(json.dumps(res))
     finally:
