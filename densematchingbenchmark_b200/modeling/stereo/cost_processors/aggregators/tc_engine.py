@@ -38,6 +38,23 @@ def _transposed_kind(cin, cout):
         return 6
     return 5 if (DECONV_K64 and cin % 64 == 0 and cout % 32 == 0) else 2
 
+# fp16 element formats saturate: |x| > 65504 becomes inf in the hi plane and `lo = x - inf` poisons everything
+# downstream.  BatchNorm'ed cost volumes stay orders of magnitude below that, so production runs unchecked;
+# DMB_B200_CHECK_FINITE=1 verifies every tensor the tcgen05 path produces or ingests (one host synchronisation per
+# layer: a debugging aid) and raises with the layer's name.  'bf16x3' has the full fp32 exponent range.
+CHECK_FINITE = os.environ.get("DMB_B200_CHECK_FINITE", "0") == "1"
+
+
+def check_finite(blocked_or_tensor, what):
+    if not CHECK_FINITE:
+        return
+    t = blocked_or_tensor.hi if isinstance(blocked_or_tensor, Blocked) else blocked_or_tensor
+    if not bool(torch.isfinite(t).all()):
+        raise FloatingPointError(
+            "%s: non-finite values on the tcgen05 path -- activations beyond the IEEE-half range (65504)? "
+            "Use precision='bf16x3' (full fp32 exponent range) for un-normalised inputs" % what)
+
+
 PRECISIONS = {          # name -> (split, fp16)
     "fp16x3": (True, True),
     "bf16x3": (True, False),
@@ -72,6 +89,7 @@ class Blocked(object):
         out = Blocked.empty(B, Cc, (D, H, W), split, fp16, x.device)
         C.call("dmb_b200_ncdhw_to_blocked", C.ptr(x), C.ptr(out.hi), C.ptr(out.lo), B, Cc, D, H, W,
                1 if fp16 else 0, C.stream(x.device))
+        check_finite(out, "ncdhw_to_blocked")
         return out
 
     def to_ncdhw(self):
@@ -188,6 +206,7 @@ def conv_tc_raw(x, blob, bias, Cin, Cout, scale, kind, residual=None, relu=False
         C.call("dmb_b200_conv3d_tc", C.ptr(x.hi), C.ptr(x.lo), Cin, C.ptr(blob), float(scale), C.ptr(bias),
                None, None, None, None, 1, C.ptr(y), C.ptr(res_f32), x.B, D, H, W, kind, 1 if relu else 0, fp16,
                C.stream(dev))
+        check_finite(y, "conv3d_tc (%d->1)" % Cin)
         return y
     if residual is not None and (residual.dims != odims or residual.C != Cout):
         raise ValueError("residual geometry %s x%d does not match the output %s x%d"
@@ -197,6 +216,7 @@ def conv_tc_raw(x, blob, bias, Cin, Cout, scale, kind, residual=None, relu=False
            C.ptr(residual.hi) if residual is not None else None,
            C.ptr(residual.lo) if residual is not None else None,
            C.ptr(y.hi), C.ptr(y.lo), Cout, None, None, x.B, D, H, W, kind, 1 if relu else 0, fp16, C.stream(dev))
+    check_finite(y, "conv3d_tc (%d->%d, kind %d)" % (Cin, Cout, kind))
     return y
 
 
@@ -307,6 +327,7 @@ def classif_head(seq, x, res_f32=None):
            C.stream(dev))
     y = torch.empty(x.B, 1, D, H, W, dtype=torch.float32, device=dev)
     C.call("dmb_b200_head_gather", C.ptr(taps), C.ptr(res_f32), C.ptr(y), x.B, D, H, W, C.stream(dev))
+    check_finite(y, "classifier head")
     return y
 
 
@@ -338,6 +359,7 @@ def cat_volume_blocked(reference_fm, target_fm, max_disp, start_disp, dilation, 
     out = Blocked.empty(B, 2 * Cc, (len(idx), H, W), split, fp16, l.device)
     C.call("dmb_b200_cat_volume_blocked", C.ptr(l), C.ptr(r), C.ptr(out.hi), C.ptr(out.lo), B, Cc, H, W,
            C.int_array(idx), len(idx), 1 if fp16 else 0, C.stream(l.device))
+    check_finite(out, "cat_volume_blocked")
     return out
 
 

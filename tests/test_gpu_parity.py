@@ -570,6 +570,21 @@ def test_cat_volume_blocked_matches_oracle(P):
             assert float((got - want).abs().max()) < 2.0 ** -20 * float(want.abs().max())
 
 
+def test_fp16_range_guard(P, monkeypatch):
+    """IEEE-half elements saturate at 65504: the debug guard (DMB_B200_CHECK_FINITE=1) names the layer instead of
+    letting inf - inf = NaN travel to the disparity map; 'bf16x3' takes the same input without trouble."""
+    tc = _tc_or_skip()
+    monkeypatch.setattr(tc, "CHECK_FINITE", True)
+    l, r = seeded.feature_pair(1, 32, 8, 16, seed=2)
+    lg, rg = (l * 1e6).to(DEV), (r * 1e6).to(DEV)
+    with pytest.raises(FloatingPointError):
+        tc.cat_volume_blocked(lg, rg, 4, 0, 1, "fp16x3")
+    blk = tc.cat_volume_blocked(lg, rg, 4, 0, 1, "bf16x3")
+    assert bool(torch.isfinite(blk.to_ncdhw()).all())
+    ok = tc.cat_volume_blocked(l.to(DEV), r.to(DEV), 4, 0, 1, "fp16x3")          # in range: passes the guard
+    assert ok.C == 64
+
+
 def test_acfnet_tc_engine_vs_reference_golden(P, golden_dir):
     """AcfAggregator (conv biases + learned deconv upsampling) with the trunk on tcgen05."""
     _tc_or_skip()
