@@ -53,7 +53,8 @@ SIGNATURES = {
     "dmb_b200_bn_backward_reduce": [_P, _P, _P, _P, _P, _P, _I, _I, _LL, _P],
     "dmb_b200_bn_backward_apply": [_P, _P, _P, _P, _P, _P, _P, _D, _P, _P, _I, _I, _LL, _P],
     "dmb_b200_conv3d_wgrad": [_P, _P, _P, _I, _I, _I, _IP, _IP, _I, _I, _P],
-    "dmb_b200_conv3d_wgrad_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dmb_b200_conv3d_wgrad_tc": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "dmb_b200_ncdhw_to_blocked_wsplit": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_upsample_deconv_wgrad": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_upsample_trilinear_backward": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_soft_argmin_backward": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _F, _F, _P, _P],

@@ -73,25 +73,35 @@ __global__ void __launch_bounds__(256) volume_rows_kernel(const float* __restric
     const size_t kstride = (size_t)H * W;
 
     if (VEC) {
-        const int W4 = W >> 2;
-        for (int i = threadIdx.x; i < D * W4; i += blockDim.x) {
-            const int k = i / W4;
-            const int x = (i - k * W4) << 2;
-            const int d = dl.d[k];
-            float v[4];
+        // a thread owns 4 consecutive columns and walks the disparities: the left / minuend values stay in registers,
+        // only the shifted right row is re-read from shared memory (no index divisions in the loop: the flat-index
+        // version spent ~40 instructions per 16-byte store and stalled at 3.9 TB/s)
+        for (int x = threadIdx.x << 2; x < W; x += blockDim.x << 2) {
+            const bool own_a = (MODE == 1) || !is_right;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            if (own_a) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int xx = x + j;
-                float val = 0.f;
-                if (col_valid(xx, d, W)) {
-                    if (MODE == 0)
-                        val = is_right ? row_a[xx - d] : row_a[xx];
-                    else
-                        val = row_a[xx] - row_b[xx - d];
-                }
-                v[j] = val;
+                for (int j = 0; j < 4; ++j) a[j] = row_a[x + j];
             }
-            st_cs_f4(out_row0 + k * kstride + x, make_float4(v[0], v[1], v[2], v[3]));
+            float* o = out_row0 + x;
+#pragma unroll 4
+            for (int k = 0; k < D; ++k, o += kstride) {
+                const int d = dl.d[k];
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int xx = x + j;
+                    float val = 0.f;
+                    if (col_valid(xx, d, W)) {
+                        if (MODE == 0)
+                            val = is_right ? row_a[xx - d] : a[j];
+                        else
+                            val = a[j] - row_b[xx - d];
+                    }
+                    v[j] = val;
+                }
+                st_cs_f4(o, make_float4(v[0], v[1], v[2], v[3]));
+            }
         }
     } else {
         for (int i = threadIdx.x; i < D * W; i += blockDim.x) {
@@ -134,8 +144,10 @@ static int launch_volume_rows(const float* left, const float* right, float* out,
             if (dl.d[i] >= W) dl.d[i] = W;
             if (dl.d[i] <= -W) dl.d[i] = -W;
         }
+        int vthreads = (int)(((W / 4) + 31) / 32) * 32;          // one thread per 4 columns
+        if (vthreads > 256) vthreads = 256;
         if (vec)
-            volume_rows_kernel<MODE, true><<<grid, 256, smem, as_stream(stream)>>>(left, right, out, C, H, W, n, k0, D, dl);
+            volume_rows_kernel<MODE, true><<<grid, vthreads, smem, as_stream(stream)>>>(left, right, out, C, H, W, n, k0, D, dl);
         else
             volume_rows_kernel<MODE, false><<<grid, 256, smem, as_stream(stream)>>>(left, right, out, C, H, W, n, k0, D, dl);
         int rc = check_launch("volume_rows_kernel");
@@ -221,7 +233,10 @@ __global__ void __launch_bounds__(256) gwc_rows_kernel(const float* __restrict__
 // feed 32 FMAs -- 12 shared loads per 32 FMAs instead of 8 per 4.  The right rows are staged with PAD
 // zeros on both sides: "shifted column outside the image" needs no branch (cat_fms.py:36-44 validity
 // is exactly 0 <= x - d < W).
-template <int CPG>   // channels per group (0 = runtime)
+// ALIGNED (d0 % 4 == 0): the right-row window is fetched as three aligned 16-byte loads starting one column earlier
+// -- the 11 scalar loads at a 16-byte lane stride were 4-way bank conflicted (44 + 4 shared-memory wavefronts per 32
+// FMAs: the kernel sat at the shared-memory bandwidth, 0.45 of the HBM peak; now 12 + 4).
+template <int CPG, bool ALIGNED>   // channels per group (0 = runtime)
 __global__ void __launch_bounds__(256) gwc_rows_unit_kernel(const float* __restrict__ left, const float* __restrict__ right,
                                                             float* __restrict__ out, int C, int G, int H, int W, int D,
                                                             int d0, int PAD) {
@@ -266,19 +281,27 @@ __global__ void __launch_bounds__(256) gwc_rows_unit_kernel(const float* __restr
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[kk][j] = 0.f;
         const float* lp0 = sl + x;
-        const float* rp0 = sr + PAD + x - dk - 7;                 // window start: index x - (dk+7)
+        const float* rp0 = sr + PAD + x - dk - 8;                 // window start: index x - (dk+8) (16-byte aligned if ALIGNED)
 #pragma unroll
         for (int c = 0; c < cpg; ++c) {
             const float4 lv = *reinterpret_cast<const float4*>(lp0 + c * W);
             const float l[4] = {lv.x, lv.y, lv.z, lv.w};
             const float* rp = rp0 + c * WR;
-            float rw[11];
+            float rw[12];
+            if (ALIGNED) {
 #pragma unroll
-            for (int j = 0; j < 11; ++j) rw[j] = rp[j];
+                for (int q = 0; q < 3; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(rp + 4 * q);
+                    rw[4 * q] = t.x; rw[4 * q + 1] = t.y; rw[4 * q + 2] = t.z; rw[4 * q + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 1; j < 12; ++j) rw[j] = rp[j];
+            }
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[kk][j] = fmaf(l[j], rw[j - kk + 7], acc[kk][j]);
+                for (int j = 0; j < 4; ++j) acc[kk][j] = fmaf(l[j], rw[j - kk + 8], acc[kk][j]);
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
@@ -382,14 +405,23 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo, int
 
 // x: [B,C,S] fp32 -> hi/lo: [B][C/8][S][8] bf16.  One thread per (b, cb, s): 8 strided-by-S reads
 // (coalesced across s) and one 16-byte store per plane.
+// wsplit_w > 0: the output rows are W-PARITY-SPLIT -- [..][row][even | odd][W/2][8] instead of [..][row][W][8] -- the
+// operand layout of the stride-2 tcgen05 weight gradient (csrc/wgrad_tc.cu); wsplit_w = W (even).
 __global__ void __launch_bounds__(256) ncs_to_blocked_kernel(const float* __restrict__ x, uint4* __restrict__ hi,
-                                                             uint4* __restrict__ lo, int C, size_t S, size_t total, int fp16) {
+                                                             uint4* __restrict__ lo, int C, size_t S, size_t total, int fp16,
+                                                             int wsplit_w) {
     const int CBS = C / 8;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t s = i % S;
+        size_t s = i % S;
         const size_t r = i / S;
         const int cb = r % CBS;
         const size_t b = r / CBS;
+        if (wsplit_w > 0) {                       // output position (row, parity, w2) <- input voxel (row, 2 * w2 + parity)
+            const size_t row = s / wsplit_w;
+            const int rem = (int)(s - row * wsplit_w), half = wsplit_w / 2;
+            const int par = rem / half, w2 = rem - par * half;
+            s = row * wsplit_w + 2 * w2 + par;
+        }
         const float* src = x + (b * C + (size_t)cb * 8) * S + s;
         float v[8];
 #pragma unroll
@@ -433,36 +465,60 @@ __global__ void __launch_bounds__(256) blocked_to_ncs_kernel(const uint4* __rest
 }
 
 // cat volume straight into the blocked layout: out [B][2C/8][D][H][W][8] from fp32 NCHW features.
-// One thread per (b, cb, k, y, x).
+// One CTA per (b, 8-channel block, y): the source row's 8 channels are split into 16-bit (hi, lo) ONCE -- the left
+// half keeps its own column in registers, the right half stages the converted row in shared memory -- and every
+// thread then walks the D disparities of its column with nothing but a validity test, (two shared loads) and two
+// 16-byte streaming stores per disparity.  (The first version decoded a flat index with four 64-bit divisions and
+// redid the 8 loads + split for every output voxel: ~300 instructions per 32 bytes written, instruction bound at
+// 3.4 TB/s where a plain fill reaches 7.2 TB/s on this part -- profiles/README.md.)
 __global__ void __launch_bounds__(256) cat_volume_blocked_kernel(const float* __restrict__ left,
                                                                  const float* __restrict__ right,
                                                                  uint4* __restrict__ o_hi, uint4* __restrict__ o_lo,
-                                                                 int B, int C, int H, int W, int D, DispList dl,
-                                                                 size_t total, int fp16) {
+                                                                 int C, int H, int W, int D, DispList dl, int fp16) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint4* s_hi = reinterpret_cast<uint4*>(smem_raw);              // [W] converted right row (right half only)
+    uint4* s_lo = s_hi + W;
+    const int y = blockIdx.x, cb = blockIdx.y, b = blockIdx.z;
     const int CBS = 2 * C / 8, CB_L = C / 8;
+    const bool is_r = cb >= CB_L;
     const size_t plane = (size_t)H * W;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        size_t r = i;
-        const int x = r % W; r /= W;
-        const int y = r % H; r /= H;
-        const int k = r % D; r /= D;
-        const int cb = r % CBS;
-        const int b = r / CBS;
-        const int d = dl.d[k];
-        float v[8];
+    const float* src = (is_r ? right : left) + ((size_t)b * C + (size_t)(is_r ? cb - CB_L : cb) * 8) * plane + (size_t)y * W;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    if (is_r) {                                                    // block-uniform
+        for (int x = threadIdx.x; x < W; x += blockDim.x) {
+            float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        if (col_valid(x, d, W)) {
-            const bool is_r = cb >= CB_L;
-            const float* src = (is_r ? right : left) + ((size_t)b * C + (size_t)(is_r ? cb - CB_L : cb) * 8) * plane +
-                               (size_t)y * W + (is_r ? x - d : x);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e * plane);
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e * plane + x);
+            uint4 h, l;
+            split8(v, h, l, fp16);
+            s_hi[x] = h;
+            s_lo[x] = l;
         }
-        uint4 h, l;
-        split8(v, h, l, fp16);
-        __stcs(o_hi + i, h);
-        if (o_lo) __stcs(o_lo + i, l);
+        __syncthreads();
+    }
+    for (int x0 = 0; x0 < W; x0 += blockDim.x) {
+        const int x = x0 + threadIdx.x;
+        if (x >= W) break;
+        uint4 h = zero, l = zero;
+        if (!is_r) {                                               // own column: converted once, kept in registers
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __ldg(src + e * plane + x);
+            split8(v, h, l, fp16);
+        }
+        size_t o = (((size_t)b * CBS + cb) * D) * plane + (size_t)y * W + x;
+#pragma unroll 4
+        for (int k = 0; k < D; ++k, o += plane) {
+            const int d = dl.d[k];
+            const bool ok = col_valid(x, d, W);
+            uint4 vh = zero, vl = zero;
+            if (ok) {
+                vh = is_r ? s_hi[x - d] : h;
+                vl = is_r ? s_lo[x - d] : l;
+            }
+            __stcs(o_hi + o, vh);
+            if (o_lo) __stcs(o_lo + o, vl);
+        }
     }
 }
 
@@ -506,12 +562,23 @@ extern "C" int dmb_b200_gwc_volume(const float* left, const float* right, float*
         const int PAD = ((maxabs + 8 + 8) + 3) & ~3;          // window reaches 7 before / 3 after the shifted column
         const size_t smem_u = (size_t)cpg * (W + W + 2 * PAD) * 4;
         if (smem_u <= 200 * 1024) {
+            // threads: the W/4 x ceil(D/8) register-block units spread evenly over as few sweeps as possible
+            const int units = (W / 4) * ((D + 7) / 8), sweeps = (units + 255) / 256;
+            int uthreads = (((units + sweeps - 1) / sweeps + 31) / 32) * 32;
+            if (uthreads > 256) uthreads = 256;
+            const bool aligned = (d0 % 4 == 0);
 #define DMB_GWC_UNIT(CPG)                                                                                              \
     do {                                                                                                               \
-        if (smem_u > 48 * 1024)                                                                                        \
-            DMB_CUDA(cudaFuncSetAttribute(gwc_rows_unit_kernel<CPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+        if (smem_u > 48 * 1024) {                                                                                      \
+            DMB_CUDA(cudaFuncSetAttribute(gwc_rows_unit_kernel<CPG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                           (int)smem_u));                                                               \
-        gwc_rows_unit_kernel<CPG><<<grid, 256, smem_u, as_stream(stream)>>>(left, right, out, C, G, H, W, D, d0, PAD); \
+            DMB_CUDA(cudaFuncSetAttribute(gwc_rows_unit_kernel<CPG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)smem_u));                                                               \
+        }                                                                                                              \
+        if (aligned)                                                                                                   \
+            gwc_rows_unit_kernel<CPG, true><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, G, H, W, D, d0, PAD);  \
+        else                                                                                                           \
+            gwc_rows_unit_kernel<CPG, false><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, G, H, W, D, d0, PAD); \
     } while (0)
             if (cpg == 8) DMB_GWC_UNIT(8);
             else if (cpg == 4) DMB_GWC_UNIT(4);
@@ -567,7 +634,17 @@ extern "C" int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo,
     DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ncdhw_to_blocked: non-positive dimension");
     DMB_REQUIRE(C % 8 == 0, "ncdhw_to_blocked: C=%d must be a multiple of 8", C);
     const size_t S = (size_t)D * H * W, total = (size_t)B * (C / 8) * S;
-    ncs_to_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)y_hi, (uint4*)y_lo, C, S, total, fp16 ? 1 : 0);
+    ncs_to_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)y_hi, (uint4*)y_lo, C, S, total, fp16 ? 1 : 0, 0);
+    return check_launch("ncs_to_blocked_kernel");
+}
+
+extern "C" int dmb_b200_ncdhw_to_blocked_wsplit(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W,
+                                                int fp16, void* stream) {
+    DMB_REQUIRE(x && y_hi, "ncdhw_to_blocked_wsplit: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && D > 0 && H > 0 && W > 0, "ncdhw_to_blocked_wsplit: non-positive dimension");
+    DMB_REQUIRE(C % 8 == 0 && W % 2 == 0, "ncdhw_to_blocked_wsplit: C=%d must be a multiple of 8 and W=%d even", C, W);
+    const size_t S = (size_t)D * H * W, total = (size_t)B * (C / 8) * S;
+    ncs_to_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(x, (uint4*)y_hi, (uint4*)y_lo, C, S, total, fp16 ? 1 : 0, W);
     return check_launch("ncs_to_blocked_kernel");
 }
 
@@ -594,8 +671,13 @@ extern "C" int dmb_b200_cat_volume_blocked(const float* left, const float* right
         int d = disp_idx_host[i];
         dl.d[i] = d >= W ? W : (d <= -W ? -W : d);
     }
-    const size_t total = (size_t)B * (2 * C / 8) * D * H * W;
-    cat_volume_blocked_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>(left, right, (uint4*)out_hi, (uint4*)out_lo,
-                                                                             B, C, H, W, D, dl, total, fp16 ? 1 : 0);
+    DMB_REQUIRE(H <= 65535 && 2 * C / 8 <= 65535 && B <= 65535, "cat_volume_blocked: grid dimension too large");
+    const size_t smem = (size_t)W * 32;
+    DMB_REQUIRE(smem <= 200 * 1024, "cat_volume_blocked: feature row too wide (W=%d)", W);
+    if (smem > 48 * 1024)
+        DMB_CUDA(cudaFuncSetAttribute(cat_volume_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const dim3 grid(H, 2 * C / 8, B);
+    cat_volume_blocked_kernel<<<grid, 256, smem, as_stream(stream)>>>(left, right, (uint4*)out_hi, (uint4*)out_lo, C, H, W, D,
+                                                                     dl, fp16 ? 1 : 0);
     return check_launch("cat_volume_blocked_kernel");
 }

@@ -27,6 +27,13 @@
 //
 // Tiles are TH x TW = 4 x 64 voxels of one depth plane; halos, ragged edges and the planes d = -1 / D are zero-filled
 // by the TMA (tensor maps over 8-byte elements: a box row of 66 voxels exceeds the 256-element box limit at 2 bytes).
+//
+// STRIDE 2 (Hourglass conv1 / conv3, and conv5 / conv6 with the roles of input and output swapped):
+//     dw[tap][ca][cg] = sum over the LOW-resolution grid of  a[2d+kd-1][2h+kh-1][2w+kw-1] * g[d][h][w]
+// K = 16 consecutive low-resolution voxels pair with every second voxel of `a`, which a 16-byte K pitch cannot
+// express, so `a` arrives W-PARITY-SPLIT ([..][H][even | odd][W/2][8], written by the layout conversion that the
+// training path runs anyway): kw = 1 reads the even half, kw = 0 / 2 the odd half at offsets -1 / 0.  Rows 2h-1, 2h of
+// the tile are adjacent (taps kh = 0, 1: the M = 128 pair), row 2h+1 is the single; 4 x 32 tiles.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -35,21 +42,29 @@ namespace wg {
 
 using namespace dmb::tc;
 
-constexpr int TH = 4, TW = 64;                       // g tile: rows x voxels of one depth plane
-constexpr int XR = TH + 2, XW = TW + 2;              // x tile incl. halo
 constexpr int CB = 4;                                // 8-channel blocks per pass (32 channels)
-constexpr uint32_t PW = XW * 16;                     // x: pitch between channel groups (one row of one block): 1056
-constexpr uint32_t XROW = 2 * CB * PW;               // x: one tile row = [hi cb0..3 | lo cb0..3]: 8448
-constexpr uint32_t X_BYTES = XR * XROW;              // 50688
-constexpr uint32_t PG = TH * TW * 16;                // g: pitch between channel groups: 4096
-constexpr uint32_t G_BYTES = 2 * CB * PG;            // 32768
-constexpr uint32_t STAGE_BYTES = X_BYTES + G_BYTES;  // 83456
 constexpr int NSTAGE = 2;
-constexpr uint32_t BAR_OFF = NSTAGE * STAGE_BYTES;
-constexpr uint32_t SMEM_TOTAL = BAR_OFF + 128;
 constexpr int ACC_COLS = 64;                         // [. g_hi | . g_lo]
-static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget exceeded");
-static_assert(XROW % 128 == 0 && (CB * PW) % 128 == 0 && X_BYTES % 128 == 0 && (CB * PG) % 128 == 0, "TMA destinations must be 128-byte aligned");
+
+template <int STRIDE>
+struct Geo {
+    static constexpr int TH = 4, TW = STRIDE == 1 ? 64 : 32;          // g tile: rows x voxels of one depth plane
+    static constexpr int NPAR = STRIDE;                               // w-parity halves of the x tile
+    static constexpr int XR = STRIDE == 1 ? TH + 2 : 2 * TH + 1;      // x tile rows incl. halo
+    static constexpr int XW = TW + 2;                                 // x tile voxels per row (and parity) incl. halo
+    static constexpr uint32_t PW = XW * 16;                           // x: pitch between channel groups: 1056 | 544
+    static constexpr uint32_t XROW = 2 * CB * PW;                     // x: one tile row = [hi cb0..3 | lo cb0..3]
+    static constexpr uint32_t XPAR = XR * XROW;                       // x: one parity half
+    static constexpr uint32_t X_BYTES = NPAR * XPAR;                  // 50688 | 78336
+    static constexpr uint32_t PG = TH * TW * 16;                      // g: pitch between channel groups
+    static constexpr uint32_t G_BYTES = 2 * CB * PG;                  // 32768 | 16384
+    static constexpr uint32_t STAGE_BYTES = X_BYTES + G_BYTES;
+    static constexpr uint32_t BAR_OFF = NSTAGE * STAGE_BYTES;
+    static constexpr uint32_t SMEM_TOTAL = BAR_OFF + 128;
+    static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    static_assert(XROW % 128 == 0 && (CB * PW) % 128 == 0 && X_BYTES % 128 == 0 && (CB * PG) % 128 == 0,
+                  "TMA destinations must be 128-byte aligned");
+};
 
 struct Maps {
     CUtensorMap x_hi, x_lo, g_hi, g_lo;
@@ -71,8 +86,12 @@ __host__ __device__ constexpr uint32_t idesc_mn(int m, int n, uint32_t fmt) {
 
 __device__ __forceinline__ void red_add(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 
-template <bool FP16>
+template <bool FP16, int STRIDE>
 __global__ void __launch_bounds__(128, 1) wgrad_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
+    using G = Geo<STRIDE>;
+    constexpr int TH = G::TH, TW = G::TW, XR = G::XR;
+    constexpr uint32_t PW = G::PW, XROW = G::XROW, X_BYTES = G::X_BYTES, PG = G::PG, STAGE_BYTES = G::STAGE_BYTES,
+                       BAR_OFF = G::BAR_OFF;
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);     // [NSTAGE]
     uint64_t* empty = full + NSTAGE;                                   // [NSTAGE]
@@ -115,10 +134,23 @@ __global__ void __launch_bounds__(128, 1) wgrad_tc_kernel(const __grid_constant_
                 unsigned char* gs = xs + X_BYTES;
                 mbar_expect_tx(&full[slot], STAGE_BYTES);
                 // coordinates are in 8-byte elements along w (2 per voxel); out-of-volume parts are zero-filled
+                if (STRIDE == 1) {
 #pragma unroll 1
-                for (int row = 0; row < XR; ++row) {
-                    tma_load_5d(xs + row * XROW, &maps.x_hi, &full[slot], 2 * (w0 - 1), h0 - 1 + row, d + kd - 1, p.a_cb0, b);
-                    tma_load_5d(xs + row * XROW + CB * PW, &maps.x_lo, &full[slot], 2 * (w0 - 1), h0 - 1 + row, d + kd - 1, p.a_cb0, b);
+                    for (int row = 0; row < XR; ++row) {
+                        tma_load_5d(xs + row * XROW, &maps.x_hi, &full[slot], 2 * (w0 - 1), h0 - 1 + row, d + kd - 1, p.a_cb0, b);
+                        tma_load_5d(xs + row * XROW + CB * PW, &maps.x_lo, &full[slot], 2 * (w0 - 1), h0 - 1 + row, d + kd - 1, p.a_cb0, b);
+                    }
+                } else {
+                    // W-parity-split input: map row index = 2 * (input row) + parity; tile row `row` = input row 2 h0 - 1 + row,
+                    // tile voxel j of either half = half-resolution column w0 - 1 + j
+#pragma unroll 1
+                    for (int pr = 0; pr < 2 * XR; ++pr) {
+                        const int par = pr / XR, row = pr - par * XR;
+                        unsigned char* dst = xs + par * G::XPAR + row * XROW;
+                        const int hrow = 2 * (2 * h0 - 1 + row) + par;
+                        tma_load_5d(dst, &maps.x_hi, &full[slot], 2 * (w0 - 1), hrow, 2 * d + kd - 1, p.a_cb0, b);
+                        tma_load_5d(dst + CB * PW, &maps.x_lo, &full[slot], 2 * (w0 - 1), hrow, 2 * d + kd - 1, p.a_cb0, b);
+                    }
                 }
                 tma_load_5d(gs, &maps.g_hi, &full[slot], 2 * w0, h0, d, p.g_cb0, b);
                 tma_load_5d(gs + CB * PG, &maps.g_lo, &full[slot], 2 * w0, h0, d, p.g_cb0, b);
@@ -149,7 +181,10 @@ __global__ void __launch_bounds__(128, 1) wgrad_tc_kernel(const __grid_constant_
                         const uint32_t accumulate = (acc_flag | (uint32_t)(r | s)) ? 1u : 0u;
 #pragma unroll
                         for (int kw = 0; kw < 3; ++kw) {
-                            const uint32_t a_off = r * XROW + (s * 16 + kw) * 16;
+                            // stride 1: x rows r, r+1, r+2 at voxel offset kw; stride 2: rows 2r, 2r+1, 2r+2 of the even (kw = 1,
+                            // offset 1) or odd (kw = 0 / 2, offset 0 / 1) half
+                            const uint32_t a_off = STRIDE == 1 ? r * XROW + (s * 16 + kw) * 16
+                                                               : (kw == 1 ? 0u : G::XPAR) + 2 * r * XROW + (s * 16 + (kw == 0 ? 0 : 1)) * 16;
                             // x rows r, r+1 (taps kh = 0, 1) -> 128-lane accumulator; x row r+2 (kh = 2) -> 64-row accumulator
                             mma_f16_ss_rt(tmem_base + kw * 2 * ACC_COLS, a_lo0 + (a_off >> 4), a_hiw, b_lo, b_hiw, idesc_pair, accumulate);
                             mma_f16_ss_rt(tmem_base + (kw * 2 + 1) * ACC_COLS, a_lo0 + ((a_off + 2 * XROW) >> 4), a_hiw, b_lo, b_hiw,
@@ -204,13 +239,40 @@ __global__ void __launch_bounds__(128, 1) wgrad_tc_kernel(const __grid_constant_
     }
 }
 
-// map over [B][CBS][D][H][W][8 x 16-bit] seen as 8-byte elements: dims (2W, H, D, CBS, B)
-static int make_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W, int box_w, int box_h) {
-    const cuuint64_t dims[5] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)CBS, (cuuint64_t)B};
-    const cuuint64_t strides[4] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
+// map over [B][CBS][D][H][W][8 x 16-bit] seen as 8-byte elements: dims (2W, H, D, CBS, B).  wsplit: the tensor is
+// W-parity-split ([..][H][2][W/2][8]) and seen as 2H rows of W/2 voxels.
+static int make_map(CUtensorMap* map, const void* base, int B, int CBS, int D, int H, int W, int box_w, int box_h,
+                    bool wsplit = false) {
+    const cuuint64_t rows = wsplit ? 2 * (cuuint64_t)H : (cuuint64_t)H, cols = wsplit ? (cuuint64_t)W / 2 : (cuuint64_t)W;
+    const cuuint64_t dims[5] = {cols * 2, rows, (cuuint64_t)D, (cuuint64_t)CBS, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {cols * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16,
                                    (cuuint64_t)CBS * D * H * W * 16};
     const cuuint32_t box[5] = {(cuuint32_t)box_w * 2, (cuuint32_t)box_h, 1, CB, 1};
     return encode_typed(map, base, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_INT64);
+}
+
+template <bool FP16, int STRIDE>
+static int launch(const Maps& maps, Params& p, int Ca, int Cg, void* stream) {
+    using G = Geo<STRIDE>;
+    p.tiles_h = (int)cdiv(p.H, G::TH);
+    p.tiles_w = (int)cdiv(p.W, G::TW);
+    p.n_items = p.B * p.D * p.tiles_h * p.tiles_w;
+    // three populations (depth taps) of persistent CTAs, one per SM
+    int per_pop = sm_count() / 3;
+    if (per_pop < 1) per_pop = 1;
+    if (per_pop > p.n_items) per_pop = p.n_items;
+    const dim3 grid(per_pop, 3);
+    DMB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<FP16, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM_TOTAL));
+    for (int ia = 0; ia < Ca / 32; ++ia) {
+        for (int ig = 0; ig < Cg / 32; ++ig) {
+            p.a_cb0 = ia * CB; p.g_cb0 = ig * CB;
+            p.ca0 = ia * 32; p.cg0 = ig * 32;
+            wgrad_tc_kernel<FP16, STRIDE><<<grid, 128, G::SMEM_TOTAL, as_stream(stream)>>>(maps, p);
+            const int rc = check_launch("wgrad_tc_kernel");
+            if (rc) return rc;
+        }
+    }
+    return DMB_OK;
 }
 
 }  // namespace wg
@@ -220,40 +282,26 @@ using namespace dmb;
 using namespace dmb::wg;
 
 extern "C" int dmb_b200_conv3d_wgrad_tc(const void* a_hi, const void* a_lo, const void* g_hi, const void* g_lo, float* dw,
-                                        int B, int Ca, int Cg, int D, int H, int W, int fp16, void* stream) {
+                                        int B, int Ca, int Cg, int D, int H, int W, int stride, int fp16, void* stream) {
     DMB_REQUIRE(a_hi && a_lo && g_hi && g_lo && dw, "conv3d_wgrad_tc: null pointer (split hi / lo planes are required)");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_wgrad_tc: non-positive dimension");
+    DMB_REQUIRE(stride == 1 || stride == 2, "conv3d_wgrad_tc: stride %d not supported (1 or 2)", stride);
     DMB_REQUIRE(Ca > 0 && Cg > 0 && Ca % 32 == 0 && Cg % 32 == 0, "conv3d_wgrad_tc: channel counts (%d, %d) must be multiples of 32", Ca, Cg);
     if (!tc::device_ok()) return fail(DMB_ERR_UNSUPPORTED, "conv3d_wgrad_tc: needs an sm_100 device and a TMA-capable driver");
     Maps maps;
     int rc;
-    if ((rc = make_map(&maps.x_hi, a_hi, B, Ca / 8, D, H, W, XW, 1))) return rc;
-    if ((rc = make_map(&maps.x_lo, a_lo, B, Ca / 8, D, H, W, XW, 1))) return rc;
-    if ((rc = make_map(&maps.g_hi, g_hi, B, Cg / 8, D, H, W, TW, TH))) return rc;
-    if ((rc = make_map(&maps.g_lo, g_lo, B, Cg / 8, D, H, W, TW, TH))) return rc;
+    // D, H, W: extents of g (the conv output for a strided conv); `a` has stride times those
+    const int Da = stride * D, Ha = stride * H, Wa = stride * W;
+    const int xw = stride == 1 ? Geo<1>::XW : Geo<2>::XW, tw = stride == 1 ? Geo<1>::TW : Geo<2>::TW;
+    const int th = stride == 1 ? Geo<1>::TH : Geo<2>::TH;
+    if ((rc = make_map(&maps.x_hi, a_hi, B, Ca / 8, Da, Ha, Wa, xw, 1, stride == 2))) return rc;
+    if ((rc = make_map(&maps.x_lo, a_lo, B, Ca / 8, Da, Ha, Wa, xw, 1, stride == 2))) return rc;
+    if ((rc = make_map(&maps.g_hi, g_hi, B, Cg / 8, D, H, W, tw, th))) return rc;
+    if ((rc = make_map(&maps.g_lo, g_lo, B, Cg / 8, D, H, W, tw, th))) return rc;
     Params p;
     p.dw = dw;
     p.B = B; p.D = D; p.H = H; p.W = W;
-    p.tiles_h = (int)cdiv(H, TH);
-    p.tiles_w = (int)cdiv(W, TW);
-    p.n_items = B * D * p.tiles_h * p.tiles_w;
     p.Ca = Ca; p.Cg = Cg;
-    // three populations (depth taps) of persistent CTAs, one per SM
-    int per_pop = sm_count() / 3;
-    if (per_pop < 1) per_pop = 1;
-    if (per_pop > p.n_items) per_pop = p.n_items;
-    const dim3 grid(per_pop, 3);
-    if (fp16) DMB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-    else DMB_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
-    for (int ia = 0; ia < Ca / 32; ++ia) {
-        for (int ig = 0; ig < Cg / 32; ++ig) {
-            p.a_cb0 = ia * CB; p.g_cb0 = ig * CB;
-            p.ca0 = ia * 32; p.cg0 = ig * 32;
-            if (fp16) wgrad_tc_kernel<true><<<grid, 128, SMEM_TOTAL, as_stream(stream)>>>(maps, p);
-            else wgrad_tc_kernel<false><<<grid, 128, SMEM_TOTAL, as_stream(stream)>>>(maps, p);
-            rc = check_launch("wgrad_tc_kernel");
-            if (rc) return rc;
-        }
-    }
-    return DMB_OK;
+    if (stride == 1) return fp16 ? launch<true, 1>(maps, p, Ca, Cg, stream) : launch<false, 1>(maps, p, Ca, Cg, stream);
+    return fp16 ? launch<true, 2>(maps, p, Ca, Cg, stream) : launch<false, 2>(maps, p, Ca, Cg, stream);
 }

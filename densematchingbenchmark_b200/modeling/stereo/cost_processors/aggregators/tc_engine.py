@@ -83,12 +83,13 @@ class Blocked(object):
         return Blocked(hi, lo, B, Cc, dims, fp16)
 
     @staticmethod
-    def from_ncdhw(x, split, fp16=False):
+    def from_ncdhw(x, split, fp16=False, wsplit=False):
+        """wsplit: every row W-parity-split ([even | odd] halves) -- only the stride-2 weight gradient reads that."""
         x = C.f32(x)
         B, Cc, D, H, W = x.shape
         out = Blocked.empty(B, Cc, (D, H, W), split, fp16, x.device)
-        C.call("dmb_b200_ncdhw_to_blocked", C.ptr(x), C.ptr(out.hi), C.ptr(out.lo), B, Cc, D, H, W,
-               1 if fp16 else 0, C.stream(x.device))
+        C.call("dmb_b200_ncdhw_to_blocked_wsplit" if wsplit else "dmb_b200_ncdhw_to_blocked", C.ptr(x), C.ptr(out.hi),
+               C.ptr(out.lo), B, Cc, D, H, W, 1 if fp16 else 0, C.stream(x.device))
         check_finite(out, "ncdhw_to_blocked")
         return out
 
@@ -249,26 +250,27 @@ def conv3d_ncdhw_tc(x, w_packed, bias, stride, transposed, precision, residual=N
     return conv_tc_raw(xb, blob, bias, Cin, Cout, scale, kind, rb, relu).to_ncdhw()
 
 
-def wgrad_tc(a, g, a_blocked=None, g_blocked=None):
-    """Weight gradient of a 3x3x3 / stride 1 / pad 1 convolution on tcgen05 (csrc/wgrad_tc.cu): a = layer input,
-    g = gradient w.r.t. the layer output, float32 NCDHW (or already Blocked bf16 split pairs) -> [27, Ca, Cg] float32.
-    bfloat16 split pairs: gradients can be arbitrarily small, so the fp32 exponent range matters more than the three
-    extra mantissa bits of IEEE half."""
-    ab = a_blocked if a_blocked is not None else Blocked.from_ncdhw(a, True, False)
+def wgrad_tc(a, g, stride=1, a_blocked=None, g_blocked=None):
+    """Weight gradient of a 3x3x3 / pad 1 convolution of stride 1 or 2 on tcgen05 (csrc/wgrad_tc.cu):
+    dw[tap][ca][cg] = sum a[s*v + tap - 1] * g[v].  a, g: float32 NCDHW (or already Blocked bf16 split pairs; with
+    stride 2 `a` W-parity-split) -> [27, Ca, Cg] float32.  bfloat16 split pairs: gradients can be arbitrarily small,
+    so the fp32 exponent range matters more than the three extra mantissa bits of IEEE half."""
+    ab = a_blocked if a_blocked is not None else Blocked.from_ncdhw(a, True, False, wsplit=(stride == 2))
     gb = g_blocked if g_blocked is not None else Blocked.from_ncdhw(g, True, False)
-    if ab.dims != gb.dims or ab.B != gb.B or ab.fp16 or gb.fp16 or not (ab.split and gb.split):
-        raise ValueError("wgrad_tc: input and output gradient must be bf16 split pairs of one geometry")
-    D, H, W = ab.dims
+    if ab.dims != tuple(stride * n for n in gb.dims) or ab.B != gb.B or ab.fp16 or gb.fp16 or not (ab.split and gb.split):
+        raise ValueError("wgrad_tc: a and g must be bf16 split pairs with dims(a) == stride * dims(g)")
+    D, H, W = gb.dims
     dw = torch.zeros(27, ab.C, gb.C, device=ab.hi.device, dtype=torch.float32)
     C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), ab.B, ab.C, gb.C,
-           D, H, W, 0, C.stream(dw.device))
+           D, H, W, stride, 0, C.stream(dw.device))
     return dw
 
 
-def wgrad_tc_eligible(a, g, ksize, stride, pad, transposed):
-    return (not transposed and stride == 1 and pad == 1 and tuple(ksize) == (3, 3, 3) and a.is_cuda
-            and a.shape[1] % 32 == 0 and g.shape[1] % 32 == 0 and tuple(a.shape[2:]) == tuple(g.shape[2:])
-            and tc_available())
+def wgrad_tc_eligible(a, g, ksize, stride, pad):
+    """a: the tensor the taps slide over (the conv input; for a transposed conv the output gradient), g the other one."""
+    return (stride in (1, 2) and pad == 1 and tuple(ksize) == (3, 3, 3) and a.is_cuda
+            and a.shape[1] % 32 == 0 and g.shape[1] % 32 == 0
+            and tuple(a.shape[2:]) == tuple(stride * n for n in g.shape[2:]) and tc_available())
 
 
 def conv3d_tc_eligible(x, Cin, Cout, ksize, stride, pad, transposed, opad, out_dims=None):

@@ -72,10 +72,15 @@ TRAIN_TC_WGRAD = os.environ.get("DMB_B200_TRAIN_TC_WGRAD", "1") != "0"
 
 
 def _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
-    if not (TRAIN_TC and TRAIN_TC_WGRAD):
+    if not (TRAIN_TC and TRAIN_TC_WGRAD) or (transposed and stride == 1):
         return False
     from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
-    return T.wgrad_tc_eligible(x, dz, ksize, stride, pad, transposed)
+    a, g = (dz, x) if transposed else (x, dz)
+    if g.shape[1] < 32 and stride == 1:
+        # the 32 -> 1 classifier heads (aggregators/PSMNet.py:41-52): g is padded to one 32-channel block with zeros --
+        # 31/32 of the MMA columns idle, still ~25x faster than the SIMT kernel's 3.4 ms (profiles/README.md)
+        return T.wgrad_tc_eligible(a, g.expand(-1, 32, -1, -1, -1), ksize, stride, pad)
+    return T.wgrad_tc_eligible(a, g, ksize, stride, pad)
 
 
 def _wgrad(x, dz, transposed, ksize, stride, pad, weight_shape, dz_blocked=None):
@@ -86,7 +91,14 @@ def _wgrad(x, dz, transposed, ksize, stride, pad, weight_shape, dz_blocked=None)
     Cg = g.shape[1]
     if _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
         from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
-        dw = T.wgrad_tc(a, g, g_blocked=dz_blocked)
+        if Cg < 32:                                    # zero-padded to one channel block (see _wgrad_on_tc)
+            gp = torch.zeros((B, 32) + tuple(g.shape[2:]), device=g.device, dtype=torch.float32)
+            gp[:, :Cg] = g
+            dw = T.wgrad_tc(a, gp, stride)[:, :, :Cg]
+        else:
+            # dz_blocked (shared with the input-gradient kernel) is g for a plain conv; for the transposed conv dz is
+            # `a` and needs the W-parity-split layout instead
+            dw = T.wgrad_tc(a, g, stride, g_blocked=None if transposed else dz_blocked)
         return dw.permute(2, 1, 0).reshape(weight_shape).contiguous()
     dw = torch.zeros(27, Ca, Cg, device=x.device, dtype=torch.float32)
     C.call("dmb_b200_conv3d_wgrad", C.ptr(a), C.ptr(g), C.ptr(dw), B, Ca, Cg, C.int_array(list(a.shape[2:])),
@@ -186,7 +198,7 @@ class ConvUnitFn(torch.autograd.Function):
                        C.stream(dev))
                 dbias = sums[:Co].float()
         dz_blocked = None
-        if need_x and need_w and _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
+        if need_x and need_w and dz.shape[1] % 32 == 0 and not transposed and _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
             # one bf16 split-pair conversion of dz shared by the input-gradient and the weight-gradient kernels
             from ..modeling.stereo.cost_processors.aggregators import tc_engine as T
             if T.PRECISIONS[TRAIN_TC_BWD] == (True, False):

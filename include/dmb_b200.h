@@ -231,6 +231,9 @@ int dmb_b200_conv3d_tc_available(void);
 
 /* layout helpers for the trunk boundary: [B,C,D,H,W] float32 <-> [B][C/8][D][H][W][8] 16-bit (hi[,lo]) */
 int dmb_b200_ncdhw_to_blocked(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, int fp16, void* stream);
+/* the same conversion with every row W-PARITY-SPLIT: [B][C/8][D][H][even | odd][W/2][8] -- the operand layout of the
+   stride-2 tcgen05 weight gradient (dmb_b200_conv3d_wgrad_tc with stride 2); W even */
+int dmb_b200_ncdhw_to_blocked_wsplit(const float* x, void* y_hi, void* y_lo, int B, int C, int D, int H, int W, int fp16, void* stream);
 int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, float* y, int B, int C, int D, int H, int W, int fp16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -272,14 +275,16 @@ int dmb_b200_upsample_deconv_wgrad(const float* cost_low, const float* dcost, fl
 /* backward of the trilinear (align_corners=True) cost upsampling: dcost [B,D,H,W] -> dcost_low [B,Dl,Hl,Wl] */
 int dmb_b200_upsample_trilinear_backward(const float* dcost, float* dcost_low, int B, int Dl, int Hl, int Wl,
                                          int D, int H, int W, void* stream);
-/* Weight gradient of a 3x3x3 / stride 1 / pad 1 convolution on tcgen05 (csrc/wgrad_tc.cu; replaces cuDNN's wgrad
-   behind nn.Conv3d in the backward of layers/basic_layers.py:68-177):
-       dw[tap][ca][cg] += sum_{b,d,h,w} a[b][ca][d+kd-1][h+kh-1][w+kw-1] * g[b][cg][d][h][w]
-   a (layer input) and g (gradient w.r.t. the layer output) are blocked 16-bit split pairs [B][C/8][D][H][W][8]
-   (hi and lo planes, dmb_b200_ncdhw_to_blocked); fp16 = 0: bfloat16 elements, 1: IEEE half.  dw [27][Ca][Cg] fp32 is
-   ACCUMULATED into (zero it first); Ca, Cg multiples of 32. */
+/* Weight gradient of a 3x3x3 / pad 1 convolution of stride 1 or 2 on tcgen05 (csrc/wgrad_tc.cu; replaces cuDNN's
+   wgrad behind nn.Conv3d / nn.ConvTranspose3d in the backward of layers/basic_layers.py:68-216):
+       dw[tap][ca][cg] += sum_{b,d,h,w} a[b][ca][s*d+kd-1][s*h+kh-1][s*w+kw-1] * g[b][cg][d][h][w]        (s = stride)
+   g has extents D, H, W; a has stride times those.  For a strided Conv3d a = layer input, g = gradient w.r.t. the layer
+   output; for the stride-2 ConvTranspose3d the roles swap (a = output gradient, g = layer input).  Both are blocked
+   16-bit split pairs [B][C/8][..][8] (hi and lo planes, dmb_b200_ncdhw_to_blocked); with stride 2, `a` must be the
+   W-parity-split variant (dmb_b200_ncdhw_to_blocked_wsplit).  fp16 = 0: bfloat16 elements, 1: IEEE half.
+   dw [27][Ca][Cg] fp32 is ACCUMULATED into (zero it first); Ca, Cg multiples of 32. */
 int dmb_b200_conv3d_wgrad_tc(const void* a_hi, const void* a_lo, const void* g_hi, const void* g_lo, float* dw, int B,
-                             int Ca, int Cg, int D, int H, int W, int fp16, void* stream);
+                             int Ca, int Cg, int D, int H, int W, int stride, int fp16, void* stream);
 /* backward of dmb_b200_soft_argmin (disp_values / ramp variants): dcost [B,D,H,W] fully written */
 int dmb_b200_soft_argmin_backward(const float* cost, const float* grad_disp, float* dcost, int B, int D, int H, int W,
                                   float alpha, int normalize, float start_disp, float disp_step,

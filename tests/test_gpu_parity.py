@@ -657,6 +657,10 @@ def test_config3_gwc_full_size_vs_oracle(P):
     # dilation / negative start at full size (disparities -8, -4, ..., 36)
     vol3 = P.GWC_FUNCS["default"](lg, rg, max_disp=48, start_disp=-8, dilation=4, num_groups=40)
     torch.testing.assert_close(vol3.cpu(), O.gwc_volume(l, r, 40, 48, -8, 4), atol=2e-6, rtol=1e-5)
+    # unit-step lists starting at a multiple of 4 (aligned 16-byte window loads) and not (scalar window loads)
+    for start, md in ((-8, 24), (-6, 21), (3, 10)):
+        got = P.GWC_FUNCS["default"](lg, rg, max_disp=md, start_disp=start, dilation=1, num_groups=40)
+        torch.testing.assert_close(got.cpu(), O.gwc_volume(l, r, 40, md, start, 1), atol=2e-6, rtol=1e-5)
 
 
 def test_config4_ganet_full_size_vs_oracle(P):

@@ -157,19 +157,54 @@ def test_conv_wgrad_tcgen05(P, case):
     gy = torch.randn(y.shape, generator=g) * 0.01              # small gradients: the reason for bfloat16's exponent range
     y.backward(gy)
     xg, gg = x.to(DEV), gy.to(DEV)
-    assert T.wgrad_tc_eligible(xg, gg, (3, 3, 3), 1, 1, False)
+    assert T.wgrad_tc_eligible(xg, gg, (3, 3, 3), 1, 1)
     dw = T.wgrad_tc(xg, gg)
     got = dw.permute(2, 1, 0).reshape(Cg, Ca, 3, 3, 3)
     close(got, w.grad, 2e-4, "dw tcgen05")
     # accumulation semantics of the raw entry point: a second call adds onto the first
     from densematchingbenchmark_b200 import _cabi as C
     ab, gb = T.Blocked.from_ncdhw(xg, True, False), T.Blocked.from_ncdhw(gg, True, False)
-    C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), B, Ca, Cg, D, H, W, 0,
+    C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), B, Ca, Cg, D, H, W, 1, 0,
            C.stream(torch.device(DEV)))
     close(dw.permute(2, 1, 0).reshape(Cg, Ca, 3, 3, 3), 2.0 * w.grad, 2e-4, "dw accumulated twice")
     with pytest.raises(C.DmbB200Error):
-        C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), B, Ca, 48, D, H, W, 0,
+        C.call("dmb_b200_conv3d_wgrad_tc", C.ptr(ab.hi), C.ptr(ab.lo), C.ptr(gb.hi), C.ptr(gb.lo), C.ptr(dw), B, Ca, 48, D, H, W, 1, 0,
                C.stream(torch.device(DEV)))
+
+
+WGRAD_TC_S2_CASES = [
+    # transposed?, B, C(high-res tensor), C(low-res tensor), low-res D, H, W
+    (False, 1, 32, 64, 2, 4, 32), (False, 2, 64, 64, 3, 5, 18), (True, 1, 64, 32, 2, 6, 40), (True, 2, 64, 64, 1, 3, 7),
+    (False, 1, 32, 64, 6, 8, 64),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_TC_S2_CASES, ids=["x".join(map(str, c)) for c in WGRAD_TC_S2_CASES])
+def test_conv_wgrad_tcgen05_stride2(P, case):
+    """Stride-2 weight gradients on tcgen05 (W-parity-split operand): Conv3d(k3, s2, p1) -- Hourglass conv1 / conv3 --
+    and ConvTranspose3d(k3, s2, p1, op1) -- conv5 / conv6 -- through the same `_wgrad` the autograd Function calls,
+    against torch autograd on the CPU."""
+    from densematchingbenchmark_b200.ops import autograd as A
+    from densematchingbenchmark_b200.modeling.stereo.cost_processors.aggregators import tc_engine as T
+    if not T.tc_available():
+        pytest.skip("tcgen05 path unavailable on this device")
+    transposed, B, Chi, Clo, D, H, W = case
+    g = torch.Generator().manual_seed(B * 5 + W)
+    if transposed:            # input low-res (Clo channels), output high-res (Chi channels)
+        conv = torch.nn.ConvTranspose3d(Clo, Chi, 3, 2, 1, output_padding=1, bias=False)
+        x = torch.randn(B, Clo, D, H, W, generator=g)
+    else:                     # input high-res (Chi channels), output low-res (Clo channels)
+        conv = torch.nn.Conv3d(Chi, Clo, 3, 2, 1, bias=False)
+        x = torch.randn(B, Chi, 2 * D, 2 * H, 2 * W, generator=g)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) * 0.05)
+    y = conv(x)
+    gy = torch.randn(y.shape, generator=g) * 0.01
+    y.backward(gy)
+    xg, gg = x.to(DEV), gy.to(DEV)
+    assert A._wgrad_on_tc(xg, gg, transposed, (3, 3, 3), 2, 1)
+    got = A._wgrad(xg, gg, transposed, (3, 3, 3), 2, 1, conv.weight.shape)
+    close(got, conv.weight.grad, 2e-4, "dw stride 2 tcgen05")
 
 
 def test_conv_wgrad_tcgen05_long_accumulation(P):
