@@ -434,6 +434,22 @@ __global__ void __launch_bounds__(128) sga_horizontal_kernel(const float* __rest
 //   horizontal (dir 0/1): lanes run along y, a lane moves 16 bytes (4 scan steps) per disparity and chunk; the
 //                         second half of each 32-byte sector is consumed one chunk later out of L1.
 // ---------------------------------------------------------------------------------------
+// max over the G adjacent lanes of a scan line's lane group as ONE redux.sync instead of log2(G) dependent
+// shuffle + max rounds (the max over d sits on the critical path of every scan step): floats are mapped to integers
+// of the same order (flip the magnitude bits of negative values), reduced with redux.sync.max.s32 over the group's
+// own lane mask, and mapped back.  -inf / finite values only (NaN costs are not ordered by the reference either).
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+    if (G == 1) return v;
+    int i = __float_as_int(v);
+    i ^= (i >> 31) & 0x7fffffff;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned mask = (G >= 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (lane & ~(unsigned)(G - 1)));
+    i = __reduce_max_sync(mask, i);
+    i ^= (i >> 31) & 0x7fffffff;
+    return __int_as_float(i);
+}
+
 template <int DPL, int G>
 __device__ __forceinline__ void sga_lane_step(float (&A)[DPL], const float (&xv)[DPL], float (&w)[5], bool started,
                                               int q, int dbase, int D, float (&cur)[DPL]) {
@@ -451,8 +467,7 @@ __device__ __forceinline__ void sga_lane_step(float (&A)[DPL], const float (&xv)
 #pragma unroll
     for (int j = 0; j < DPL; ++j)
         if (dbase + j < D) mx = fmaxf(mx, A[j]);
-#pragma unroll
-    for (int o = 1; o < G; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mx = group_max<G>(mx);
 #pragma unroll
     for (int j = 0; j < DPL; ++j) {
         const int d = dbase + j;
@@ -592,6 +607,160 @@ __global__ void __launch_bounds__(128) sga_h_lanes_kernel(const float* __restric
             if (rowok && dbase + j < D)
                 *reinterpret_cast<float4*>(ob + (size_t)j * plane + t0) = make_float4(oc[j][0], oc[j][1], oc[j][2], oc[j][3]);
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// SGA, BIDIRECTIONAL kernels: both scans of one orientation in one launch.  The first half of a CTA's warps runs the
+// forward scan (left->right / top->bottom) of the CTA's scan lines, the second half the backward scan of the SAME
+// lines, concurrently.  Phase 1: each direction covers its half of the line; when the launch is the first one to
+// write `out` (first = 1) the values are stored plainly, otherwise combined with max.  One __syncthreads.  Phase 2:
+// each direction continues through the other half, where `out` now holds the other direction's phase-1 result (and
+// whatever was there before), and max-combines.  Two launches (vertical pair, horizontal pair) instead of four,
+// each with half the sequential length in flight per line -- and the host runs them over channel groups small
+// enough for x and out to stay in L2 between the two launches (dmb_b200_sga below).
+// ---------------------------------------------------------------------------------------
+template <int DPL, int G>
+__global__ void __launch_bounds__(256) sga_v_bi_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                       float* __restrict__ out, int C, int D, int H, int W, int first) {
+    constexpr int CPB = 128 / G;                              // columns per CTA (each direction: 128 threads)
+    const int back = threadIdx.x >> 7;                        // 0: top->bottom (dir 2), 1: bottom->top (dir 3)
+    const int t = threadIdx.x & 127;
+    const int q = t % G;
+    const int col = blockIdx.x * CPB + t / G;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const bool colok = col < W;
+    const int dbase = q * DPL;
+    const size_t plane = (size_t)H * W;
+    const size_t base = ((size_t)(b * C + c) * D + dbase) * plane + (colok ? col : 0);
+    const float* xb = x + base;
+    float* ob = out + base;
+    const float* gb = guid + (((size_t)(b * 4 + 2 + back) * 5) * C + c) * plane + (colok ? col : 0);
+    const size_t gk = (size_t)C * plane;
+    float A[DPL], xn[DPL], on[DPL], wn[5];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) A[j] = 0.f;
+    auto fetch = [&](int step, bool want_out) {
+        const size_t row = (size_t)(back ? H - 1 - step : step) * W;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) wn[k] = colok ? __ldg(gb + k * gk + row) : 0.f;
+#pragma unroll
+        for (int j = 0; j < DPL; ++j) {
+            const bool ok = colok && dbase + j < D;
+            xn[j] = ok ? __ldcs(xb + (size_t)j * plane + row) : 0.f;
+            on[j] = (ok && want_out) ? ob[(size_t)j * plane + row] : -INFINITY;
+        }
+    };
+    // forward covers rows [0, h1) in phase 1, backward rows [H-1 .. h1] (steps [0, H - h1))
+    const int h1 = H / 2;
+    const int n1 = back ? H - h1 : h1;
+    auto run = [&](int s0, int s1, bool want_out) {
+        if (s0 < s1) fetch(s0, want_out);
+        for (int step = s0; step < s1; ++step) {
+            const size_t row = (size_t)(back ? H - 1 - step : step) * W;
+            float xv[DPL], ov[DPL], w[5], cur[DPL];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) w[k] = wn[k];
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                xv[j] = xn[j];
+                ov[j] = on[j];
+            }
+            if (step + 1 < s1) fetch(step + 1, want_out);
+            sga_lane_step<DPL, G>(A, xv, w, step > 0, q, dbase, D, cur);
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                if (colok && dbase + j < D) ob[(size_t)j * plane + row] = fmaxf(ov[j], cur[j]);   // ov = -inf: plain store
+                A[j] = cur[j];
+            }
+        }
+    };
+    run(0, n1, !first);
+    __syncthreads();                                          // phase-1 stores of both directions visible CTA-wide
+    run(n1, H, true);
+}
+
+template <int DPL, int G>
+__global__ void __launch_bounds__(256) sga_h_bi_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                       float* __restrict__ out, int C, int D, int H, int W, int first) {
+    constexpr int RPB = 128 / G;                              // rows per CTA (each direction: 128 threads)
+    const int back = threadIdx.x >> 7;                        // 0: left->right (dir 0), 1: right->left (dir 1)
+    const int t = threadIdx.x & 127;
+    const int q = t % G;
+    const int rowi = blockIdx.x * RPB + t / G;
+    const int c = blockIdx.y, b = blockIdx.z;
+    const bool rowok = rowi < H;
+    const int dbase = q * DPL;
+    const size_t plane = (size_t)H * W;
+    const size_t base = ((size_t)(b * C + c) * D + dbase) * plane + (size_t)(rowok ? rowi : 0) * W;
+    const float* xb = x + base;
+    float* ob = out + base;
+    const float* gb = guid + (((size_t)(b * 4 + back) * 5) * C + c) * plane + (size_t)(rowok ? rowi : 0) * W;
+    const size_t gk = (size_t)C * plane;
+    const int nchunks = W / 4;                                // W % 4 == 0 (checked by the host)
+    float A[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; ++j) A[j] = 0.f;
+    float4 xn[DPL], wn[5];
+    auto fetch = [&](int i) {                                 // i = scan-order chunk index
+        const int t0 = 4 * (back ? nchunks - 1 - i : i);
+#pragma unroll
+        for (int k = 0; k < 5; ++k)
+            wn[k] = rowok ? __ldg(reinterpret_cast<const float4*>(gb + k * gk + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < DPL; ++j)
+            xn[j] = (rowok && dbase + j < D) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * plane + t0))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    const int c1 = nchunks / 2;
+    const int n1 = back ? nchunks - c1 : c1;                  // chunks of phase 1 for this direction
+    bool started = false;
+    auto run = [&](int i0, int i1, bool want_out) {
+        if (i0 < i1) fetch(i0);
+        for (int i = i0; i < i1; ++i) {
+            const int t0 = 4 * (back ? nchunks - 1 - i : i);
+            float xc[DPL][4], oc[DPL][4], wc[5][4];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                wc[k][0] = wn[k].x; wc[k][1] = wn[k].y; wc[k][2] = wn[k].z; wc[k][3] = wn[k].w;
+            }
+#pragma unroll
+            for (int j = 0; j < DPL; ++j) {
+                xc[j][0] = xn[j].x; xc[j][1] = xn[j].y; xc[j][2] = xn[j].z; xc[j][3] = xn[j].w;
+                float4 o = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                if (want_out && rowok && dbase + j < D) o = *reinterpret_cast<const float4*>(ob + (size_t)j * plane + t0);
+                oc[j][0] = o.x; oc[j][1] = o.y; oc[j][2] = o.z; oc[j][3] = o.w;
+            }
+            if (i + 1 < i1) fetch(i + 1);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                float xv[DPL], w[5], cur[DPL];
+                float xf[DPL], xr[DPL];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) w[k] = back ? wc[k][3 - s] : wc[k][s];
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) {
+                    xf[j] = xc[j][s];
+                    xr[j] = xc[j][3 - s];
+                    xv[j] = back ? xr[j] : xf[j];
+                }
+                sga_lane_step<DPL, G>(A, xv, w, started, q, dbase, D, cur);
+                started = true;
+#pragma unroll
+                for (int j = 0; j < DPL; ++j) {
+                    if (back) oc[j][3 - s] = fmaxf(oc[j][3 - s], cur[j]);      // -inf: plain store
+                    else oc[j][s] = fmaxf(oc[j][s], cur[j]);
+                    A[j] = cur[j];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < DPL; ++j)
+                if (rowok && dbase + j < D)
+                    *reinterpret_cast<float4*>(ob + (size_t)j * plane + t0) = make_float4(oc[j][0], oc[j][1], oc[j][2], oc[j][3]);
+        }
+    };
+    run(0, n1, !first);
+    __syncthreads();                                          // phase-1 stores of both directions visible CTA-wide
+    run(n1, nchunks, true);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -266,10 +266,11 @@ def wgrad_tc(a, g, stride=1, a_blocked=None, g_blocked=None):
     return dw
 
 
-def wgrad_tc_eligible(a, g, ksize, stride, pad):
-    """a: the tensor the taps slide over (the conv input; for a transposed conv the output gradient), g the other one."""
+def wgrad_tc_eligible(a, g, ksize, stride, pad, pad_g=False):
+    """a: the tensor the taps slide over (the conv input; for a transposed conv the output gradient), g the other one.
+    pad_g: g will be zero-padded to a multiple of 32 channels by the caller."""
     return (stride in (1, 2) and pad == 1 and tuple(ksize) == (3, 3, 3) and a.is_cuda
-            and a.shape[1] % 32 == 0 and g.shape[1] % 32 == 0
+            and a.shape[1] % 32 == 0 and (pad_g or g.shape[1] % 32 == 0)
             and tuple(a.shape[2:]) == tuple(stride * n for n in g.shape[2:]) and tc_available())
 
 

@@ -79,7 +79,7 @@ def _wgrad_on_tc(x, dz, transposed, ksize, stride, pad):
     if g.shape[1] < 32 and stride == 1:
         # the 32 -> 1 classifier heads (aggregators/PSMNet.py:41-52): g is padded to one 32-channel block with zeros --
         # 31/32 of the MMA columns idle, still ~25x faster than the SIMT kernel's 3.4 ms (profiles/README.md)
-        return T.wgrad_tc_eligible(a, g.expand(-1, 32, -1, -1, -1), ksize, stride, pad)
+        return T.wgrad_tc_eligible(a, g, ksize, stride, pad, pad_g=True)
     return T.wgrad_tc_eligible(a, g, ksize, stride, pad)
 
 
