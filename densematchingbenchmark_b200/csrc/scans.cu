@@ -679,12 +679,14 @@ __global__ void __launch_bounds__(256) sga_v_bi_kernel(const float* __restrict__
     run(n1, H, true);
 }
 
-template <int DPL, int G>
-__global__ void __launch_bounds__(256) sga_h_bi_kernel(const float* __restrict__ x, const float* __restrict__ guid,
-                                                       float* __restrict__ out, int C, int D, int H, int W, int first) {
-    constexpr int RPB = 128 / G;                              // rows per CTA (each direction: 128 threads)
-    const int back = threadIdx.x >> 7;                        // 0: left->right (dir 0), 1: right->left (dir 1)
-    const int t = threadIdx.x & 127;
+// TPD threads per direction (a multiple of 32): few rows per CTA spread a channel group's rows over many SMs -- the
+// horizontal pair works out of L2 and a handful of SMs could not pull the group's slices fast enough
+template <int DPL, int G, int TPD>
+__global__ void __launch_bounds__(2 * TPD) sga_h_bi_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                           float* __restrict__ out, int C, int D, int H, int W, int first) {
+    constexpr int RPB = TPD / G;                              // rows per CTA
+    const int back = threadIdx.x / TPD;                       // 0: left->right (dir 0), 1: right->left (dir 1)
+    const int t = threadIdx.x % TPD;
     const int q = t % G;
     const int rowi = blockIdx.x * RPB + t / G;
     const int c = blockIdx.y, b = blockIdx.z;
@@ -876,6 +878,103 @@ __global__ void __launch_bounds__(256, 1) lga_r2_tiled_kernel(const float* __res
     }
 }
 
+// LGA, radius 2, accumulator-rotating variant (the production kernel).  Instead of holding the 25-pixel neighbourhood
+// of three depth planes in registers (75 + 75 weights = 204 registers, one 8-warp CTA per SM, a barrier per depth step),
+// every staged value x(q, d') is used the moment it is read from shared memory for its THREE consumers
+//     out(d') += w0(q) x,   out(d'+1) += w1(q) x,   out(d'-1) += w2(q) x
+// so a thread keeps the 75 weights and three (x2 for instruction-level parallelism) running sums: ~100 registers, two
+// CTAs per SM.  NP depth planes of the tile + halo are staged per barrier pair with cp.async (zero-filled outside the
+// volume), double buffered.  25 conflict-free shared loads + 75 FMAs per output value: FMA-issue bound.
+template <int NP>
+__global__ void __launch_bounds__(256, 2) lga_r2_rot_kernel(const float* __restrict__ x, const float* __restrict__ guid,
+                                                            float* __restrict__ out, int D, int H, int W) {
+    constexpr int TX = 32, TY = 8, PW = TX + 4, PH = TY + 4, NE = PH * PW;   // 432 tile elements per plane
+    constexpr int NS = (NP * NE + 255) / 256;                                 // staged elements per thread and stage
+    __shared__ __align__(16) float tile[2][NP * NE];
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int px = x0 + tx, py = y0 + ty;
+    const int b = blockIdx.z;
+    const bool inside = px < W && py < H;
+    const size_t plane = (size_t)H * W;
+    float w[75];
+    {
+        const float* gb = guid + (size_t)b * 75 * plane + (size_t)(inside ? py : 0) * W + (inside ? px : 0);
+        float nrm = 0.f;
+#pragma unroll
+        for (int i = 0; i < 75; ++i) {
+            w[i] = __ldg(gb + (size_t)i * plane);
+            nrm += fabsf(w[i]);
+        }
+        nrm = fmaxf(nrm, 1e-12f);
+#pragma unroll
+        for (int i = 0; i < 75; ++i) w[i] = w[i] / nrm;
+    }
+    const float* xb = x + (size_t)b * D * plane;
+    float* ob = out + (size_t)b * D * plane + (size_t)py * W + px;
+    // loop-invariant staging descriptors: element e = tid + 256 k of a stage = (plane pl, tile position)
+    int spl[NS], sgo[NS];                          // plane inside the stage (-1: no element), in-plane global offset (-1: outside)
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const int e = tid + k * 256;
+        const int pl = e / NE, idx = e - pl * NE;
+        const int r = idx / PW, c = idx - r * PW;
+        const int yy = y0 + r - 2, xx = x0 + c - 2;
+        spl[k] = e < NP * NE ? pl : -1;
+        sgo[k] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? yy * W + xx : -1;
+    }
+    auto issue = [&](int st) {                     // planes st*NP .. st*NP+NP-1 -> buffer st & 1 (zero-filled outside)
+        const int d0 = st * NP;
+        float* dst = tile[st & 1];
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            if (spl[k] < 0) continue;
+            const int d = d0 + spl[k];
+            const bool ok = d < D && sgo[k] >= 0;
+            const float* src = ok ? xb + (size_t)d * plane + sgo[k] : xb;
+            const uint32_t sz = ok ? 4u : 0u;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst + tid + k * 256)), "l"(src), "r"(sz) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nst = (D + 1 + NP - 1) / NP;         // planes 0 .. D (plane D is all zeros: it completes out(D-1))
+    issue(0);
+    issue(1);                                      // (an all-zero stage when nst == 1: harmless)
+    float pa = 0.f, pb = 0.f, ca = 0.f, cb = 0.f, na = 0.f, nb = 0.f;   // sums for out(d-1), out(d), out(d+1)
+    for (int st = 0; st < nst; ++st) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const float* tb0 = &tile[st & 1][ty * PW + tx];
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+            const float* tb = tb0 + pl * NE;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int i = ky * 5 + kx;
+                    const float v = tb[ky * PW + kx];
+                    if (i & 1) {
+                        cb = fmaf(w[i], v, cb);
+                        nb = fmaf(w[25 + i], v, nb);
+                        pb = fmaf(w[50 + i], v, pb);
+                    } else {
+                        ca = fmaf(w[i], v, ca);
+                        na = fmaf(w[25 + i], v, na);
+                        pa = fmaf(w[50 + i], v, pa);
+                    }
+                }
+            const int d = st * NP + pl;            // the plane just consumed: out(d-1) is complete
+            if (inside && d >= 1 && d <= D) st_cs_f(ob + (size_t)(d - 1) * plane, pa + pb);
+            pa = ca; pb = cb; ca = na; cb = nb; na = 0.f; nb = 0.f;
+        }
+        __syncthreads();                           // everybody is done with buffer st & 1
+        issue(st + 2);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 // any radius: weights re-read per use (slow path, kept for generality)
 __global__ void __launch_bounds__(256) lga_generic_kernel(const float* __restrict__ x, const float* __restrict__ guid,
                                                           float* __restrict__ out, int D, int H, int W, int radius) {
@@ -976,6 +1075,46 @@ extern "C" int dmb_b200_sga(const float* x, const float* guidance, float* out, i
     }
     const bool aligned16 = (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(guidance) |
                             reinterpret_cast<uintptr_t>(out)) % 16 == 0;
+    static int bi_mode = -1;                       // DMB_B200_SGA_BIDIR=0: the four single-direction launches (A/B)
+    if (bi_mode < 0) {
+        const char* e = getenv("DMB_B200_SGA_BIDIR");
+        bi_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    if (lanes_mode && bi_mode && D <= 64 && W % 4 == 0 && W >= 8 && H >= 2 && aligned16) {
+        // Two bidirectional launches (vertical pair first: its x reads are the coalesced ones, so x comes from HBM
+        // once, in full lines; then the horizontal pair) per CHANNEL GROUP, groups sized so that the group's x and
+        // out slices (2 * GC * D*H*W*4 bytes) stay in the 126 MB L2 between the two launches: the horizontal pair
+        // then reads x and read-modify-writes out in L2, and HBM sees x once, the guidance once and out once.
+        const size_t slice = (size_t)D * H * W * 4;
+        int GC = (int)((size_t)88 * 1024 * 1024 / (2 * slice));
+        if (GC < 1) GC = 1;
+        if (GC > C) GC = C;
+        const size_t plane = (size_t)H * W;
+        for (int b = 0; b < B; ++b) {
+            for (int c0 = 0; c0 < C; c0 += GC) {
+                const int gc = (C - c0 < GC) ? C - c0 : GC;
+                // channel c0 of batch b: x / out advance by whole channel slices; the guidance pointer advances by c0
+                // planes inside every (direction, tap) block, its per-tap stride stays C planes
+                const float* xg = x + ((size_t)b * C + c0) * D * plane;
+                float* og = out + ((size_t)b * C + c0) * D * plane;
+                const float* gg = guidance + (size_t)b * 20 * C * plane + (size_t)c0 * plane;
+#define DMB_SGA_BI(DPLV, GV, DPLH, GH)                                                                                        \
+    do {                                                                                                                     \
+        sga_v_bi_kernel<DPLV, GV><<<dim3((unsigned)cdiv(W, 128 / GV), gc, 1), 256, 0, s>>>(xg, gg, og, C, D, H, W, 1);        \
+        sga_h_bi_kernel<DPLH, GH, 32><<<dim3((unsigned)cdiv(H, 32 / GH), gc, 1), 64, 0, s>>>(xg, gg, og, C, D, H, W, 0);      \
+    } while (0)
+                // vertical: 8 lanes per column (16 columns = 64-byte row segments per CTA and direction);
+                // horizontal: 8 lanes per row, 4 rows per CTA (one warp per direction)
+                if (D <= 16) DMB_SGA_BI(2, 8, 2, 8);
+                else if (D <= 32) DMB_SGA_BI(4, 8, 4, 8);
+                else DMB_SGA_BI(8, 8, 8, 8);
+#undef DMB_SGA_BI
+                int rc = check_launch("sga_bi_kernels");
+                if (rc) return rc;
+            }
+        }
+        return DMB_OK;
+    }
     for (int dir = 0; dir < 4; ++dir) {
         const int first = dir == 0 ? 1 : 0;
         if (lanes_mode && dir < 2 && D <= 64 && W % 4 == 0 && aligned16) {
@@ -1064,6 +1203,15 @@ extern "C" int dmb_b200_lga(const float* x, const float* guidance, float* out, i
     if (radius == 2) {
         dim3 grid((unsigned)cdiv(W, 32), (unsigned)cdiv(H, 8), B);
         DMB_REQUIRE(grid.y <= 65535, "lga: image too tall");
+        static int rot_mode = -1;                  // DMB_B200_LGA_ROT=0: the register-plane kernel (A/B)
+        if (rot_mode < 0) {
+            const char* e = getenv("DMB_B200_LGA_ROT");
+            rot_mode = (e && e[0] == '0') ? 0 : 1;
+        }
+        if (rot_mode) {
+            lga_r2_rot_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(x, guidance, out, D, H, W);
+            return check_launch("lga_r2_rot_kernel");
+        }
         lga_r2_tiled_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, guidance, out, D, H, W);
         return check_launch("lga_r2_tiled_kernel");
     }
