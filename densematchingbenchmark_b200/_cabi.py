@@ -68,6 +68,7 @@ OTHER = {
     "dmb_b200_launch_count": ([], c_int64),
     "dmb_b200_conv3d_tc_weight_bytes": ([_I, _I, _I, _I], c_int64),
     "dmb_b200_conv3d_tc_available": ([], c_int),
+    "dmb_b200_conv3d_tc_head_floats": ([_I, _I, _I, _I], c_int64),
 }
 
 # debug-only entry points that an older build handed in through DMB_B200_LIB may lack

@@ -176,7 +176,8 @@ struct Params {
     // convolution that follows is then a 27-term gather (head_gather_kernel)
     long long* trace;          // debug timeline (dmb_b200_debug_set_trace) or null: CTA 0 records clock64() per role
     const float* head_w;       // [27][32] fp32 (device) or null
-    float* head_t;             // [B][27][Do][Ho][Wo] fp32 (null: ordinary layer)
+    float* head_t;             // per batch element [9][Do][Ho][Wo] Q planes + [nseg][2][9][Ho][Wo] segment spills, fp32
+                               // (null: ordinary layer)
 };
 
 // 16-bit element codecs: FP16 = true -> IEEE half (11-bit significand), false -> bfloat16 (8-bit)
@@ -315,73 +316,110 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
     }
 }
 
-// fused classifier head: bias + ReLU, then the per-tap projections of the voxel's 32 channels for taps
-// [T0, T1) (fp32 FMAs on the un-rounded activation; weights broadcast from shared memory), one coalesced fp32
-// store per tap plane.  Three taps x four partial sums = 12 independent FMA chains: the epilogue warp is alone
-// on its scheduler, so instruction-level parallelism is what hides the FMA / shared-load latency.
-template <int T0, int T1>
-__device__ __forceinline__ void store_head(const Params& p, float (&v)[NB], const float (&bias)[NB],
-                                           const float4* __restrict__ hw, int b, int d, int h, int w) {
-    const size_t vol = (size_t)p.Do * p.Ho * p.Wo;
-    float* t = p.head_t + (size_t)b * TAPS * vol + ((size_t)d * p.Ho + h) * p.Wo + w;
+// fused classifier head.  The 32 -> 1 3x3x3 convolution that follows the 32 -> 32 layer is
+//     out(d, h, w) = sum_{kd,kh,kw} P[kd][kh][kw](d + kd - 1, h + kh - 1, w + kw - 1),   P[tap](voxel) = <a(voxel), head_w[tap]>.
+// The epilogue thread of a tile position marches along depth, so the kd sum is local to it:
+//     Q[kh][kw](d) = P[0][kh][kw](d - 1) + P[1][kh][kw](d) + P[2][kh][kw](d + 1)
+// is accumulated in registers across consecutive planes and NINE planes are stored instead of 27 tap planes (the
+// gather then reads 9 values per output).  At the two ends of a depth segment the missing neighbour plane belongs
+// to another work item: the two boundary projections go to small per-segment "spill" planes that the gather adds.
+//   head_t (per batch element): Q [9][D][H][W], then spills [nseg][2][9][H][W]  (0: P[2](d0) -> Q(d0 - 1), 1: P[0](d1 - 1) -> Q(d1))
+// K0..K1: the (kh, kw) combinations this warp owns (two warps share a TMEM lane quarter).
+__device__ __forceinline__ size_t head_batch_stride(const Params& p) {
+    return ((size_t)9 * p.Do + (size_t)18 * p.nseg) * p.Ho * p.Wo;
+}
+template <int K0, int K1>
+__device__ __forceinline__ void head_step(const Params& p, float (&v)[NB], const float (&bias)[NB],
+                                          const float4* __restrict__ hw, const Item& it, int d, int h, int w,
+                                          float (&qprev)[5], float (&qcur)[5]) {
+    const size_t hw_sz = (size_t)p.Ho * p.Wo;
+    float* base = p.head_t + (size_t)it.b * head_batch_stride(p) + (size_t)h * p.Wo + w;
+    const bool first = d == it.d0;
+    float* spill_lo = base + ((size_t)9 * p.Do + (size_t)(it.d0 / p.seg_len) * 18) * hw_sz;
 #pragma unroll
     for (int c = 0; c < NB; ++c) {
         v[c] += bias[c];
         if (p.relu) v[c] = fmaxf(v[c], 0.f);
     }
 #pragma unroll
-    for (int g = T0; g < T1; g += 3) {
+    for (int khw = K0; khw < K1; ++khw) {
+        // three taps (kd = 0, 1, 2) x four partial sums = 12 independent FMA chains
         float acc[3][4];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+        for (int kd = 0; kd < 3; ++kd) acc[kd][0] = acc[kd][1] = acc[kd][2] = acc[kd][3] = 0.f;
 #pragma unroll
         for (int c4 = 0; c4 < NB / 4; ++c4) {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                if (g + j < T1) {
-                    const float4 wv = hw[(g + j) * (NB / 4) + c4];
-                    acc[j][0] = fmaf(v[4 * c4 + 0], wv.x, acc[j][0]);
-                    acc[j][1] = fmaf(v[4 * c4 + 1], wv.y, acc[j][1]);
-                    acc[j][2] = fmaf(v[4 * c4 + 2], wv.z, acc[j][2]);
-                    acc[j][3] = fmaf(v[4 * c4 + 3], wv.w, acc[j][3]);
-                }
+            for (int kd = 0; kd < 3; ++kd) {
+                const float4 wv = hw[(kd * 9 + khw) * (NB / 4) + c4];
+                acc[kd][0] = fmaf(v[4 * c4 + 0], wv.x, acc[kd][0]);
+                acc[kd][1] = fmaf(v[4 * c4 + 1], wv.y, acc[kd][1]);
+                acc[kd][2] = fmaf(v[4 * c4 + 2], wv.z, acc[kd][2]);
+                acc[kd][3] = fmaf(v[4 * c4 + 3], wv.w, acc[kd][3]);
             }
         }
+        const float p0 = (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]);
+        const float p1 = (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]);
+        const float p2 = (acc[2][0] + acc[2][1]) + (acc[2][2] + acc[2][3]);
+        const int k = khw - K0;
+        if (first) {
+            spill_lo[(size_t)khw * hw_sz] = p2;                                  // contribution to Q(d0 - 1)
+            qprev[k] = p1;                                                       // Q(d0) so far (P[0](d0 - 1): the neighbour's spill)
+        } else {
+            base[((size_t)khw * p.Do + (d - 1)) * hw_sz] = qprev[k] + p2;        // Q(d - 1) complete
+            qprev[k] = qcur[k] + p1;                                             // Q(d) so far
+        }
+        qcur[k] = p0;                                                            // towards Q(d + 1)
+    }
+}
+template <int K0, int K1>
+__device__ __forceinline__ void head_finish(const Params& p, const Item& it, int h, int w, const float (&qprev)[5],
+                                            const float (&qcur)[5]) {
+    const size_t hw_sz = (size_t)p.Ho * p.Wo;
+    float* base = p.head_t + (size_t)it.b * head_batch_stride(p) + (size_t)h * p.Wo + w;
+    float* spill_hi = base + ((size_t)9 * p.Do + (size_t)(it.d0 / p.seg_len) * 18 + 9) * hw_sz;
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-            if (g + j < T1) t[(size_t)(g + j) * vol] = (acc[j][0] + acc[j][1]) + (acc[j][2] + acc[j][3]);
+    for (int khw = K0; khw < K1; ++khw) {
+        base[((size_t)khw * p.Do + (it.d1 - 1)) * hw_sz] = qprev[khw - K0];      // Q(d1 - 1) without P[2](d1)
+        spill_hi[(size_t)khw * hw_sz] = qcur[khw - K0];                          // P[0](d1 - 1): contribution to Q(d1)
     }
 }
 
-// out[b,d,h,w] = res + sum_tap T[b][tap][d+kd-1][h+kh-1][w+kw-1] (zero outside the volume): the
-// 32->1 3x3x3 head (aggregators/PSMNet.py:41-52) after store_head; every T element is read once
+// out[b,d,h,w] = res + sum_{kh,kw} Qfull[kh][kw][d][h+kh-1][w+kw-1] (zero outside the plane), where Qfull adds the
+// neighbouring depth segments' spill planes at the first / last plane of a segment: the 32->1 3x3x3 head
+// (aggregators/PSMNet.py:41-52) after head_step / head_finish; every Q element is read once per use (9 per output).
 __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ T, const float* __restrict__ res,
-                                                          float* __restrict__ y, int B, int D, int H, int W) {
-    const size_t vol = (size_t)D * H * W;
+                                                          float* __restrict__ y, int B, int D, int H, int W, int seg_len,
+                                                          int nseg) {
+    const size_t hw_sz = (size_t)H * W, vol = (size_t)D * hw_sz;
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= (size_t)B * vol) return;
     const int b = (int)(i / vol);
     size_t r = i - (size_t)b * vol;
-    const int d = (int)(r / ((size_t)H * W));
-    r -= (size_t)d * H * W;
+    const int d = (int)(r / hw_sz);
+    r -= (size_t)d * hw_sz;
     const int h = (int)(r / W), w = (int)(r - (size_t)h * W);
-    const float* tb = T + (size_t)b * TAPS * vol;
+    const float* tb = T + (size_t)b * ((size_t)9 * D + (size_t)18 * nseg) * hw_sz;
+    const int seg = d / seg_len;
+    const int seg_end = min(D, (seg + 1) * seg_len);
+    // spill planes to add: previous segment's "hi" at the first plane, next segment's "lo" at the last plane
+    const float* sp_a = (d == seg * seg_len && seg > 0) ? tb + ((size_t)9 * D + (size_t)(seg - 1) * 18 + 9) * hw_sz : nullptr;
+    const float* sp_b = (d == seg_end - 1 && seg + 1 < nseg) ? tb + ((size_t)9 * D + (size_t)(seg + 1) * 18) * hw_sz : nullptr;
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
-        const int dd = d + kd - 1;
-        if (dd < 0 || dd >= D) continue;
+    for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        if (hh < 0 || hh >= H) continue;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int hh = h + kh - 1;
-            if (hh < 0 || hh >= H) continue;
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int ww = w + kw - 1;
-                if (ww < 0 || ww >= W) continue;
-                const int tap = (kd * 3 + kh) * 3 + kw;
-                acc[kd] += __ldg(tb + (size_t)tap * vol + ((size_t)dd * H + hh) * W + ww);
-            }
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ww = w + kw - 1;
+            if (ww < 0 || ww >= W) continue;
+            const int khw = kh * 3 + kw;
+            const size_t o = (size_t)hh * W + ww;
+            float q = __ldg(tb + ((size_t)khw * D + d) * hw_sz + o);
+            if (sp_a) q += __ldg(sp_a + (size_t)khw * hw_sz + o);
+            if (sp_b) q += __ldg(sp_b + (size_t)khw * hw_sz + o);
+            acc[kh] += q;
         }
     }
     float o = (acc[0] + acc[1]) + acc[2];
@@ -966,6 +1004,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             const bool valid = KIND == 3 ? (h < p.Hm && wl >= 1 && wl <= K3_TWV && w < p.Wm)
                              : KIND == 4 ? (h < p.Hm && wl >= 1 && wl <= TWV && (win & 1) == 0 && win < p.Wm)
                                          : (h < p.Hm && w < p.Wm);
+            float hq_prev[5], hq_cur[5];                   // fused head: running Q sums of this thread's (kh, kw) share
             for (int d = it.d0; d < it.d1; ++d) {
                 if (KIND == 3 || KIND == 4) {
                     const uint32_t buf = t & 1;
@@ -1029,9 +1068,10 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     if (valid) {
                         if constexpr (HEAD) {
                             // two warps per TMEM lane quarter: warps 2..5 project taps 0..13, warps 6..9 taps 14..26
+                            // two warps per TMEM lane quarter: warps 2..5 own (kh, kw) 0..4, warps 6..9 own 5..8
                             const float4* hw4 = reinterpret_cast<const float4*>(smem + S::HEAD_OFF);
-                            if (warp < 6) store_head<0, 14>(p, v, bias, hw4, it.b, d, h, w);
-                            else store_head<14, TAPS>(p, v, bias, hw4, it.b, d, h, w);
+                            if (warp < 6) head_step<0, 5>(p, v, bias, hw4, it, d, h, w, hq_prev, hq_cur);
+                            else head_step<5, 9>(p, v, bias, hw4, it, d, h, w, hq_prev, hq_cur);
                         } else if (!(p.y_f32 && half)) {       // single-channel output: the first half's warp writes it
                             store_voxel<FP16, 2>(p, v, bias, it.b, d, h, w, half * 2);
                         }
@@ -1176,6 +1216,12 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             if (valid) store_voxel<FP16, (KIND == 5 ? 2 : 4)>(p, v, bias, it.b, 2 * d + rd, 2 * h + (cls >> 1), 2 * w + (cls & 1));
                         }
                     }
+                }
+            }
+            if constexpr (HEAD) {                          // last plane of the segment: Q(d1 - 1) and the upward spill
+                if (valid) {
+                    if (warp < 6) head_finish<0, 5>(p, it, h, w, hq_prev, hq_cur);
+                    else head_finish<5, 9>(p, it, h, w, hq_prev, hq_cur);
                 }
             }
         }
@@ -1517,11 +1563,22 @@ extern "C" int dmb_b200_conv3d_tc_head(const void* x_hi, const void* x_lo, const
                           D, H, W, 3, relu, fp16, head_w, head_t, stream);
 }
 
+extern "C" int64_t dmb_b200_conv3d_tc_head_floats(int B, int D, int H, int W) {
+    // floats of the head_t buffer that dmb_b200_conv3d_tc_head writes and dmb_b200_head_gather reads:
+    // per batch element 9 Q planes per depth + 2 x 9 spill planes per depth segment of the launch's schedule
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    Params p;
+    plan_schedule(p, 3, B, D, H, W);
+    return (int64_t)B * ((int64_t)9 * D + (int64_t)18 * p.nseg) * H * W;
+}
+
 extern "C" int dmb_b200_head_gather(const float* head_t, const float* res, float* y, int B, int D, int H, int W,
                                     void* stream) {
     DMB_REQUIRE(head_t && y, "head_gather: null pointer");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "head_gather: non-positive dimension");
+    Params p;                                      // the same static schedule the head launch used
+    plan_schedule(p, 3, B, D, H, W);
     const int64_t n = (int64_t)B * D * H * W;
-    head_gather_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(head_t, res, y, B, D, H, W);
+    head_gather_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(head_t, res, y, B, D, H, W, p.seg_len, p.nseg);
     return check_launch("head_gather_kernel");
 }

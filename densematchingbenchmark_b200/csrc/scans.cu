@@ -619,7 +619,11 @@ __global__ void __launch_bounds__(128) sga_h_lanes_kernel(const float* __restric
 // each with half the sequential length in flight per line -- and the host runs them over channel groups small
 // enough for x and out to stay in L2 between the two launches (dmb_b200_sga below).
 // ---------------------------------------------------------------------------------------
-template <int DPL, int G>
+// PF: software-pipeline depth in scan steps (vertical) / 4-step chunks (horizontal).  A channel group is only a few
+// dozen CTAs, so unlike the all-channel launches there is little thread-level parallelism to hide memory latency
+// behind: every operand (x, the guidance taps and, where needed, the previous contents of out) is requested PF steps
+// ahead into registers (measured with PF = 1: 2300 cycles per scan step, 0.8 TB/s).
+template <int DPL, int G, int PF>
 __global__ void __launch_bounds__(256) sga_v_bi_kernel(const float* __restrict__ x, const float* __restrict__ guid,
                                                        float* __restrict__ out, int C, int D, int H, int W, int first) {
     constexpr int CPB = 128 / G;                              // columns per CTA (each direction: 128 threads)
@@ -636,41 +640,49 @@ __global__ void __launch_bounds__(256) sga_v_bi_kernel(const float* __restrict__
     float* ob = out + base;
     const float* gb = guid + (((size_t)(b * 4 + 2 + back) * 5) * C + c) * plane + (colok ? col : 0);
     const size_t gk = (size_t)C * plane;
-    float A[DPL], xn[DPL], on[DPL], wn[5];
+    float A[DPL], xn[PF][DPL], on[PF][DPL], wn[PF][5];
 #pragma unroll
     for (int j = 0; j < DPL; ++j) A[j] = 0.f;
-    auto fetch = [&](int step, bool want_out) {
-        const size_t row = (size_t)(back ? H - 1 - step : step) * W;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) wn[k] = colok ? __ldg(gb + k * gk + row) : 0.f;
-#pragma unroll
-        for (int j = 0; j < DPL; ++j) {
-            const bool ok = colok && dbase + j < D;
-            xn[j] = ok ? __ldcs(xb + (size_t)j * plane + row) : 0.f;
-            on[j] = (ok && want_out) ? ob[(size_t)j * plane + row] : -INFINITY;
-        }
-    };
     // forward covers rows [0, h1) in phase 1, backward rows [H-1 .. h1] (steps [0, H - h1))
     const int h1 = H / 2;
     const int n1 = back ? H - h1 : h1;
     auto run = [&](int s0, int s1, bool want_out) {
-        if (s0 < s1) fetch(s0, want_out);
-        for (int step = s0; step < s1; ++step) {
+        auto fetch = [&](int u, int step) {                   // u is a compile-time stage index after unrolling
             const size_t row = (size_t)(back ? H - 1 - step : step) * W;
-            float xv[DPL], ov[DPL], w[5], cur[DPL];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) w[k] = wn[k];
+            for (int k = 0; k < 5; ++k) wn[u][k] = colok ? __ldg(gb + k * gk + row) : 0.f;
 #pragma unroll
             for (int j = 0; j < DPL; ++j) {
-                xv[j] = xn[j];
-                ov[j] = on[j];
+                const bool ok = colok && dbase + j < D;
+                xn[u][j] = ok ? __ldg(xb + (size_t)j * plane + row) : 0.f;      // (no evict-first: the horizontal pair re-reads x from L2)
+                on[u][j] = (ok && want_out) ? ob[(size_t)j * plane + row] : -INFINITY;
             }
-            if (step + 1 < s1) fetch(step + 1, want_out);
-            sga_lane_step<DPL, G>(A, xv, w, step > 0, q, dbase, D, cur);
+        };
 #pragma unroll
-            for (int j = 0; j < DPL; ++j) {
-                if (colok && dbase + j < D) ob[(size_t)j * plane + row] = fmaxf(ov[j], cur[j]);   // ov = -inf: plain store
-                A[j] = cur[j];
+        for (int u = 0; u < PF; ++u)
+            if (s0 + u < s1) fetch(u, s0 + u);
+        for (int sb = s0; sb < s1; sb += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int step = sb + u;
+                if (step < s1) {
+                    const size_t row = (size_t)(back ? H - 1 - step : step) * W;
+                    float xv[DPL], ov[DPL], w[5], cur[DPL];
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) w[k] = wn[u][k];
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) {
+                        xv[j] = xn[u][j];
+                        ov[j] = on[u][j];
+                    }
+                    if (step + PF < s1) fetch(u, step + PF);
+                    sga_lane_step<DPL, G>(A, xv, w, step > 0, q, dbase, D, cur);
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j) {
+                        if (colok && dbase + j < D) ob[(size_t)j * plane + row] = fmaxf(ov[j], cur[j]);   // ov = -inf: plain store
+                        A[j] = cur[j];
+                    }
+                }
             }
         }
     };
@@ -681,7 +693,7 @@ __global__ void __launch_bounds__(256) sga_v_bi_kernel(const float* __restrict__
 
 // TPD threads per direction (a multiple of 32): few rows per CTA spread a channel group's rows over many SMs -- the
 // horizontal pair works out of L2 and a handful of SMs could not pull the group's slices fast enough
-template <int DPL, int G, int TPD>
+template <int DPL, int G, int TPD, int PF>
 __global__ void __launch_bounds__(2 * TPD) sga_h_bi_kernel(const float* __restrict__ x, const float* __restrict__ guid,
                                                            float* __restrict__ out, int C, int D, int H, int W, int first) {
     constexpr int RPB = TPD / G;                              // rows per CTA
@@ -702,62 +714,66 @@ __global__ void __launch_bounds__(2 * TPD) sga_h_bi_kernel(const float* __restri
     float A[DPL];
 #pragma unroll
     for (int j = 0; j < DPL; ++j) A[j] = 0.f;
-    float4 xn[DPL], wn[5];
-    auto fetch = [&](int i) {                                 // i = scan-order chunk index
-        const int t0 = 4 * (back ? nchunks - 1 - i : i);
-#pragma unroll
-        for (int k = 0; k < 5; ++k)
-            wn[k] = rowok ? __ldg(reinterpret_cast<const float4*>(gb + k * gk + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int j = 0; j < DPL; ++j)
-            xn[j] = (rowok && dbase + j < D) ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * plane + t0))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
+    float4 xn[PF][DPL], on[PF][DPL], wn[PF][5];
     const int c1 = nchunks / 2;
     const int n1 = back ? nchunks - c1 : c1;                  // chunks of phase 1 for this direction
     bool started = false;
+    const float4 ninf = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     auto run = [&](int i0, int i1, bool want_out) {
-        if (i0 < i1) fetch(i0);
-        for (int i = i0; i < i1; ++i) {
+        auto fetch = [&](int u, int i) {                      // i = scan-order chunk index, u = stage (compile time)
             const int t0 = 4 * (back ? nchunks - 1 - i : i);
-            float xc[DPL][4], oc[DPL][4], wc[5][4];
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                wc[k][0] = wn[k].x; wc[k][1] = wn[k].y; wc[k][2] = wn[k].z; wc[k][3] = wn[k].w;
-            }
+            for (int k = 0; k < 5; ++k)
+                wn[u][k] = rowok ? __ldg(reinterpret_cast<const float4*>(gb + k * gk + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < DPL; ++j) {
-                xc[j][0] = xn[j].x; xc[j][1] = xn[j].y; xc[j][2] = xn[j].z; xc[j][3] = xn[j].w;
-                float4 o = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                if (want_out && rowok && dbase + j < D) o = *reinterpret_cast<const float4*>(ob + (size_t)j * plane + t0);
-                oc[j][0] = o.x; oc[j][1] = o.y; oc[j][2] = o.z; oc[j][3] = o.w;
+                const bool ok = rowok && dbase + j < D;
+                xn[u][j] = ok ? __ldg(reinterpret_cast<const float4*>(xb + (size_t)j * plane + t0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                on[u][j] = (ok && want_out) ? *reinterpret_cast<const float4*>(ob + (size_t)j * plane + t0) : ninf;
             }
-            if (i + 1 < i1) fetch(i + 1);
+        };
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                float xv[DPL], w[5], cur[DPL];
-                float xf[DPL], xr[DPL];
+        for (int u = 0; u < PF; ++u)
+            if (i0 + u < i1) fetch(u, i0 + u);
+        for (int ib = i0; ib < i1; ib += PF) {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) w[k] = back ? wc[k][3 - s] : wc[k][s];
+            for (int u = 0; u < PF; ++u) {
+                const int i = ib + u;
+                if (i < i1) {
+                    const int t0 = 4 * (back ? nchunks - 1 - i : i);
+                    float xc[DPL][4], oc[DPL][4], wc[5][4];
 #pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    xf[j] = xc[j][s];
-                    xr[j] = xc[j][3 - s];
-                    xv[j] = back ? xr[j] : xf[j];
-                }
-                sga_lane_step<DPL, G>(A, xv, w, started, q, dbase, D, cur);
-                started = true;
+                    for (int k = 0; k < 5; ++k) {
+                        wc[k][0] = wn[u][k].x; wc[k][1] = wn[u][k].y; wc[k][2] = wn[u][k].z; wc[k][3] = wn[u][k].w;
+                    }
 #pragma unroll
-                for (int j = 0; j < DPL; ++j) {
-                    if (back) oc[j][3 - s] = fmaxf(oc[j][3 - s], cur[j]);      // -inf: plain store
-                    else oc[j][s] = fmaxf(oc[j][s], cur[j]);
-                    A[j] = cur[j];
+                    for (int j = 0; j < DPL; ++j) {
+                        xc[j][0] = xn[u][j].x; xc[j][1] = xn[u][j].y; xc[j][2] = xn[u][j].z; xc[j][3] = xn[u][j].w;
+                        oc[j][0] = on[u][j].x; oc[j][1] = on[u][j].y; oc[j][2] = on[u][j].z; oc[j][3] = on[u][j].w;
+                    }
+                    if (i + PF < i1) fetch(u, i + PF);
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4) {
+                        float xv[DPL], w[5], cur[DPL];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) w[k] = back ? wc[k][3 - s4] : wc[k][s4];
+#pragma unroll
+                        for (int j = 0; j < DPL; ++j) xv[j] = back ? xc[j][3 - s4] : xc[j][s4];
+                        sga_lane_step<DPL, G>(A, xv, w, started, q, dbase, D, cur);
+                        started = true;
+#pragma unroll
+                        for (int j = 0; j < DPL; ++j) {
+                            if (back) oc[j][3 - s4] = fmaxf(oc[j][3 - s4], cur[j]);      // -inf: plain store
+                            else oc[j][s4] = fmaxf(oc[j][s4], cur[j]);
+                            A[j] = cur[j];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < DPL; ++j)
+                        if (rowok && dbase + j < D)
+                            *reinterpret_cast<float4*>(ob + (size_t)j * plane + t0) = make_float4(oc[j][0], oc[j][1], oc[j][2], oc[j][3]);
                 }
             }
-#pragma unroll
-            for (int j = 0; j < DPL; ++j)
-                if (rowok && dbase + j < D)
-                    *reinterpret_cast<float4*>(ob + (size_t)j * plane + t0) = make_float4(oc[j][0], oc[j][1], oc[j][2], oc[j][3]);
         }
     };
     run(0, n1, !first);
@@ -1098,16 +1114,17 @@ extern "C" int dmb_b200_sga(const float* x, const float* guidance, float* out, i
                 const float* xg = x + ((size_t)b * C + c0) * D * plane;
                 float* og = out + ((size_t)b * C + c0) * D * plane;
                 const float* gg = guidance + (size_t)b * 20 * C * plane + (size_t)c0 * plane;
-#define DMB_SGA_BI(DPLV, GV, DPLH, GH)                                                                                        \
+#define DMB_SGA_BI(DPLV, GV, PFV, DPLH, GH, PFH)                                                                              \
     do {                                                                                                                     \
-        sga_v_bi_kernel<DPLV, GV><<<dim3((unsigned)cdiv(W, 128 / GV), gc, 1), 256, 0, s>>>(xg, gg, og, C, D, H, W, 1);        \
-        sga_h_bi_kernel<DPLH, GH, 32><<<dim3((unsigned)cdiv(H, 32 / GH), gc, 1), 64, 0, s>>>(xg, gg, og, C, D, H, W, 0);      \
+        sga_v_bi_kernel<DPLV, GV, PFV><<<dim3((unsigned)cdiv(W, 128 / GV), gc, 1), 256, 0, s>>>(xg, gg, og, C, D, H, W, 1);   \
+        sga_h_bi_kernel<DPLH, GH, 64, PFH><<<dim3((unsigned)cdiv(H, 64 / GH), gc, 1), 128, 0, s>>>(xg, gg, og, C, D, H, W, 0); \
     } while (0)
-                // vertical: 8 lanes per column (16 columns = 64-byte row segments per CTA and direction);
-                // horizontal: 8 lanes per row, 4 rows per CTA (one warp per direction)
-                if (D <= 16) DMB_SGA_BI(2, 8, 2, 8);
-                else if (D <= 32) DMB_SGA_BI(4, 8, 4, 8);
-                else DMB_SGA_BI(8, 8, 8, 8);
+                // vertical: 8 lanes per column (16 columns = 64-byte row segments per CTA and direction), 3 steps ahead;
+                // horizontal: 16 lanes per row (4 disparities each: short per-step chains), 4 rows per CTA and
+                // direction, 2-3 chunks (8-12 steps) ahead
+                if (D <= 16) DMB_SGA_BI(2, 8, 4, 1, 16, 3);
+                else if (D <= 32) DMB_SGA_BI(4, 8, 4, 2, 16, 3);
+                else DMB_SGA_BI(8, 8, 3, 4, 16, 2);
 #undef DMB_SGA_BI
                 int rc = check_launch("sga_bi_kernels");
                 if (rc) return rc;

@@ -324,7 +324,9 @@ def classif_head(seq, x, res_f32=None):
     blob, bias, Cin, Cout, scale, kind, _ = _blob(unit, x.split, x.fp16)
     D, H, W = x.dims
     dev = x.hi.device
-    taps = torch.empty(x.B, 27, D, H, W, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):          # the schedule (depth segments -> spill planes) depends on the device's SM count
+        nfloats = C.load().dmb_b200_conv3d_tc_head_floats(x.B, D, H, W)
+    taps = torch.empty(nfloats, dtype=torch.float32, device=dev)
     C.call("dmb_b200_conv3d_tc_head", C.ptr(x.hi), C.ptr(x.lo), C.ptr(blob), float(scale), C.ptr(bias),
            C.ptr(_head_weight(conv)), C.ptr(taps), x.B, D, H, W, 1 if unit._has_relu else 0, 1 if x.fp16 else 0,
            C.stream(dev))

@@ -182,10 +182,14 @@ int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* 
                        void* stream);
 /* Fused classifier head (replaces the nn.Sequential(conv3d_bn_relu(32,32), Conv3d(32,1,3,1,1,bias=False)) of
  * aggregators/PSMNet.py:41-52 / AcfNet.py:43-53): the 32->32 stride-1 layer (w_blob packed for kind 3, BatchNorm
- * folded, bias or NULL) runs on tcgen05 and its epilogue writes, instead of the activation a, the 27 per-tap
- * projections head_t[b][tap][d][h][w] = sum_c relu?(a[c]) * head_w[tap][c] (float32, head_w = the Conv3d(32,1)
- * weight as [27][32]).  dmb_b200_head_gather then forms y[b,d,h,w] = res? + sum_tap head_t[b][tap][d+kd-1][h+kh-1]
- * [w+kw-1] (zero padding): the 32->1 convolution as one streaming pass instead of a second tensor-core launch. */
+ * folded, bias or NULL) runs on tcgen05; its epilogue does not store the activation a but projects it on the 27 taps
+ * of the Conv3d(32,1) weight (head_w as [27][32] float32) and, marching along depth, sums the three depth taps in
+ * registers: head_t holds, per batch element, the nine planes Q[kh][kw][d][h][w] followed by 2 x 9 spill planes per
+ * depth segment of the launch's schedule (dmb_b200_conv3d_tc_head_floats gives the total size in floats).
+ * dmb_b200_head_gather then forms y[b,d,h,w] = res? + sum_{kh,kw} Q[kh][kw][d][h+kh-1][w+kw-1] (zero padding, spills
+ * added at segment borders): the 32->1 convolution as one streaming pass over 9 (not 27) values per output instead
+ * of a second tensor-core launch.  Both calls must see the same B, D, H, W on the same device. */
+int64_t dmb_b200_conv3d_tc_head_floats(int B, int D, int H, int W);
 int dmb_b200_conv3d_tc_head(const void* x_hi, const void* x_lo, const void* w_blob, float w_scale, const float* bias,
                             const float* head_w, float* head_t, int B, int D, int H, int W, int relu, int fp16,
                             void* stream);
