@@ -27,6 +27,7 @@ SIGNATURES = {
     "dmb_b200_cat_volume": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
     "dmb_b200_dif_volume": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
     "dmb_b200_gwc_volume": [_P, _P, _P, _I, _I, _I, _I, _I, _IP, _I, _P],
+    "dmb_b200_corr1d_volume": [_P, _P, _P, _I, _I, _I, _I, _I, _F, _P],
     "dmb_b200_warp_volume": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P],
     "dmb_b200_conv3d_direct": [_P, _P, _P, _P, _P, _I, _I, _I, _IP, _IP, _IP, _I, _I, _I, _I, _P],
     "dmb_b200_upsample_regress": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _I, _F, _F, _P, _P],
@@ -68,6 +69,7 @@ OTHER = {
     "dmb_b200_launch_count": ([], c_int64),
     "dmb_b200_conv3d_tc_weight_bytes": ([_I, _I, _I, _I], c_int64),
     "dmb_b200_conv3d_tc_available": ([], c_int),
+    "dmb_b200_sga_set_bidirectional": ([_I], c_int),
     "dmb_b200_conv3d_tc_head_floats": ([_I, _I, _I, _I], c_int64),
 }
 

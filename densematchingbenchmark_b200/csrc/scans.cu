@@ -1076,6 +1076,13 @@ static int launch_sga_h(const float* x, const float* g, float* out, int B, int C
     return 0;
 }
 
+static int g_sga_bidir = -1;     // -1: read DMB_B200_SGA_BIDIR on first use
+extern "C" int dmb_b200_sga_set_bidirectional(int on) {       // selects the SGA schedule; returns the previous setting
+    const int prev = g_sga_bidir;
+    g_sga_bidir = on < 0 ? -1 : (on ? 1 : 0);
+    return prev;
+}
+
 extern "C" int dmb_b200_sga(const float* x, const float* guidance, float* out, int B, int C, int D, int H, int W,
                             void* stream) {
     DMB_REQUIRE(x && guidance && out, "sga: null pointer");
@@ -1091,10 +1098,16 @@ extern "C" int dmb_b200_sga(const float* x, const float* guidance, float* out, i
     }
     const bool aligned16 = (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(guidance) |
                             reinterpret_cast<uintptr_t>(out)) % 16 == 0;
-    static int bi_mode = -1;                       // DMB_B200_SGA_BIDIR=0: the four single-direction launches (A/B)
+    // DMB_B200_SGA_BIDIR=1: the bidirectional, L2-blocked launches below.  OFF by default -- measured on B200
+    // (profiles/README.md, round 2): they cut the DRAM traffic from 4.8 GB to 1.15 GB (1.15x algorithmic) as designed,
+    // but run 4.4 ms against 1.9 ms for the four all-channel launches: with 16-byte-per-lane accesses every load /
+    // store request touches 8 (vertical) or 32 (horizontal) distinct lines, the LSU processes about one line per cycle,
+    // and a 3-channel group keeps only ~80-100 CTAs busy, so the kernels sit at the L1 tag throughput of those few SMs.
+    // The fix is the one the north star names -- TMA-staged tiles so that global traffic bypasses the LSU.
+    int bi_mode = g_sga_bidir;
     if (bi_mode < 0) {
         const char* e = getenv("DMB_B200_SGA_BIDIR");
-        bi_mode = (e && e[0] == '0') ? 0 : 1;
+        bi_mode = g_sga_bidir = (e && e[0] == '1') ? 1 : 0;
     }
     if (lanes_mode && bi_mode && D <= 64 && W % 4 == 0 && W >= 8 && H >= 2 && aligned16) {
         // Two bidirectional launches (vertical pair first: its x reads are the coalesced ones, so x comes from HBM

@@ -239,7 +239,10 @@ __global__ void __launch_bounds__(256) gwc_rows_kernel(const float* __restrict__
 template <int CPG, bool ALIGNED>   // channels per group (0 = runtime)
 __global__ void __launch_bounds__(256) gwc_rows_unit_kernel(const float* __restrict__ left, const float* __restrict__ right,
                                                             float* __restrict__ out, int C, int G, int H, int W, int D,
-                                                            int d0, int PAD) {
+                                                            int d0, int PAD, float scale, float slope, int reverse) {
+    // scale: 1 / channels-per-group (GwcNet mean) or 1 (plain correlation sum); slope: negative slope of a leaky ReLU
+    // applied to the result (1 = none); reverse: disparity d0 + k is written to output plane D - 1 - k
+    // (correlation1d_cost's channel order, correlation1d_cost.py:12-22)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cpg = CPG ? CPG : C / G;
     const int WR = W + 2 * PAD;
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(256) gwc_rows_unit_kernel(const float* __restr
     mbar_wait(&bar, 0);
 
     float* out_row0 = out + (((size_t)(b * G + g) * D) * H + y) * W;
-    const float inv = 1.0f / (float)cpg;          // mean = sum * (1/n): exact for power-of-two group sizes
+    const float inv = scale;                      // mean = sum * (1/n): exact for power-of-two group sizes
     const int W4 = W >> 2, KG = (D + 7) >> 3;
     for (int u = threadIdx.x; u < W4 * KG; u += blockDim.x) {
         const int kg = u / W4;
@@ -306,9 +309,12 @@ __global__ void __launch_bounds__(256) gwc_rows_unit_kernel(const float* __restr
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
             const int k = kg * 8 + kk;
-            if (k < D)
-                st_cs_f4(out_row0 + (size_t)k * plane + x,
-                         make_float4(acc[kk][0] * inv, acc[kk][1] * inv, acc[kk][2] * inv, acc[kk][3] * inv));
+            if (k < D) {
+                float4 o = make_float4(acc[kk][0] * inv, acc[kk][1] * inv, acc[kk][2] * inv, acc[kk][3] * inv);
+                o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+                o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+                st_cs_f4(out_row0 + (size_t)(reverse ? D - 1 - k : k) * plane + x, o);
+            }
         }
     }
 }
@@ -576,9 +582,11 @@ extern "C" int dmb_b200_gwc_volume(const float* left, const float* right, float*
                                           (int)smem_u));                                                               \
         }                                                                                                              \
         if (aligned)                                                                                                   \
-            gwc_rows_unit_kernel<CPG, true><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, G, H, W, D, d0, PAD);  \
+            gwc_rows_unit_kernel<CPG, true><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, G, H, W, D, d0, PAD, \
+                                                                                           1.0f / (float)cpg, 1.0f, 0);          \
         else                                                                                                           \
-            gwc_rows_unit_kernel<CPG, false><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, G, H, W, D, d0, PAD); \
+            gwc_rows_unit_kernel<CPG, false><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, G, H, W, D, d0, PAD, \
+                                                                                            1.0f / (float)cpg, 1.0f, 0);         \
     } while (0)
             if (cpg == 8) DMB_GWC_UNIT(8);
             else if (cpg == 4) DMB_GWC_UNIT(4);
@@ -603,6 +611,34 @@ extern "C" int dmb_b200_gwc_volume(const float* left, const float* right, float*
         if (rc) return rc;
     }
     return DMB_OK;
+}
+
+// correlation1d_cost (dmb/modeling/stereo/cost_processors/utils/correlation1d_cost.py:7-27): the reference calls the
+// un-vendored SpatialCorrelationSampler(patch_size = (1, 2 max_disp - 1), kernel 1, stride 1, padding 0, dilation_patch 1)
+// -- out[j] = sum_c L[c, y, x] * R[c, y, x + j - (max_disp - 1)], zero outside the image -- keeps the first max_disp
+// channels (shifts -(max_disp - 1) .. 0) and applies leaky ReLU(0.1).  I.e. a ONE-group correlation with a plain sum,
+// channel j holding disparity max_disp - 1 - j: the GWC register-blocked kernel with scale 1, reversed output planes
+// and the leaky ReLU in its store.  out: [B, max_disp, H, W].
+extern "C" int dmb_b200_corr1d_volume(const float* left, const float* right, float* out, int B, int C, int H, int W,
+                                      int max_disp, float negative_slope, void* stream) {
+    DMB_REQUIRE(left && right && out, "corr1d_volume: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && max_disp > 0, "corr1d_volume: non-positive dimension");
+    DMB_REQUIRE(H <= 65535 && B <= 65535, "corr1d_volume: grid dimension too large");
+    DMB_REQUIRE(W % 4 == 0 && ((reinterpret_cast<uintptr_t>(left) | reinterpret_cast<uintptr_t>(right) |
+                                reinterpret_cast<uintptr_t>(out)) % 16 == 0),
+                "corr1d_volume: W must be a multiple of 4 and the tensors 16-byte aligned");
+    const int D = max_disp;
+    const int PAD = ((D - 1 + 8 + 8) + 3) & ~3;
+    const size_t smem_u = (size_t)C * (W + W + 2 * PAD) * 4;
+    DMB_REQUIRE(smem_u <= 200 * 1024, "corr1d_volume: %d feature rows of width %d do not fit shared memory", C, W);
+    DMB_CUDA(cudaFuncSetAttribute(gwc_rows_unit_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
+    const int units = (W / 4) * ((D + 7) / 8), sweeps = (units + 255) / 256;
+    int uthreads = (((units + sweeps - 1) / sweeps + 31) / 32) * 32;
+    if (uthreads > 256) uthreads = 256;
+    dim3 grid(H, 1, B);
+    gwc_rows_unit_kernel<0, true><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, 1, H, W, D, 0, PAD, 1.0f,
+                                                                                  negative_slope, 1);
+    return check_launch("gwc_rows_unit_kernel<corr1d>");
 }
 
 extern "C" int dmb_b200_warp_volume(const float* left, const float* right, const float* disp_sample, float* out, int B,

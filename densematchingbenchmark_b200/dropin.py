@@ -24,9 +24,10 @@ def install_into_dmb(dmb_module_name="dmb"):
         replaced[name] = sorted(ours.keys())
     # processors: ours resolve the volume function at construction through OUR tables and build
     # the aggregator through OUR builder, so swap the classes (keeps 'DeepPruner'/'AnyNet' as is)
-    for key in ("Concatenation", "Difference", "GroupWiseCorrelation"):
+    # ('Correlation': the reference's own COR_FUNCS import needs the un-vendored spatial_correlation_sampler; ours does not)
+    for key in ("Concatenation", "Difference", "Correlation", "GroupWiseCorrelation"):
         ref_cp.PROCESSORS[key] = cp.PROCESSORS[key]
-    replaced["PROCESSORS"] = ["Concatenation", "Difference", "GroupWiseCorrelation"]
+    replaced["PROCESSORS"] = ["Concatenation", "Difference", "Correlation", "GroupWiseCorrelation"]
     # dmb.ops.spn
     try:
         ref_ops = importlib.import_module(dmb_module_name + ".ops")

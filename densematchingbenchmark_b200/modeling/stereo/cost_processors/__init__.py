@@ -3,3 +3,4 @@ from .aggregators import AGGREGATORS, build_cost_aggregator, DeferredCost  # noq
 from .utils.cat_fms import CAT_FUNCS  # noqa: F401
 from .utils.dif_fms import DIF_FUNCS  # noqa: F401
 from .utils.gwc_fms import GWC_FUNCS  # noqa: F401
+from .utils.correlation1d_cost import COR_FUNCS  # noqa: F401

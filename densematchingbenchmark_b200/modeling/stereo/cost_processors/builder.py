@@ -4,6 +4,7 @@ import torch.nn as nn
 from .utils.cat_fms import CAT_FUNCS
 from .utils.dif_fms import DIF_FUNCS
 from .utils.gwc_fms import GWC_FUNCS
+from .utils.correlation1d_cost import COR_FUNCS
 from .aggregators import build_cost_aggregator
 
 
@@ -61,14 +62,13 @@ class GwcCostProcessor(_VolumeThenAggregate):
     table = GWC_FUNCS
 
 
-class CorCostProcessor(CostProcessor):
-    """'Correlation' needs the un-vendored spatial_correlation_sampler extension in the reference
-    (correlation1d_cost.py:5-17); no shipped config uses it and it has no oracle -> not provided."""
+class CorCostProcessor(_VolumeThenAggregate):
+    """'Correlation' (builder.py:67-87): correlation1d_cost, then the configured aggregator."""
+    table = COR_FUNCS
 
-    def __init__(self, cfg):
-        super(CorCostProcessor, self).__init__()
-        raise NotImplementedError("cost_processor type 'Correlation' is outside the B200 hot path "
-                                  "(parity unpinned: its reference dependency is not vendored)")
+    @property
+    def cor_func(self):
+        return self.func
 
 
 PROCESSORS = {

@@ -133,6 +133,10 @@ int dmb_b200_spn_backward(const float* X, const float* G1, const float* G2, cons
 /* ------------------------------------------------------------------------------------------
  * GANet aggregation layers (NO reference code; semantics fixed by oracle/dmb_oracle.py).
  * ---------------------------------------------------------------------------------------- */
+/* SGA schedule switch: 1 = two bidirectional launches per L2-sized channel group (1.15x algorithmic DRAM traffic,
+   latency-bound at present), 0 = four all-channel single-direction launches (default), -1 = re-read
+   DMB_B200_SGA_BIDIR.  Returns the previous setting (not a status code). */
+int dmb_b200_sga_set_bidirectional(int on);
 /* SGA: x [B,C,D,H,W], guidance [B,4,5,C,H,W] (un-normalised; L1-normalised over the 5 taps
  * inside), out [B,C,D,H,W] = max over the 4 scan directions. */
 int dmb_b200_sga(const float* x, const float* guidance, float* out,
@@ -146,6 +150,12 @@ int dmb_b200_lga(const float* x, const float* guidance, float* out,
  * Tensor-core (tcgen05) trunk: channels-last bf16 activations, optionally as a (hi, lo) split
  * pair that carries ~16 mantissa bits through bf16 MMAs with fp32 accumulation.
  * ---------------------------------------------------------------------------------------- */
+
+/* correlation1d_cost (cost_processors/utils/correlation1d_cost.py:7-27; the reference goes through the un-vendored
+ * SpatialCorrelationSampler): out[b, j, y, x] = leaky_relu( sum_c L[b,c,y,x] * R[b,c,y,x - (max_disp-1-j)] ), zero where
+ * the shifted column leaves the image; out [B, max_disp, H, W] float32.  W % 4 == 0. */
+int dmb_b200_corr1d_volume(const float* left, const float* right, float* out, int B, int C, int H, int W, int max_disp,
+                           float negative_slope, void* stream);
 
 /* cat volume straight into the trunk's blocked layout: out_hi/out_lo [B][2C/8][D][H][W][8] bf16
  * from the float32 NCHW features (out_lo NULL => plain bf16, no split).  C % 8 == 0. */

@@ -12,8 +12,11 @@ outputs of the reference itself (`oracle/make_golden.py` imports the reference t
 them).  The functions with NO counterpart in the reference snapshot -- `gwc_volume`,
 `sga`, `lga` -- are **parity unpinned**: they restate the published
 GwcNet / GANet definitions and are the contract for the kernels by themselves.
-`spn_scan*` restates `dmb/ops/spn/src/gaterecurrent2dnoind_kernel.cu`, which cannot run in
-this container (CUDA only, no CPU path) -- also **parity unpinned**.
+`correlation1d_cost` restates the published definition of the un-vendored `spatial_correlation_sampler`
+dependency -- **parity unpinned** as well.  `spn_scan*` restates `dmb/ops/spn/src/gaterecurrent2dnoind_kernel.cu`:
+the CPU restatement cannot be pinned in this container (CUDA only, no CPU path), but on the GPU box it IS pinned --
+`tests/test_gpu_spn_ref.py` checks it (and csrc/scans.cu) against the reference kernel itself, compiled from the
+reference tree into the test-only `oracle/_ref/libspn_ref.so` by `oracle/build_ref.py`.
 
 Everything here is deliberately simple: explicit index arithmetic and torch CPU tensor ops
 in float32 (the reference's dtype), no modules, weights addressed through reference
@@ -229,6 +232,26 @@ def gwc_volume(left, right, num_groups, max_disp=192, start_disp=0, dilation=1):
         prod = (l * r).view(B, num_groups, cpg, H, l.shape[-1])
         out[:, :, k, :, xs] = prod.mean(dim=2)
     return out
+
+
+def correlation1d_cost(left, right, max_disp=192, negative_slope=0.1):
+    """PARITY UNPINNED.  correlation1d_cost (cost_processors/utils/correlation1d_cost.py:7-27).  The reference calls
+    `spatial_correlation_sampler.SpatialCorrelationSampler(patch_size=(1, 2*max_disp-1), kernel_size=1, stride=1,
+    padding=0, dilation_patch=1)` -- a third-party CUDA extension that is neither vendored nor version-pinned by the
+    reference (INSTALL.md:60 names the repository ClementPinard/Pytorch-Correlation-extension) and cannot be imported
+    here.  Its published definition, restated: out[b, ph, pw, y, x] = sum_c in1[b,c,y,x] * in2[b,c,y+ph-PH//2,x+pw-PW//2]
+    with zero padding of in2 and no normalisation.  With PH = 1, PW = 2*max_disp-1 the reference squeezes ph, keeps
+    pw = 0 .. max_disp-1 (shifts -(max_disp-1) .. 0, :19-22) and applies leaky ReLU(0.1) (:24):
+        out[b, j, y, x] = lrelu( sum_c L[b,c,y,x] * R[b,c,y,x - (max_disp-1-j)] )."""
+    B, C, H, W = left.shape
+    out = torch.zeros(B, max_disp, H, W, dtype=torch.float32)
+    for j in range(max_disp):
+        d = max_disp - 1 - j
+        if d >= W:
+            continue
+        l, r, xs = _shift_pair(left, right, d)
+        out[:, j, :, xs] = (l * r).sum(dim=1)
+    return F.leaky_relu(out, negative_slope)
 
 
 # --------------------------------------------------------------------------------------

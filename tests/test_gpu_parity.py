@@ -338,6 +338,23 @@ def test_medium_size_psm_hot_path_vs_oracle(P, engine, precision, sharpen):
         assert abs(O.epe(got, gt, 0, 1e9) - O.epe(w32, gt, 0, 1e9)) < 1e-3      # |dEPE| vs the float32 oracle
 
 
+@pytest.mark.parametrize("shape", [(1, 8, 5, 16, 6), (2, 32, 9, 64, 48), (1, 16, 4, 24, 40), (1, 32, 34, 120, 48)])
+def test_correlation1d_cost_vs_oracle(P, shape):
+    """SURVEY 8a row a5 (`'Correlation'` processor): one-group correlation, plain sum over the channels, reversed
+    disparity order, leaky ReLU(0.1) -- against the oracle's restatement of the sampler's published definition."""
+    B, C, H, W, md = shape
+    l, r = seeded.feature_pair(B, C, H, W, seed=md)
+    got = P.COR_FUNCS["default"](l.to(DEV), r.to(DEV), max_disp=md, start_disp=3, dilation=2)   # both ignored, like the reference
+    want = O.correlation1d_cost(l, r, md)
+    assert tuple(got.shape) == (B, md, H, W)
+    torch.testing.assert_close(got.cpu(), want, atol=1e-5, rtol=1e-5)
+    # channel md-1 is the zero-disparity correlation, channel 0 the largest disparity
+    zero_d = F.leaky_relu((l * r).sum(1), 0.1)
+    torch.testing.assert_close(got[:, md - 1].cpu(), zero_d, atol=1e-5, rtol=1e-5)
+    with pytest.raises(NotImplementedError):
+        P.COR_FUNCS["default"](l.to(DEV), r.to(DEV), max_disp=md, kernel_size=3)
+
+
 # ------------------------------------------------------------------------------- scans
 @pytest.mark.parametrize("shape", [(2, 3, 5, 6), (1, 8, 34, 60), (1, 2, 1, 7), (1, 2, 7, 1)])
 def test_spn_forward_backward_vs_oracle(P, shape):
@@ -365,13 +382,21 @@ def test_spn_forward_backward_vs_oracle(P, shape):
                                    # fill a CTA, every DPL instantiation (D <= 16 / 32 / 64 horizontal, <= 8..128 vertical)
                                    (1, 2, 20, 6, 16), (2, 2, 64, 9, 24), (1, 1, 37, 21, 8), (1, 1, 7, 3, 4), (1, 1, 100, 5, 40),
                                    (1, 1, 33, 18, 72)])
-def test_sga_vs_oracle(P, shape):
+@pytest.mark.parametrize("bidir", [0, 1])
+def test_sga_vs_oracle(P, shape, bidir):
+    """bidir = 1: the bidirectional, channel-grouped schedule (kept behind DMB_B200_SGA_BIDIR / the C-ABI switch);
+    shapes it does not cover (D > 64, W % 4 != 0, W < 8) take the default kernels either way."""
     from densematchingbenchmark_b200.ops import SGA
+    from densematchingbenchmark_b200 import _cabi
     B, C, D, H, W = shape
     g = torch.Generator().manual_seed(D)
     x = torch.randn(B, C, D, H, W, generator=g)
     gd = torch.randn(B, 4 * 5 * C, H, W, generator=g)
-    got = SGA()(x.to(DEV), gd.to(DEV)).cpu()
+    prev = _cabi.load().dmb_b200_sga_set_bidirectional(bidir)
+    try:
+        got = SGA()(x.to(DEV), gd.to(DEV)).cpu()
+    finally:
+        _cabi.load().dmb_b200_sga_set_bidirectional(prev)
     torch.testing.assert_close(got, O.sga(x, gd), atol=1e-5, rtol=1e-4)
 
 
