@@ -171,6 +171,7 @@ struct Params {
     int relu;
     int n_valid_out;           // output channels that exist (1 in y_f32 mode, else 32)
     float acc_scale;           // 2^-k undoing the power-of-two weight pre-scaling (exact)
+    int flat;                  // KIND 3 only: 1 = 2-D 3x3 convolution (D == 1): only the kd = 1 taps are issued
     // fused classifier head (KIND 3 only): instead of storing the 32-channel activation a, the epilogue
     // writes its 27 per-tap projections T[tap][voxel] = sum_c a[c] * head_w[tap][c]; the 32->1 3x3x3
     // convolution that follows is then a 27-term gather (head_gather_kernel)
@@ -667,6 +668,8 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                                     const uint32_t a_off = kh * (K3_TW * 16) + 2 * kk * LBO_A;
                                     if (kd == 0 && kh == 0 && kk == 0)
                                         mma_f16_ss<false>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
+                                    else if (kd == 1 && kh == 0 && kk == 0)    // the first MMA of a flat (2-D) layer
+                                        mma_f16_ss_rt(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main, p.flat ? 0u : 1u);
                                     else
                                         mma_f16_ss<true>(acc, a_lo_kd[kd] + (a_off >> 4), a_hiw, b_lo, b_hi, idesc_main);
                                     if (SPLIT)   // lo*Whi of the three kw lands on the (small) hi*Wlo columns
@@ -679,7 +682,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                         const bool more = od + 1 < nout;
                         if (elect_one()) {
                             trace_stamp(p, 0, ntrace);                         // [0] plane start
-                            issue_kd(0);
+                            if (!p.flat) issue_kd(0);                          // flat: a 2-D 3x3 layer = the kd = 1 taps of one plane
                             issue_kd(1);
                             trace_stamp(p, 0, ntrace);                         // [1] kd 0,1 issued
                             if (more) {                                        // barriers of the NEXT plane (already complete
@@ -693,7 +696,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                                 tcgen05_fence_after();
                             }
                             trace_stamp(p, 0, ntrace);                         // [2] next plane's barriers passed
-                            issue_kd(2);
+                            if (!p.flat) issue_kd(2);
                             commit_one(&tfull[buf]);
                             commit_one(&empty[slot]);
                             if (od == nout - 1) {
@@ -1418,7 +1421,7 @@ extern "C" int dmb_b200_debug_set_trace(long long* device_buffer) {   // 3 roles
 static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
                           const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
                           int Cout, float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind,
-                          int relu, int fp16, const float* head_w, float* head_t, void* stream) {
+                          int relu, int fp16, const float* head_w, float* head_t, void* stream, int flat = 0) {
     DMB_REQUIRE(x_hi && w_blob, "conv3d_tc: null input/weights");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "conv3d_tc: non-positive dimension");
     DMB_REQUIRE(kind >= 0 && kind <= 6, "conv3d_tc: kind must be 0/3 (stride 1), 1/4 (stride 2) or 2/5/6 (transposed stride 2)");
@@ -1447,8 +1450,10 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     const int IB = Cin / (8 * cbk), OB = scalar_out ? 1 : Cout / nbo;
     const int CBS = Cin / 8;
 
+    DMB_REQUIRE(!flat || (kind == 3 && D == 1 && !head_t), "conv2d_tc: the flat variant is the stride-1 kernel on a single plane");
     Params p;
     p.trace = g_trace;
+    p.flat = flat;
     p.head_w = head_w;
     p.head_t = head_t;
     const int grid = plan_schedule(p, kind, B, D, H, W);
@@ -1543,6 +1548,18 @@ extern "C" int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, c
                                   int relu, int fp16, void* stream) {
     return conv3d_tc_impl(x_hi, x_lo, Cin, w_blob, w_scale, bias, res_hi, res_lo, y_hi, y_lo, Cout, y_f32, res_f32, B, D, H,
                           W, kind, relu, fp16, nullptr, nullptr, stream);
+}
+
+// 2-D 3x3 / stride 1 / pad 1 convolution (the confidence heads of dmb/modeling/stereo/cmn/cmn.py:29-32:
+// conv_bn_relu(192, 64) on a [B,192,H,W] cost volume) as the stride-1 tcgen05 kernel on ONE depth plane: activations
+// blocked [B][Cin/8][1][H][W][8], weights packed as a 3-D [27][Cin][Cout] tensor whose kd = 0 / 2 taps are zero
+// (pack with kind 3) -- the kernel skips them (9 instead of 27 taps issued per tile).
+extern "C" int dmb_b200_conv2d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale,
+                                  const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo,
+                                  int Cout, int B, int H, int W, int relu, int fp16, void* stream) {
+    DMB_REQUIRE(Cout > 0 && Cout % 32 == 0, "conv2d_tc: Cout=%d must be a multiple of 32", Cout);
+    return conv3d_tc_impl(x_hi, x_lo, Cin, w_blob, w_scale, bias, res_hi, res_lo, y_hi, y_lo, Cout, nullptr, nullptr, B, 1, H,
+                          W, 3, relu, fp16, nullptr, nullptr, stream, 1);
 }
 
 extern "C" int dmb_b200_conv3d_tc_schedule(int kind, int B, int D, int H, int W, int* out) {

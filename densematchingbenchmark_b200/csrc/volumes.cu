@@ -470,6 +470,43 @@ __global__ void __launch_bounds__(256) blocked_to_ncs_kernel(const uint4* __rest
     }
 }
 
+// y[b][s] = sum_c w[c] * x[b][c][s] for a blocked (hi[, lo]) activation: the 1x1 Conv2d(C, 1, bias=False) that ends a
+// confidence head (dmb/modeling/stereo/cmn/cmn.py:31).  One thread per position, C / 8 16-byte loads per plane.
+__global__ void __launch_bounds__(256) blocked_dot_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo,
+                                                          const float* __restrict__ w, float* __restrict__ y, int C, size_t S,
+                                                          size_t total, int fp16) {
+    extern __shared__ float sw[];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) sw[i] = __ldg(w + i);
+    __syncthreads();
+    const int CBS = C / 8;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / S, s_ = i - b * S;
+        float acc = 0.f;
+        for (int cb = 0; cb < CBS; ++cb) {
+            const size_t o = (b * CBS + cb) * S + s_;
+            const uint4 h = __ldg(hi + o);
+            const uint32_t hu[4] = {h.x, h.y, h.z, h.w};
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) unpack2(hu[k], fp16, v[2 * k], v[2 * k + 1]);
+            if (lo) {
+                const uint4 l = __ldg(lo + o);
+                const uint32_t lu[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float a, c2;
+                    unpack2(lu[k], fp16, a, c2);
+                    v[2 * k] += a;
+                    v[2 * k + 1] += c2;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc = fmaf(sw[cb * 8 + e], v[e], acc);
+        }
+        y[i] = acc;
+    }
+}
+
 // cat volume straight into the blocked layout: out [B][2C/8][D][H][W][8] from fp32 NCHW features.
 // One CTA per (b, 8-channel block, y): the source row's 8 channels are split into 16-bit (hi, lo) ONCE -- the left
 // half keeps its own column in registers, the right half stages the converted row in shared memory -- and every
@@ -693,6 +730,16 @@ extern "C" int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, flo
     blocked_to_ncs_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)x_hi, (const uint4*)x_lo, y, C, S,
                                                                          total, fp16 ? 1 : 0);
     return check_launch("blocked_to_ncs_kernel");
+}
+
+extern "C" int dmb_b200_blocked_dot(const void* x_hi, const void* x_lo, const float* w, float* y, int B, int C, int64_t S,
+                                    int fp16, void* stream) {
+    DMB_REQUIRE(x_hi && w && y, "blocked_dot: null pointer");
+    DMB_REQUIRE(B > 0 && C > 0 && S > 0 && C % 8 == 0 && C <= 4096, "blocked_dot: bad dimensions (C %% 8 == 0, C <= 4096)");
+    const size_t total = (size_t)B * (size_t)S;
+    blocked_dot_kernel<<<grid_for(total), 256, (size_t)C * 4, as_stream(stream)>>>((const uint4*)x_hi, (const uint4*)x_lo, w, y, C,
+                                                                                  (size_t)S, total, fp16 ? 1 : 0);
+    return check_launch("blocked_dot_kernel");
 }
 
 extern "C" int dmb_b200_cat_volume_blocked(const float* left, const float* right, void* out_hi, void* out_lo, int B,

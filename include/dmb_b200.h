@@ -190,6 +190,18 @@ int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* 
                        const float* bias, const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout,
                        float* y_f32, const float* res_f32, int B, int D, int H, int W, int kind, int relu, int fp16,
                        void* stream);
+/* 2-D 3x3 / stride 1 / pad 1 convolution on tcgen05 -- the confidence heads' conv_bn_relu(192, 64) on a full-resolution
+ * cost volume (dmb/modeling/stereo/cmn/cmn.py:29-32): the stride-1 kernel (kind 3) on one depth plane with only the
+ * kd = 1 taps issued.  x: blocked [B][Cin/8][1][H][W][8]; w_blob: dmb_b200_conv3d_tc_pack_weights(kind 3) of the 2-D
+ * weight embedded in a [27][Cin][Cout] tensor (kd = 0 / 2 taps zero); other arguments as dmb_b200_conv3d_tc. */
+int dmb_b200_conv2d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale, const float* bias,
+                       const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout, int B, int H, int W,
+                       int relu, int fp16, void* stream);
+/* y[b][s] = sum_c w[c] * x[b][c][s] over a blocked activation [B][C/8][S][8] (hi, optional lo): the 1x1
+ * Conv2d(C, 1, bias=False) closing a confidence head (cmn.py:31).  y: [B][S] float32. */
+int dmb_b200_blocked_dot(const void* x_hi, const void* x_lo, const float* w, float* y, int B, int C, int64_t S, int fp16,
+                         void* stream);
+
 /* Fused classifier head (replaces the nn.Sequential(conv3d_bn_relu(32,32), Conv3d(32,1,3,1,1,bias=False)) of
  * aggregators/PSMNet.py:41-52 / AcfNet.py:43-53): the 32->32 stride-1 layer (w_blob packed for kind 3, BatchNorm
  * folded, bias or NULL) runs on tcgen05; its epilogue does not store the activation a but projects it on the 27 taps

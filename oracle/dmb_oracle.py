@@ -378,6 +378,24 @@ def acf_aggregator(sd, raw_cost, max_disp, prefix="", batch_norm=True, train=Non
 
 
 # --------------------------------------------------------------------------------------
+# confidence measurement network
+# --------------------------------------------------------------------------------------
+def conf_head(sd, prefix, cost):
+    """ConfHead.forward in eval mode (cmn/cmn.py:26-37): conv_bn_relu(in_planes, in_planes // 3, 3x3, bias=False)
+    (layers/basic_layers.py:103-119) then Conv2d(in_planes // 3, 1, 1x1, bias=False); `prefix` ends with 'conf_net.'."""
+    y = F.conv2d(cost, sd[prefix + "0.0.weight"], None, padding=1)
+    y = F.batch_norm(y, sd[prefix + "0.1.running_mean"], sd[prefix + "0.1.running_var"], sd[prefix + "0.1.weight"],
+                     sd[prefix + "0.1.bias"], False, 0.0, BN_EPS)
+    return F.conv2d(F.relu(y), sd[prefix + "1.weight"])
+
+
+def cmn_eval(sd, costs, alpha, beta, prefix="conf_heads."):
+    """Cmn.get_confidence (cmn/cmn.py:57-70): confidence = sigmoid(conf cost), variance = alpha * (1 - conf) + beta."""
+    confs = [torch.sigmoid(conf_head(sd, "%s%d.conf_net." % (prefix, i), c)) for i, c in enumerate(costs)]
+    return confs, [alpha * (1 - c) + beta for c in confs]
+
+
+# --------------------------------------------------------------------------------------
 # disparity regression
 # --------------------------------------------------------------------------------------
 def soft_argmin(cost, max_disp, start_disp=0, dilation=1, alpha=1.0, normalize=True, disp_sample=None):

@@ -298,6 +298,58 @@ def gen_focal_loss():
     print("focal_loss.pt")
 
 
+CMN_CASE = dict(in_planes=192, num=2, alpha=1.0, beta=1.0, B=2, H=10, W=36, seed=17)
+
+
+def cmn_inputs():
+    """Seeded inputs of the Cmn fixture: `num` cost volumes [B,192,H,W] with a wide value range, a ground-truth map with
+    some invalid pixels, and a state dict for reference-layout keys (weights N(0, 0.05), BatchNorm statistics)."""
+    c = CMN_CASE
+    g = torch.Generator().manual_seed(c["seed"])
+    costs = [torch.randn(c["B"], c["in_planes"], c["H"], c["W"], generator=g) * 3.0 for _ in range(c["num"])]
+    gt = torch.rand(c["B"], 1, c["H"], c["W"], generator=g) * 230 - 10
+    sd = {}
+    mid = c["in_planes"] // 3
+    for i in range(c["num"]):
+        p = "conf_heads.%d.conf_net." % i
+        sd[p + "0.0.weight"] = torch.randn(mid, c["in_planes"], 3, 3, generator=g) * 0.05
+        sd[p + "0.1.weight"] = torch.rand(mid, generator=g) + 0.5
+        sd[p + "0.1.bias"] = torch.randn(mid, generator=g) * 0.2
+        sd[p + "0.1.running_mean"] = torch.randn(mid, generator=g) * 0.3
+        sd[p + "0.1.running_var"] = torch.rand(mid, generator=g) + 0.5
+        sd[p + "0.1.num_batches_tracked"] = torch.tensor(3)
+        sd[p + "1.weight"] = torch.randn(1, mid, 1, 1, generator=g) * 0.2
+    return costs, gt, sd
+
+
+def gen_cmn():
+    """The reference's own Cmn (cmn/cmn.py:40-82 + cmn/loss.py + losses/conf_nll_loss.py) in eval and train mode."""
+    from dmb.modeling.stereo.cmn.cmn import Cmn
+    c = CMN_CASE
+    cfg = ref_import.ConfigDict(model=dict(batch_norm=True, cmn=dict(
+        in_planes=c["in_planes"], num=c["num"], alpha=c["alpha"], beta=c["beta"],
+        losses=dict(nll_loss=dict(max_disp=192, weights=(1.0, 0.7), weight=8.0)))), data=dict(sparse=False))
+    costs, gt, sd = cmn_inputs()
+    out = {}
+    m = Cmn(cfg, c["in_planes"], c["num"], c["alpha"], c["beta"])
+    m.load_state_dict(sd)
+    m.eval()
+    with torch.no_grad():
+        cost_vars, confs = m([t.clone() for t in costs], gt)
+    out["eval"] = dict(cost_vars=[t.clone() for t in cost_vars], confs=[t.clone() for t in confs])
+    m.train()
+    xs = [t.clone().requires_grad_(True) for t in costs]
+    cost_vars, losses = m(xs, gt)
+    total = sum(losses.values()) + sum(v.mean() for v in cost_vars)
+    total.backward()
+    out["train"] = dict(losses={k: float(v) for k, v in losses.items()}, cost_vars=[t.detach().clone() for t in cost_vars],
+                        dcost=[grad_summary(x.grad) for x in xs],
+                        grads={k: grad_summary(p.grad) for k, p in m.named_parameters()},
+                        running={k: v.clone() for k, v in m.state_dict().items() if "running_" in k or "num_batches" in k})
+    torch.save(out, os.path.join(OUT, "cmn.pt"))
+    print("cmn.pt", out["train"]["losses"])
+
+
 def gen_epe():
     # the package __init__ chain pulls visualisation deps; load the single file instead
     import importlib.util
@@ -324,3 +376,4 @@ if __name__ == "__main__":
     gen_aggregators()
     gen_train_step()
     gen_focal_loss()
+    gen_cmn()

@@ -82,3 +82,56 @@ def test_focal_loss_rejects_cpu_tensors(P):
     ev = P.StereoFocalLoss(max_disp=8)
     with pytest.raises(Exception):
         ev(torch.zeros(1, 8, 4, 4), torch.ones(1, 1, 4, 4), 1.0)
+
+
+# ---------------------------------------------------------------------------- confidence heads
+def _cmn_cfg(P):
+    from make_golden import CMN_CASE as c
+    return P.ConfigDict(model=dict(batch_norm=True, cmn=dict(
+        in_planes=c["in_planes"], num=c["num"], alpha=c["alpha"], beta=c["beta"],
+        losses=dict(nll_loss=dict(max_disp=192, weights=(1.0, 0.7), weight=8.0)))), data=dict(sparse=False))
+
+
+def test_cmn_eval_vs_reference_golden(P, golden_dir):
+    """Cmn.forward in eval mode (cmn/cmn.py:57-82): confidences and confidence-modulated variances of the reference's
+    own module on seeded cost volumes; ours = flat tcgen05 conv (BatchNorm folded) + blocked dot."""
+    from make_golden import cmn_inputs
+    from densematchingbenchmark_b200.modeling.stereo.cmn import build_cmn
+    rec = torch.load(os.path.join(golden_dir, "cmn.pt"), weights_only=False)["eval"]
+    costs, gt, sd = cmn_inputs()
+    m = build_cmn(_cmn_cfg(P))
+    m.load_state_dict(sd)                                   # the reference's key layout loads unchanged
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        cost_vars, confs = m([t.to(DEV) for t in costs], gt.to(DEV))
+    for got, want in zip(confs, rec["confs"]):
+        assert float((got.cpu() - want).abs().max()) < 2e-5
+    for got, want in zip(cost_vars, rec["cost_vars"]):
+        assert float((got.cpu() - want).abs().max()) < 2e-5
+
+
+def test_cmn_train_vs_reference_golden(P, golden_dir):
+    """Training mode: batch statistics, NLL confidence losses, gradients w.r.t. the cost volumes and every parameter,
+    running-statistic updates -- against the reference module's autograd (fixture summaries)."""
+    from make_golden import cmn_inputs
+    from test_oracle_golden import check_grad_summary
+    from densematchingbenchmark_b200.modeling.stereo.cmn import build_cmn
+    rec = torch.load(os.path.join(golden_dir, "cmn.pt"), weights_only=False)["train"]
+    costs, gt, sd = cmn_inputs()
+    m = build_cmn(_cmn_cfg(P))
+    m.load_state_dict(sd)
+    m = m.to(DEV).train()
+    xs = [t.to(DEV).requires_grad_(True) for t in costs]
+    cost_vars, losses = m(xs, gt.to(DEV))
+    for k, v in rec["losses"].items():
+        assert abs(float(losses[k]) - v) < 2e-4 * max(1.0, abs(v)), (k, float(losses[k]), v)
+    for got, want in zip(cost_vars, rec["cost_vars"]):
+        assert float((got.detach().cpu() - want).abs().max()) < 1e-4
+    (sum(losses.values()) + sum(v.mean() for v in cost_vars)).backward()
+    for x, want in zip(xs, rec["dcost"]):
+        check_grad_summary(x.grad.cpu(), want, 3e-3)
+    for k, p in m.named_parameters():
+        check_grad_summary(p.grad.cpu(), rec["grads"][k], 3e-3)
+    state = m.state_dict()
+    for k, v in rec["running"].items():
+        torch.testing.assert_close(state[k].cpu().to(v.dtype), v, rtol=1e-4, atol=1e-5)

@@ -283,3 +283,23 @@ def test_backbone_train_mode_runs_the_two_views_separately():
         el, er = bb(l, r)
         torch.testing.assert_close(el, twin._forward(l), atol=1e-5, rtol=1e-5)
         torch.testing.assert_close(er, twin._forward(r), atol=1e-5, rtol=1e-5)
+
+
+def test_cmn_mirror_contract(P):
+    """Cmn / ConfHead mirror (cmn/cmn.py:10-93): reference constructor, state-dict keys, and no CPU fallback."""
+    from densematchingbenchmark_b200.modeling.stereo.cmn import build_cmn
+    from densematchingbenchmark_b200 import _cabi
+    cfg = P.ConfigDict(model=dict(batch_norm=True, cmn=dict(in_planes=192, num=3, alpha=1.0, beta=1.0,
+                                                            losses=dict(nll_loss=dict(max_disp=192, weights=(1.0, 0.7, 0.5), weight=8.0)))),
+                       data=dict(sparse=False))
+    m = build_cmn(cfg)
+    keys = set(m.state_dict().keys())
+    for i in range(3):
+        for suffix in ("0.0.weight", "0.1.weight", "0.1.bias", "0.1.running_mean", "0.1.running_var", "0.1.num_batches_tracked",
+                       "1.weight"):
+            assert "conf_heads.%d.conf_net.%s" % (i, suffix) in keys
+    assert tuple(m.conf_heads[0].conf_net[0][0].weight.shape) == (64, 192, 3, 3)
+    with pytest.raises(_cabi.DmbB200Error):
+        m.eval()([torch.zeros(1, 192, 4, 8)] * 3)
+    with pytest.raises(AssertionError):
+        m.get_confidence([torch.zeros(1, 192, 4, 8)])

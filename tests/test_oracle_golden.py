@@ -229,3 +229,15 @@ def test_laplace_disp2prob_oracle_vs_reference(golden_dir):
         inside = ((gt > -2) & (gt < 2)).expand_as(got)
         torch.testing.assert_close(got.sum(1)[inside[:, 0]], torch.ones(int(inside[:, 0].sum())), rtol=1e-6, atol=1e-6)
         assert bool((got[~inside] < 1e-39).all())
+
+
+def test_cmn_eval_matches_reference(golden_dir):
+    """The oracle's restatement of the confidence heads against the reference's own Cmn module (cmn.pt)."""
+    from make_golden import CMN_CASE, cmn_inputs
+    rec = torch.load(os.path.join(golden_dir, "cmn.pt"), weights_only=False)["eval"]
+    costs, gt, sd = cmn_inputs()
+    confs, cost_vars = O.cmn_eval(sd, costs, CMN_CASE["alpha"], CMN_CASE["beta"])
+    for got, want in zip(confs, rec["confs"]):
+        torch.testing.assert_close(got, want, atol=1e-6, rtol=1e-5)
+    for got, want in zip(cost_vars, rec["cost_vars"]):
+        torch.testing.assert_close(got, want, atol=1e-6, rtol=1e-5)
