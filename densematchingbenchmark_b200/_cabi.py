@@ -40,6 +40,7 @@ SIGNATURES = {
     "dmb_b200_cat_volume_blocked": [_P, _P, _P, _P, _I, _I, _I, _I, _IP, _I, _I, _P],
     "dmb_b200_conv3d_tc": [_P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_conv2d_tc": [_P, _P, _I, _P, _F, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
+    "dmb_b200_blocked_add": [_P, _P, _P, _P, _P, _P, c_int64, _I, _P],
     "dmb_b200_blocked_dot": [_P, _P, _P, _P, _I, _I, c_int64, _I, _P],
     "dmb_b200_conv3d_tc_head": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_head_gather": [_P, _P, _P, _I, _I, _I, _I, _P],

@@ -470,6 +470,36 @@ __global__ void __launch_bounds__(256) blocked_to_ncs_kernel(const uint4* __rest
     }
 }
 
+// y = a + b on blocked (hi[, lo]) activations of identical geometry: the skip additions that follow a ReLU and
+// therefore cannot ride in the producing convolution's epilogue (GCAggregator, aggregators/GCNet.py:108-116).
+__global__ void __launch_bounds__(256) blocked_add_kernel(const uint4* __restrict__ a_hi, const uint4* __restrict__ a_lo,
+                                                          const uint4* __restrict__ b_hi, const uint4* __restrict__ b_lo,
+                                                          uint4* __restrict__ y_hi, uint4* __restrict__ y_lo, size_t n, int fp16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        const uint4* src[4] = {a_hi, a_lo, b_hi, b_lo};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (!src[t]) continue;
+            const uint4 q = __ldg(src[t] + i);
+            const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float f0, f1;
+                unpack2(u[k], fp16, f0, f1);
+                v[2 * k] += f0;
+                v[2 * k + 1] += f1;
+            }
+        }
+        uint4 h, l;
+        split8(v, h, l, fp16);
+        y_hi[i] = h;
+        if (y_lo) y_lo[i] = l;
+    }
+}
+
 // y[b][s] = sum_c w[c] * x[b][c][s] for a blocked (hi[, lo]) activation: the 1x1 Conv2d(C, 1, bias=False) that ends a
 // confidence head (dmb/modeling/stereo/cmn/cmn.py:31).  One thread per position, C / 8 16-byte loads per plane.
 __global__ void __launch_bounds__(256) blocked_dot_kernel(const uint4* __restrict__ hi, const uint4* __restrict__ lo,
@@ -730,6 +760,17 @@ extern "C" int dmb_b200_blocked_to_ncdhw(const void* x_hi, const void* x_lo, flo
     blocked_to_ncs_kernel<<<grid_for(total), 256, 0, as_stream(stream)>>>((const uint4*)x_hi, (const uint4*)x_lo, y, C, S,
                                                                          total, fp16 ? 1 : 0);
     return check_launch("blocked_to_ncs_kernel");
+}
+
+extern "C" int dmb_b200_blocked_add(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* y_hi,
+                                    void* y_lo, int64_t n_blocks, int fp16, void* stream) {
+    DMB_REQUIRE(a_hi && b_hi && y_hi && n_blocks > 0, "blocked_add: null pointer / empty tensor");
+    DMB_REQUIRE((a_lo != nullptr) == (b_lo != nullptr) && (a_lo != nullptr) == (y_lo != nullptr),
+                "blocked_add: the three tensors must all be split pairs or all single planes");
+    blocked_add_kernel<<<grid_for((size_t)n_blocks), 256, 0, as_stream(stream)>>>((const uint4*)a_hi, (const uint4*)a_lo,
+                                                                                 (const uint4*)b_hi, (const uint4*)b_lo, (uint4*)y_hi,
+                                                                                 (uint4*)y_lo, (size_t)n_blocks, fp16 ? 1 : 0);
+    return check_launch("blocked_add_kernel");
 }
 
 extern "C" int dmb_b200_blocked_dot(const void* x_hi, const void* x_lo, const float* w, float* y, int B, int C, int64_t S,

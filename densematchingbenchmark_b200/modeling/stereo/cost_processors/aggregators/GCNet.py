@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from ...layers.basic_layers import conv3d_bn_relu, deconv3d_bn_relu, fused_plain_conv3d
+from .....ops.autograd import wants_grad
 
 
 class GCAggregator(nn.Module):
@@ -37,6 +38,9 @@ class GCAggregator(nn.Module):
         self.layer35 = self._make_tlayer(F * 2, F * 2)
         self.layer36 = self._make_tlayer(F * 2, F)
         self.layer37 = nn.ConvTranspose3d(F, 1, kernel_size=3, stride=2, padding=1, output_padding=1)
+        # 'direct': fp32 SIMT kernels; 'tc': tcgen05 (layers 19..36); 'auto': tc when the shape allows
+        self.engine = "auto"
+        self.precision = "fp16x3"
 
     def _make_layer(self, cin, cout, stride=1):
         return conv3d_bn_relu(self.batch_norm, cin, cout, kernel_size=3, stride=stride, padding=1, dilation=1,
@@ -47,6 +51,13 @@ class GCAggregator(nn.Module):
                                 bias=False)
 
     def forward(self, raw_cost):
+        if self.engine != "direct" and not self.training and not wants_grad(raw_cost):
+            from . import tc_engine
+            if tc_engine.gc_shape_ok(self, raw_cost):
+                v = tc_engine.run_gc_tc(self, raw_cost, self.precision)
+                return [fused_plain_conv3d(self.layer37, v).squeeze(dim=1)]
+            if self.engine == "tc":
+                raise RuntimeError("engine='tc' requested but the tcgen05 path does not support this shape/build")
         v18 = raw_cost
         v19 = self.layer19(v18)
         v20 = self.layer20(v19)

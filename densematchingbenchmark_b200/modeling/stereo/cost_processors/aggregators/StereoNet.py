@@ -3,6 +3,7 @@ import torch
 import torch.nn as nn
 
 from ...layers.basic_layers import conv3d_bn_relu, fused_plain_conv3d
+from .....ops.autograd import wants_grad
 
 
 class StereoNetAggregator(nn.Module):
@@ -18,8 +19,17 @@ class StereoNetAggregator(nn.Module):
             for _ in range(num)
         ])
         self.lastconv = nn.Conv3d(32, 1, kernel_size=3, stride=1, padding=1, bias=True)
+        self.engine = "auto"               # 'direct' | 'tc' | 'auto' (tcgen05 when the shape allows)
+        self.precision = "fp16x3"
 
     def forward(self, raw_cost):
+        if self.engine != "direct" and not self.training and not wants_grad(raw_cost):
+            from . import tc_engine
+            if raw_cost.is_cuda and raw_cost.dim() == 5 and raw_cost.shape[1] == self.in_planes == 32 \
+                    and tc_engine.tc_available():
+                return [torch.squeeze(tc_engine.run_stereonet_tc(self, raw_cost, self.precision), 1)]
+            if self.engine == "tc":
+                raise RuntimeError("engine='tc' requested but the tcgen05 path does not support this shape/build")
         for layer in self.classify:
             raw_cost = layer(raw_cost)
         cost = fused_plain_conv3d(self.lastconv, raw_cost)

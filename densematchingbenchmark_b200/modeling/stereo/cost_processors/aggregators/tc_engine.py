@@ -382,3 +382,68 @@ def run_trunk_tc(trunk, raw_cost):
     cost2 = classif_head(trunk.classif2, out2, res_f32=cost1)
     cost3 = classif_head(trunk.classif3, out3, res_f32=cost2)
     return cost1, cost2, cost3
+
+
+# ---- the other GeneralizedStereoModel aggregators on the same kernels --------------------
+def blocked_cat(a, b):
+    """torch.cat([a, b], dim=1) of two Blocked activations: channel blocks are the second-slowest axis of the layout."""
+    if a.dims != b.dims or a.B != b.B or a.fp16 != b.fp16 or a.split != b.split:
+        raise ValueError("blocked_cat: geometry / format mismatch")
+    n = a.dims[0] * a.dims[1] * a.dims[2] * 8
+
+    def cat(x, y):
+        return torch.cat([x.view(a.B, a.C // 8, n), y.view(b.B, b.C // 8, n)], dim=1).reshape(-1)
+
+    return Blocked(cat(a.hi, b.hi), cat(a.lo, b.lo) if a.split else None, a.B, a.C + b.C, a.dims, a.fp16)
+
+
+def blocked_add(a, b):
+    if a.dims != b.dims or a.B != b.B or a.C != b.C or a.fp16 != b.fp16 or a.split != b.split:
+        raise ValueError("blocked_add: geometry / format mismatch")
+    y = Blocked.empty(a.B, a.C, a.dims, a.split, a.fp16, a.hi.device)
+    C.call("dmb_b200_blocked_add", C.ptr(a.hi), C.ptr(a.lo), C.ptr(b.hi), C.ptr(b.lo), C.ptr(y.hi), C.ptr(y.lo),
+           a.hi.numel() // 8, 1 if a.fp16 else 0, C.stream(a.hi.device))
+    return y
+
+
+def gc_shape_ok(agg, raw_cost):
+    """GCAggregator on tcgen05: every channel count a multiple of 32 (in_planes = 64) and four clean halvings."""
+    return (raw_cost.is_cuda and raw_cost.dim() == 5 and agg.in_planes % 64 == 0 and raw_cost.shape[1] == agg.in_planes
+            and all(n % 16 == 0 for n in raw_cost.shape[2:]) and tc_available())
+
+
+def run_gc_tc(agg, raw_cost, precision="fp16x3"):
+    """GCAggregator.forward (aggregators/GCNet.py:73-120) up to layer36 on the tcgen05 kernels (stride-1, stride-2 and
+    transposed 3x3x3 units in blocked 16-bit split pairs; concatenations and post-ReLU skip additions in the blocked
+    layout); returns the float32 NCDHW input of layer37 (a 32 -> 1 transposed convolution: not a tensor-core shape)."""
+    split, fp16 = PRECISIONS[precision]
+    v18 = Blocked.from_ncdhw(raw_cost, split, fp16)
+    v19 = _unit(agg.layer19, v18)
+    v20 = _unit(agg.layer20, v19)
+    v21 = _unit(agg.layer21, blocked_cat(v18, v20))
+    v22 = _unit(agg.layer22, v21)
+    v23 = _unit(agg.layer23, v22)
+    v24 = _unit(agg.layer24, blocked_cat(v21, v23))
+    v25 = _unit(agg.layer25, v24)
+    v26 = _unit(agg.layer26, v25)
+    v27 = _unit(agg.layer27, blocked_cat(v24, v26))
+    v28 = _unit(agg.layer28, v27)
+    v29 = _unit(agg.layer29, v28)
+    v30 = _unit(agg.layer30, blocked_cat(v27, v29))
+    v31 = _unit(agg.layer31, v30)
+    v32 = _unit(agg.layer32, v31)
+    v33 = _unit(agg.layer33, v32)
+    v34 = _unit(agg.layer34, blocked_add(v33, v29))
+    v35 = _unit(agg.layer35, blocked_add(v34, v26))
+    v36 = _unit(agg.layer36, blocked_add(v35, v23))
+    return blocked_add(v36, v20).to_ncdhw()
+
+
+def run_stereonet_tc(agg, raw_cost, precision="fp16x3"):
+    """StereoNetAggregator.forward (aggregators/StereoNet.py:41-55): `num` conv3d_bn_relu(32, 32) units and the
+    Conv3d(32, 1) head, all on the stride-1 tcgen05 kernel; returns [B,1,D,H,W] float32."""
+    split, fp16 = PRECISIONS[precision]
+    x = Blocked.from_ncdhw(raw_cost, split, fp16)
+    for layer in agg.classify:
+        x = _unit(layer, x)
+    return conv_tc(agg.lastconv, x)

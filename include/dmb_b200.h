@@ -197,6 +197,10 @@ int dmb_b200_conv3d_tc(const void* x_hi, const void* x_lo, int Cin, const void* 
 int dmb_b200_conv2d_tc(const void* x_hi, const void* x_lo, int Cin, const void* w_blob, float w_scale, const float* bias,
                        const void* res_hi, const void* res_lo, void* y_hi, void* y_lo, int Cout, int B, int H, int W,
                        int relu, int fp16, void* stream);
+/* y = a + b on blocked 16-bit activations (n_blocks = B * C/8 * D*H*W 16-byte voxel blocks; lo planes all NULL or all
+ * given): the post-ReLU skip additions of GCAggregator (aggregators/GCNet.py:108-116). */
+int dmb_b200_blocked_add(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo, void* y_hi, void* y_lo,
+                         int64_t n_blocks, int fp16, void* stream);
 /* y[b][s] = sum_c w[c] * x[b][c][s] over a blocked activation [B][C/8][S][8] (hi, optional lo): the 1x1
  * Conv2d(C, 1, bias=False) closing a confidence head (cmn.py:31).  y: [B][S] float32. */
 int dmb_b200_blocked_dot(const void* x_hi, const void* x_lo, const float* w, float* y, int B, int C, int64_t S, int fp16,

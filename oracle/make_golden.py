@@ -298,6 +298,38 @@ def gen_focal_loss():
     print("focal_loss.pt")
 
 
+OTHER_AGG_CASES = dict(
+    GCNet=dict(in_planes=64, dims=(16, 16, 32), seed=23, max_disp=32),
+    StereoNet=dict(in_planes=32, dims=(6, 10, 34), seed=29, max_disp=6),
+)
+
+
+def other_agg_input(kind):
+    c = OTHER_AGG_CASES[kind]
+    g = torch.Generator().manual_seed(c["seed"] + 100)
+    return torch.randn(1, c["in_planes"], *c["dims"], generator=g) * 0.5
+
+
+def gen_other_aggregators():
+    """GCAggregator / StereoNetAggregator of the reference itself (aggregators/GCNet.py:7-120, StereoNet.py:9-55) in eval
+    mode with seeded weights (seeded.module_entries on the REFERENCE module): output volumes + an entry checksum."""
+    from dmb.modeling.stereo.cost_processors.aggregators.GCNet import GCAggregator
+    from dmb.modeling.stereo.cost_processors.aggregators.StereoNet import StereoNetAggregator
+    out = {}
+    for kind, cls in (("GCNet", GCAggregator), ("StereoNet", StereoNetAggregator)):
+        c = OTHER_AGG_CASES[kind]
+        m = cls(max_disp=c["max_disp"], in_planes=c["in_planes"], batch_norm=True)
+        entries = seeded.module_entries(m)
+        sd = seeded.seeded_state_dict(entries, seed=c["seed"])
+        m.load_state_dict(sd)
+        m.eval()
+        with torch.no_grad():
+            y = m(other_agg_input(kind))[0]
+        out[kind] = dict(cost=y.clone(), weight_checksum=seeded.checksum(sd), n_entries=len(entries))
+        print("other aggregator", kind, tuple(y.shape), float(y.abs().max()))
+    torch.save(out, os.path.join(OUT, "other_aggregators.pt"))
+
+
 CMN_CASE = dict(in_planes=192, num=2, alpha=1.0, beta=1.0, B=2, H=10, W=36, seed=17)
 
 
@@ -377,3 +409,4 @@ if __name__ == "__main__":
     gen_train_step()
     gen_focal_loss()
     gen_cmn()
+    gen_other_aggregators()

@@ -53,6 +53,24 @@ def aggregator_entries(kind="PSMNet", in_planes=64, prefix=""):
     return e
 
 
+def module_entries(module):
+    """(key, shape, role) list of ANY module made of Conv3d / ConvTranspose3d / BatchNorm3d children, in state-dict
+    order -- the reference's GCAggregator / StereoNetAggregator and our mirrors yield the same list (same keys, same
+    registration order), so one seed gives both the same weights without storing them in a fixture."""
+    e = []
+    for name, m in module.named_modules():
+        p = name + "." if name else ""
+        if isinstance(m, (torch.nn.Conv3d, torch.nn.ConvTranspose3d)):
+            e.append((p + "weight", tuple(m.weight.shape), "conv"))
+            if m.bias is not None:
+                e.append((p + "bias", tuple(m.bias.shape), "bias"))
+        elif isinstance(m, torch.nn.BatchNorm3d):
+            for suffix, role in (("weight", "bn_w"), ("bias", "bn_b"), ("running_mean", "bn_m"), ("running_var", "bn_v")):
+                e.append((p + suffix, (m.num_features,), role))
+            e.append((p + "num_batches_tracked", (), "count"))
+    return e
+
+
 def seeded_state_dict(entries, seed=0, sharpen=1.0):
     """Fill `entries` with seeded values.  Conv weights ~ N(0, 2/fan) (so activations keep an
     O(1) scale through the stack), BN affine/statistics randomised so that folding is
