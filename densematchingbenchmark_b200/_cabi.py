@@ -63,6 +63,12 @@ SIGNATURES = {
     "dmb_b200_upsample_trilinear_backward": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
     "dmb_b200_soft_argmin_backward": [_P, _P, _P, _I, _I, _I, _I, _F, _I, _F, _F, _P, _P],
     "dmb_b200_cat_volume_backward": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
+    "dmb_b200_peer_alloc": [POINTER(c_void_p)],
+    "dmb_b200_peer_free": [_P],
+    "dmb_b200_peer_export": [_P, _P],
+    "dmb_b200_peer_import": [_P, POINTER(c_void_p)],
+    "dmb_b200_peer_close": [_P],
+    "dmb_b200_peer_exchange": [POINTER(c_void_p), _I, _I, _LL, _P, _P, _I, _I, _P],
     "dmb_b200_dif_volume_backward": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
 }
 # entry points that do not return a status code
@@ -73,6 +79,7 @@ OTHER = {
     "dmb_b200_conv3d_tc_weight_bytes": ([_I, _I, _I, _I], c_int64),
     "dmb_b200_conv3d_tc_available": ([], c_int),
     "dmb_b200_sga_set_bidirectional": ([_I], c_int),
+    "dmb_b200_peer_buffer_bytes": ([], c_int64),
     "dmb_b200_conv3d_tc_head_floats": ([_I, _I, _I, _I], c_int64),
 }
 

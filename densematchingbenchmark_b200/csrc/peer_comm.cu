@@ -1,0 +1,146 @@
+// Small-vector exchange between the GPUs of one box over peer memory (NVLink / NVSwitch P2P stores), fused into ONE
+// kernel per exchange: the synchronised-BatchNorm statistics of the data-parallel training step
+// (dmb/apis/train.py:95-97 converts the model to SyncBN; every BatchNorm layer then exchanges 2*C numbers per
+// direction).  Roughly 300 such exchanges per step sit on the critical path; as NCCL collectives each costs a kernel
+// launch on a side stream, two event hops and ~100 us of host-side bookkeeping -- and torch's own SyncBatchNorm adds a
+// host synchronisation per layer (measured: +40 ms on a 56 ms step).  Here every rank writes its vector straight into
+// every peer's receive buffer, publishes a sequence number with a system-scope release store, spins (acquire loads) until
+// all peers' numbers have arrived in ITS OWN buffer, and reduces / gathers locally in a fixed rank order, so all ranks
+// obtain bit-identical results.  No NCCL, no host involvement, the caller's stream.
+//
+// Buffers are plain cudaMalloc allocations shared through CUDA IPC handles (one process per GPU, like the reference's
+// launcher tools/dist_train.sh); the handles travel through torch.distributed once at start-up (utils/dist_utils.py).
+// Layout of a rank's buffer: NSLOT x MAXR regions of SLOT_BYTES, then NSLOT x MAXR 64-bit flags.  Exchange number
+// `seq` uses slot seq % NSLOT; a slot cannot be overwritten before its reader is done because a peer can only be
+// NSLOT exchanges ahead after this rank has itself sent NSLOT - 1 later exchanges, which its stream orders after the
+// read (all exchanges of a rank must be issued on one stream, in the same order on every rank).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dmb {
+namespace peer {
+
+constexpr int MAXR = 8;                    // ranks of one box
+constexpr int NSLOT = 8;
+constexpr int SLOT_BYTES = 8192;           // per (slot, source rank): 2048 floats / 1024 doubles
+constexpr size_t FLAG_OFF = (size_t)NSLOT * MAXR * SLOT_BYTES;
+constexpr size_t BUF_BYTES = FLAG_OFF + (size_t)NSLOT * MAXR * 8;
+
+struct Ptrs {
+    unsigned char* p[MAXR];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// mode 0: gather (dst = [world][nwords] 32-bit words), 1: sum of float64 (nwords / 2 values), 2: sum of float32
+__global__ void __launch_bounds__(256) peer_exchange_kernel(Ptrs pp, int rank, int world, unsigned long long seq,
+                                                            const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                            int nwords, int mode) {
+    const int slot = (int)(seq % NSLOT);
+    const size_t region = ((size_t)slot * MAXR + rank) * SLOT_BYTES;
+    // 1. my vector into every rank's receive region (my own included): peer stores over NVLink
+    for (int p = 0; p < world; ++p) {
+        uint32_t* out = reinterpret_cast<uint32_t*>(pp.p[p] + region);
+        for (int w = threadIdx.x; w < nwords; w += blockDim.x) out[w] = src[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish, 3. wait until every rank's vector has landed in MY buffer
+    if (threadIdx.x < world) {
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(pp.p[threadIdx.x] + FLAG_OFF) + slot * MAXR + rank;
+        st_release_sys(flag, seq);
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(pp.p[rank] + FLAG_OFF) + slot * MAXR + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(mine) < seq) {
+            if (clock64() - t0 > 40000000000LL) __trap();      // ~20 s: a peer died; fail loudly instead of hanging the GPU
+        }
+    }
+    __syncthreads();
+    // 4. combine out of my own buffer, rank order fixed -> identical bits on every rank
+    const unsigned char* base = pp.p[rank] + (size_t)slot * MAXR * SLOT_BYTES;
+    if (mode == 0) {
+        for (int i = threadIdx.x; i < world * nwords; i += blockDim.x) {
+            const int p = i / nwords, w = i - p * nwords;
+            dst[i] = reinterpret_cast<const uint32_t*>(base + (size_t)p * SLOT_BYTES)[w];
+        }
+    } else if (mode == 1) {
+        for (int i = threadIdx.x; i < nwords / 2; i += blockDim.x) {
+            double acc = 0.0;
+            for (int p = 0; p < world; ++p) acc += reinterpret_cast<const double*>(base + (size_t)p * SLOT_BYTES)[i];
+            reinterpret_cast<double*>(dst)[i] = acc;
+        }
+    } else {
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+            float acc = 0.f;
+            for (int p = 0; p < world; ++p) acc += reinterpret_cast<const float*>(base + (size_t)p * SLOT_BYTES)[i];
+            reinterpret_cast<float*>(dst)[i] = acc;
+        }
+    }
+}
+
+}  // namespace peer
+}  // namespace dmb
+
+using namespace dmb;
+using namespace dmb::peer;
+
+extern "C" int64_t dmb_b200_peer_buffer_bytes(void) { return (int64_t)BUF_BYTES; }
+
+// Allocates and zeroes this rank's receive buffer (cudaMalloc: CUDA IPC cannot export pooled / VMM allocations).
+extern "C" int dmb_b200_peer_alloc(void** ptr) {
+    DMB_REQUIRE(ptr, "peer_alloc: null pointer");
+    DMB_CUDA(cudaMalloc(ptr, BUF_BYTES));
+    DMB_CUDA(cudaMemset(*ptr, 0, BUF_BYTES));
+    DMB_CUDA(cudaDeviceSynchronize());
+    return DMB_OK;
+}
+extern "C" int dmb_b200_peer_free(void* ptr) {
+    if (ptr) DMB_CUDA(cudaFree(ptr));
+    return DMB_OK;
+}
+// 64-byte CUDA IPC handle of a buffer from dmb_b200_peer_alloc / the mapping of a peer's handle in this process
+extern "C" int dmb_b200_peer_export(void* ptr, void* handle64) {
+    DMB_REQUIRE(ptr && handle64, "peer_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is expected to be 64 bytes");
+    DMB_CUDA(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), ptr));
+    return DMB_OK;
+}
+extern "C" int dmb_b200_peer_import(const void* handle64, void** ptr) {
+    DMB_REQUIRE(ptr && handle64, "peer_import: null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    DMB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return DMB_OK;
+}
+extern "C" int dmb_b200_peer_close(void* ptr) {
+    if (ptr) DMB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return DMB_OK;
+}
+
+// One exchange.  bufs: HOST array of `world` device pointers (entry `rank` = this rank's own buffer, the others the
+// imported peer mappings); seq: 1, 2, 3, ... identical on every rank; src: nbytes (multiple of 4, <= 8192) on this device;
+// dst: world * nbytes (mode 0, gather) or nbytes (mode 1: float64 sum, mode 2: float32 sum).
+extern "C" int dmb_b200_peer_exchange(void* const* bufs, int rank, int world, long long seq, const void* src, void* dst,
+                                      int nbytes, int mode, void* stream) {
+    DMB_REQUIRE(bufs && src && dst, "peer_exchange: null pointer");
+    DMB_REQUIRE(world >= 1 && world <= MAXR && rank >= 0 && rank < world, "peer_exchange: rank %d / world %d out of range (max %d)", rank, world, MAXR);
+    DMB_REQUIRE(seq >= 1, "peer_exchange: sequence numbers start at 1");
+    DMB_REQUIRE(nbytes > 0 && nbytes <= SLOT_BYTES && nbytes % 4 == 0 && (mode != 1 || nbytes % 8 == 0),
+                "peer_exchange: %d bytes not supported (multiple of 4, at most %d)", nbytes, SLOT_BYTES);
+    DMB_REQUIRE(mode >= 0 && mode <= 2, "peer_exchange: mode must be 0 (gather), 1 (sum f64) or 2 (sum f32)");
+    Ptrs pp;
+    for (int i = 0; i < MAXR; ++i) pp.p[i] = i < world ? reinterpret_cast<unsigned char*>(bufs[i]) : nullptr;
+    for (int i = 0; i < world; ++i) DMB_REQUIRE(pp.p[i], "peer_exchange: buffer of rank %d is NULL", i);
+    peer_exchange_kernel<<<1, 256, 0, as_stream(stream)>>>(pp, rank, world, (unsigned long long)seq,
+                                                           reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst),
+                                                           nbytes / 4, mode);
+    return check_launch("peer_exchange_kernel");
+}

@@ -56,7 +56,9 @@ def _sync_world(group):
 
 
 def _all_reduce_sums(sums, group):
-    dist.all_reduce(sums, group=None if group is True else group)
+    # one peer-memory kernel on the current stream when the ranks share a box (csrc/peer_comm.cu), else NCCL
+    from ..utils.dist_utils import sum_over_ranks_
+    sum_over_ranks_(sums, group)
 
 
 def _dgrad(dz, weight, transposed, ksize, stride, pad, x_dims, dz_blocked=None):

@@ -143,6 +143,227 @@ class GradReducer(object):
         self._handles = []
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Synchronised-BatchNorm statistics over peer memory (csrc/peer_comm.cu) instead of ~300 tiny NCCL collectives per
+# step.  NCCL stays the transport of the one real exchange on the path, the gradient all-reduce.
+# ---------------------------------------------------------------------------------------------------------
+class PeerComm(object):
+    """Per-process-group receive buffers shared through CUDA IPC.  `exchange` is one kernel on the current stream.
+    All ranks must call it in the same order, from one stream."""
+    MAX_BYTES = 8192
+
+    def __init__(self, group=None):
+        import ctypes
+        from .. import _cabi as C
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError("PeerComm covers the GPUs of one box (<= 8 ranks)")
+        lib = C.load()
+        self._C, self._ct = C, ctypes
+        own = ctypes.c_void_p()
+        C.call("dmb_b200_peer_alloc", ctypes.byref(own))
+        self._own = own
+        handle = ctypes.create_string_buffer(64)
+        C.call("dmb_b200_peer_export", own, handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.rank, bytes(handle.raw), torch.cuda.current_device()), group=group)
+        self._bufs = (ctypes.c_void_p * self.world)()
+        self._imported = []
+        for r, raw, _dev in sorted(handles):
+            if r == self.rank:
+                self._bufs[r] = own
+            else:
+                ptr = ctypes.c_void_p()
+                C.call("dmb_b200_peer_import", ctypes.create_string_buffer(raw, 64), ctypes.byref(ptr))
+                self._bufs[r] = ptr
+                self._imported.append(ptr)
+        self.seq = 0
+        dist.barrier(group=group)                   # every buffer is zeroed and mapped before the first exchange
+        self.exchanges = 0
+        _ = lib
+
+    def exchange(self, src, mode):
+        """mode 'gather' -> [world, n]; 'sum' -> same shape as src (float64 or float32).  src: contiguous CUDA tensor
+        of at most 8192 bytes."""
+        C = self._C
+        if not src.is_contiguous():
+            src = src.contiguous()
+        nbytes = src.numel() * src.element_size()
+        if nbytes > self.MAX_BYTES or nbytes % 4:
+            raise ValueError("PeerComm.exchange: %d bytes (multiple of 4, <= %d)" % (nbytes, self.MAX_BYTES))
+        if mode == "gather":
+            dst, m = torch.empty((self.world,) + tuple(src.shape), dtype=src.dtype, device=src.device), 0
+        elif src.dtype == torch.float64:
+            dst, m = torch.empty_like(src), 1
+        elif src.dtype == torch.float32:
+            dst, m = torch.empty_like(src), 2
+        else:
+            raise TypeError("PeerComm.exchange('sum') takes float32 / float64")
+        self.seq += 1
+        self.exchanges += 1
+        C.call("dmb_b200_peer_exchange", self._bufs, self.rank, self.world, self.seq, C.ptr(src), C.ptr(dst), nbytes, m,
+               C.stream(src.device))
+        return dst
+
+    def close(self):
+        C = self._C
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        for ptr in self._imported:
+            C.call("dmb_b200_peer_close", ptr)
+        self._imported = []
+        if self._own is not None:
+            C.call("dmb_b200_peer_free", self._own)
+            self._own = None
+
+
+_PEER_COMMS = {}
+
+
+def peer_comm(group=None, create=True):
+    """The PeerComm of `group` (None = default group), created on first use; None when peer memory is unavailable
+    (single GPU, no CUDA IPC / P2P between the ranks' devices, DMB_B200_PEER_COMM=0): callers then use NCCL."""
+    import os
+    key = id(group) if group not in (None, True) else None
+    if key in _PEER_COMMS:
+        return _PEER_COMMS[key]
+    if not create or os.environ.get("DMB_B200_PEER_COMM", "1") == "0" or not dist.is_initialized():
+        return None
+    g = None if group in (None, True) else group
+    if not torch.cuda.is_available() or dist.get_world_size(g) <= 1 or dist.get_backend(g) != "nccl":
+        _PEER_COMMS[key] = None                       # (gloo / single rank: nothing to set up, the same on every rank)
+        return None
+    comm = None
+    ok = torch.tensor([1], device="cuda")
+    try:
+        if True:
+            comm = PeerComm(g)
+            probe = comm.exchange(torch.full((4,), float(comm.rank + 1), device="cuda", dtype=torch.float64), "sum")
+            want = sum(range(1, comm.world + 1))
+            if not bool((probe == want).all()):
+                raise RuntimeError("peer exchange self-test failed")
+    except Exception as e:                            # noqa: BLE001 -- fall back to NCCL, loudly
+        import warnings
+        warnings.warn("dmb_b200: peer-memory exchange unavailable (%s); SyncBN statistics go through NCCL" % (e,))
+        comm = None
+        ok.zero_()
+    # all ranks must agree (one rank falling back alone would deadlock the others)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=g)
+    if int(ok.item()) == 0:
+        comm = None
+    _PEER_COMMS[key] = comm
+    return comm
+
+
+def close_peer_comms():
+    for comm in _PEER_COMMS.values():
+        if comm is not None:
+            comm.close()
+    _PEER_COMMS.clear()
+
+
+def sum_over_ranks_(t, group=None):
+    """In-place SUM of a small statistics tensor over the ranks: peer-memory kernel when available, else NCCL."""
+    comm = peer_comm(group)
+    if comm is not None and t.numel() * t.element_size() <= PeerComm.MAX_BYTES and t.dtype in (torch.float32, torch.float64):
+        t.copy_(comm.exchange(t, "sum"))
+    else:
+        dist.all_reduce(t, group=None if group in (None, True) else group)
+    return t
+
+
+class _PeerSyncBatchNormFn(torch.autograd.Function):
+    """Synchronised BatchNorm of a torch module (the 2-D backbone) with torch's own statistics / normalisation kernels
+    (batch_norm_stats, batch_norm_gather_stats_with_counts, batch_norm_elemt and their backward twins) and the
+    exchange of the per-rank statistics through `PeerComm` -- the arithmetic of torch.nn.SyncBatchNorm without its
+    all_gather collective and without the host synchronisation that its empty-rank mask costs per layer."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, eps, momentum, group):
+        if not (x.is_contiguous(memory_format=torch.channels_last) or x.is_contiguous()):
+            x = x.contiguous()
+        C_ = x.shape[1]
+        mean, invstd = torch.batch_norm_stats(x, eps)
+        count = torch.full((1,), x.numel() // C_, dtype=mean.dtype, device=mean.device)
+        combined = torch.cat([mean, invstd, count], dim=0)                       # [2C + 1]
+        comm = peer_comm(group)
+        if comm is not None:
+            allc = comm.exchange(combined, "gather")                             # [world, 2C + 1]
+        else:
+            world = dist.get_world_size(None if group in (None, True) else group)
+            allc = torch.empty(world, combined.numel(), dtype=combined.dtype, device=combined.device)
+            dist.all_gather_into_tensor(allc.view(-1), combined, None if group in (None, True) else group)
+        mean_all, invstd_all, count_all = torch.split(allc, C_, dim=1)
+        counts = count_all.reshape(-1)
+        mean, invstd = torch.batch_norm_gather_stats_with_counts(x, mean_all, invstd_all, running_mean, running_var,
+                                                                 momentum, eps, counts)
+        ctx.save_for_backward(x, weight, mean, invstd, counts.to(torch.int32))
+        ctx.group = group
+        return torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not (gy.is_contiguous(memory_format=torch.channels_last) or gy.is_contiguous()):
+            gy = gy.contiguous()
+        x, weight, mean, invstd, counts = ctx.saved_tensors
+        sum_dy, sum_dy_xmu, gw, gb = torch.batch_norm_backward_reduce(gy, x, mean, invstd, weight, ctx.needs_input_grad[0],
+                                                                      ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        gx = None
+        if ctx.needs_input_grad[0]:
+            combined = torch.cat([sum_dy, sum_dy_xmu], dim=0)
+            sum_over_ranks_(combined, ctx.group)
+            sum_dy, sum_dy_xmu = torch.split(combined, sum_dy.shape[0])
+            gx = torch.batch_norm_backward_elemt(gy, x, mean, invstd, weight, sum_dy, sum_dy_xmu, counts)
+        return gx, (gw if ctx.needs_input_grad[1] else None), (gb if ctx.needs_input_grad[2] else None), None, None, None, None, None
+
+
+class PeerSyncBatchNorm(torch.nn.modules.batchnorm._BatchNorm):
+    """BatchNorm over (N, C, ...) whose batch statistics are taken over all ranks of `group`; parameters, buffers and
+    state-dict keys of the BatchNorm it replaces (counterpart of apex.parallel.SyncBatchNorm for the torch parts of
+    the model, dmb/apis/train.py:95-97)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True, group=None):
+        super(PeerSyncBatchNorm, self).__init__(num_features, eps, momentum, affine, track_running_stats)
+        self.group = group
+
+    def _check_input_dim(self, x):
+        if x.dim() < 2:
+            raise ValueError("expected at least 2D input (got {}D input)".format(x.dim()))
+
+    def forward(self, x):
+        world = dist.get_world_size(None if self.group in (None, True) else self.group) if dist.is_initialized() else 1
+        if not self.training or world == 1 or not x.is_cuda:
+            return torch.nn.functional.batch_norm(x, self.running_mean if not self.training or self.track_running_stats else None,
+                                                  self.running_var if not self.training or self.track_running_stats else None,
+                                                  self.weight, self.bias, self.training, self.momentum or 0.0, self.eps)
+        momentum = self.momentum
+        if self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
+            if momentum is None:
+                momentum = 1.0 / float(self.num_batches_tracked)
+        return _PeerSyncBatchNormFn.apply(x, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
+                                          self.running_var if self.track_running_stats else None, self.eps,
+                                          momentum if momentum is not None else 0.0, self.group)
+
+
+def convert_sync_batchnorm(module, group=None):
+    """Replace every torch BatchNorm{1,2,3}d below `module` by a PeerSyncBatchNorm sharing its parameters and buffers
+    (what apex.parallel.convert_syncbn_model / nn.SyncBatchNorm.convert_sync_batchnorm do in the reference's trainer)."""
+    out = module
+    if isinstance(module, torch.nn.modules.batchnorm._BatchNorm) and not isinstance(module, PeerSyncBatchNorm):
+        out = PeerSyncBatchNorm(module.num_features, module.eps, module.momentum, module.affine, module.track_running_stats, group)
+        if module.affine:
+            out.weight, out.bias = module.weight, module.bias
+        out.running_mean, out.running_var, out.num_batches_tracked = module.running_mean, module.running_var, module.num_batches_tracked
+        out.training = module.training
+    for name, child in module.named_children():
+        new = convert_sync_batchnorm(child, group)
+        if new is not child:
+            out.add_module(name, new)
+    return out
+
+
 def enable_sync_batchnorm(module, group=True):
     """Synchronise the batch statistics of every fused conv unit across `group` (True = the default
     group) -- the counterpart of apex.parallel.convert_syncbn_model in dmb/apis/train.py:95-97."""

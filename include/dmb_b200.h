@@ -327,6 +327,26 @@ int dmb_b200_cat_volume_backward(const float* dvol, float* dleft, float* dright,
 int dmb_b200_dif_volume_backward(const float* dvol, float* dleft, float* dright, int B, int C, int H, int W,
                                  const int* disp_idx_host, int D, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Small-vector exchange between the GPUs of one box over peer memory (csrc/peer_comm.cu): the per-layer
+ * statistics of synchronised BatchNorm in data-parallel training (dmb/apis/train.py:95-97, apex
+ * convert_syncbn_model; torch.distributed all-reduce / all-gather of 2*C numbers per BatchNorm layer and direction).
+ * One kernel per exchange on the caller's stream: peer stores into every rank's receive buffer, a system-scope
+ * release / acquire flag per (slot, rank), a local fixed-order reduction.  One process per GPU; buffers are shared
+ * through CUDA IPC handles that the host exchanges once (utils/dist_utils.py:PeerComm).  All ranks must issue the same
+ * sequence of exchanges (seq = 1, 2, 3, ...) on one stream each.
+ * ------------------------------------------------------------------------------------------ */
+int64_t dmb_b200_peer_buffer_bytes(void);
+int dmb_b200_peer_alloc(void** ptr);                             /* this rank's zeroed receive buffer (cudaMalloc) */
+int dmb_b200_peer_free(void* ptr);
+int dmb_b200_peer_export(void* ptr, void* handle64);             /* 64-byte CUDA IPC handle */
+int dmb_b200_peer_import(const void* handle64, void** ptr);      /* map a peer's buffer into this process */
+int dmb_b200_peer_close(void* ptr);
+/* bufs: host array of `world` device pointers (own buffer at index `rank`); src: nbytes (multiple of 4, <= 8192);
+ * mode 0: gather -> dst [world][nbytes]; mode 1: float64 sum -> dst [nbytes]; mode 2: float32 sum -> dst [nbytes] */
+int dmb_b200_peer_exchange(void* const* bufs, int rank, int world, long long seq, const void* src, void* dst, int nbytes,
+                           int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -470,3 +470,72 @@ def test_data_parallel_train_step_two_gpus(P, kind):
     # scaled by 1/world only through the loss definition of the oracle
     close(res[0][4] * 0.5, want["dleft"][0:1], 3e-3, "dleft rank 0")
     assert res[0][5] >= 1                                          # at least one bucket reduced inside backward
+
+
+# ---------------------------------------------------------------------------- peer-memory statistics exchange (2 GPUs)
+def _peer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from densematchingbenchmark_b200.utils import dist_utils as DU
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        comm = DU.peer_comm()
+        assert comm is not None, "peer-memory exchange could not be set up between two GPUs of one box"
+        dev = "cuda:%d" % rank
+        ok = True
+        g = torch.Generator().manual_seed(3)
+        base = [torch.randn(r + 5, 70, generator=g, dtype=torch.float64) for r in range(world)]      # same on every rank
+        for it in range(40):                       # more exchanges than ring slots, varying sizes and modes
+            n = 1 + (it * 7) % 70
+            mine = base[rank][it % (rank + 5), :n].to(dev)
+            want_sum = sum(b[it % (r + 5), :n] for r, b in enumerate(base))
+            got = comm.exchange(mine.contiguous(), "sum").cpu()
+            ok = ok and torch.equal(got, want_sum) if world == 2 else ok and torch.allclose(got, want_sum)
+            got32 = comm.exchange(mine.float().contiguous(), "gather").cpu()
+            ok = ok and all(torch.equal(got32[r], base[r][it % (r + 5), :n].float()) for r in range(world))
+        # synchronised BatchNorm of a torch module == BatchNorm of the concatenated batch in one process
+        torch.manual_seed(0)
+        bn_ref = torch.nn.BatchNorm2d(6).train()
+        bn = DU.convert_sync_batchnorm(torch.nn.Sequential(torch.nn.BatchNorm2d(6)))[0].to(dev).train()
+        assert isinstance(bn, DU.PeerSyncBatchNorm)
+        xs = [torch.randn(3, 6, 5, 7, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
+        xall = torch.cat(xs, 0).requires_grad_(True)
+        yall = bn_ref(xall)
+        gys = [torch.randn(3, 6, 5, 7, generator=torch.Generator().manual_seed(20 + r)) for r in range(world)]
+        yall.backward(torch.cat(gys, 0))
+        x = xs[rank].to(dev).requires_grad_(True)
+        y = bn(x)
+        y.backward(gys[rank].to(dev))
+        sl = slice(3 * rank, 3 * rank + 3)
+        ok = ok and torch.allclose(y.detach().cpu(), yall.detach()[sl], atol=1e-5, rtol=1e-5)
+        ok = ok and torch.allclose(x.grad.cpu(), xall.grad[sl], atol=1e-5, rtol=1e-4)
+        ok = ok and torch.allclose(bn.running_mean.cpu(), bn_ref.running_mean, atol=1e-6, rtol=1e-5)
+        ok = ok and torch.allclose(bn.running_var.cpu(), bn_ref.running_var, atol=1e-6, rtol=1e-5)
+        q.put((rank, bool(ok), comm.exchanges))
+        DU.close_peer_comms()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_exchange_and_sync_batchnorm_two_gpus(P):
+    """csrc/peer_comm.cu between two processes / two GPUs: exact sums and gathers over 80 exchanges (ring-slot reuse),
+    and PeerSyncBatchNorm forward / backward / running statistics against single-process BatchNorm of the joint batch."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29650 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_peer_worker, args=(rk, 2, port, q)) for rk in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    assert res[0][2] >= 80

@@ -34,7 +34,7 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
     import torch.distributed as dist
     import densematchingbenchmark_b200 as P
     from densematchingbenchmark_b200 import _cabi
-    from densematchingbenchmark_b200.utils.dist_utils import GradReducer, enable_sync_batchnorm
+    from densematchingbenchmark_b200.utils.dist_utils import GradReducer, enable_sync_batchnorm, peer_comm
     from densematchingbenchmark_b200.modeling.stereo.backbones.PSMNet import PSMNetBackbone
     from densematchingbenchmark_b200.modeling.stereo.layers.basic_layers import FusedConvUnit
     from densematchingbenchmark_b200.modeling.stereo.losses.stereo_focal_loss import StereoFocalLoss
@@ -60,7 +60,9 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
     if synced:
         n_bn = enable_sync_batchnorm(proc)
         if bb is not None and sync_backbone_bn:                      # dmb/apis/train.py:95-97 converts the WHOLE model
-            bb = torch.nn.SyncBatchNorm.convert_sync_batchnorm(bb)
+            from densematchingbenchmark_b200.utils.dist_utils import convert_sync_batchnorm
+            bb = convert_sync_batchnorm(bb)                          # (torch's own SyncBatchNorm synchronises with the
+            #                                                          host once per layer: +40 ms on this step)
     params = list(proc.parameters()) + (list(bb.parameters()) if bb is not None else [])
     opt = torch.optim.RMSprop(params, lr=1e-3)                       # configs/PSMNet/scene_flow.py:134
     reducer = GradReducer(params, bucket_mb=bucket_mb) if world > 1 else None
@@ -145,9 +147,16 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
         "backbone_sync_bn": bool(synced and bb is not None and sync_backbone_bn),
         "backbone": "torch autograd (cuDNN), outside the hot path" if bb is not None else "none (synthetic features)",
         "collective": ("NCCL all-reduce (mean) of all gradients, %d buckets of <= %.0f MB issued from inside backward; "
-                       "SyncBN = all-reduce of 2*C fp64 channel sums per BatchNorm layer and direction"
-                       % (len(reducer.buckets), bucket_mb)) if reducer is not None else "none (1 GPU)",
-        "nccl_bytes_per_step": (int(grad_bytes + (2 * 2 * 8 * bn_channels if synced else 0)) if world > 1 else 0),
+                       "SyncBN statistics (2*C numbers per BatchNorm layer and direction): %s"
+                       % (len(reducer.buckets), bucket_mb,
+                          ("one peer-memory kernel per exchange over NVLink P2P stores (csrc/peer_comm.cu), %d exchanges per step"
+                           % (peer_comm(create=False).exchanges // max(1, steps + warmup)))
+                          if (synced and peer_comm(create=False) is not None) else "NCCL all-reduce per layer"))
+                      if reducer is not None else "none (1 GPU)",
+        "nccl_bytes_per_step": (int(grad_bytes + (2 * 2 * 8 * bn_channels
+                                                   if (synced and peer_comm(create=False) is None) else 0)) if world > 1 else 0),
+        "peer_exchanges_per_step": (peer_comm(create=False).exchanges // max(1, steps + warmup)
+                                    if (world > 1 and peer_comm(create=False) is not None) else 0),
         "buckets_reduced_inside_backward": (reducer.launched_early // max(1, steps + warmup) if reducer is not None else 0),
         "library_launches_per_step": (_cabi.launch_count() - n0) // steps,
         "loss": float(total), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
