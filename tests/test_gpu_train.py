@@ -429,9 +429,11 @@ def _ddp_worker(rank, world, port, kind, q):
         sl = slice(rank, rank + 1)                      # one pair per rank
         proc, loss, disps, dl, dr, red = run_train_step(pkg, kind, sd, l[sl], r[sl], gt[sl], TRAIN_CASE,
                                                         device="cuda:%d" % rank, sync=True, reducer=True)
-        grads = {k: p.grad.cpu() for k, p in proc.aggregator.named_parameters()}
-        running = {k: v.cpu() for k, v in proc.aggregator.state_dict().items() if "running_" in k}
-        q.put((rank, float(loss), grads, running, dl.cpu(), red.launched_early))
+        # numpy arrays travel through the queue by value (torch tensors go through a file-descriptor hand-over that
+        # needs the sender alive when the parent un-pickles: a race with this process's exit)
+        grads = {k: p.grad.cpu().numpy() for k, p in proc.aggregator.named_parameters()}
+        running = {k: v.cpu().numpy() for k, v in proc.aggregator.state_dict().items() if "running_" in k}
+        q.put((rank, float(loss), grads, running, dl.cpu().numpy(), red.launched_early))
     finally:
         dist.destroy_process_group()
 
@@ -454,6 +456,8 @@ def test_data_parallel_train_step_two_gpus(P, kind):
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
+    res = [(r[0], r[1], {k: torch.from_numpy(v) for k, v in r[2].items()}, {k: torch.from_numpy(v) for k, v in r[3].items()},
+            torch.from_numpy(r[4]), r[5]) for r in res]
     sd = seeded.seeded_state_dict(seeded.aggregator_entries(kind, 64), seed=TRAIN_CASE["seed"])
     l, r, gt = train_inputs()
     want = O.train_step(sd, l, r, gt, TRAIN_CASE["max_disp"], kind, shards=2)

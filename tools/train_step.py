@@ -41,6 +41,12 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
 
     device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
     torch.backends.cudnn.benchmark = True
+
+    def exchanges():
+        c = peer_comm(create=False)
+        return c.exchanges if c is not None else 0
+
+    ex0 = exchanges()
     cfg = P.ConfigDict(model=dict(
         batch_norm=True,
         cost_processor=dict(type="Concatenation",
@@ -150,13 +156,12 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
                        "SyncBN statistics (2*C numbers per BatchNorm layer and direction): %s"
                        % (len(reducer.buckets), bucket_mb,
                           ("one peer-memory kernel per exchange over NVLink P2P stores (csrc/peer_comm.cu), %d exchanges per step"
-                           % (peer_comm(create=False).exchanges // max(1, steps + warmup)))
+                           % ((exchanges() - ex0) // max(1, steps + warmup)))
                           if (synced and peer_comm(create=False) is not None) else "NCCL all-reduce per layer"))
                       if reducer is not None else "none (1 GPU)",
         "nccl_bytes_per_step": (int(grad_bytes + (2 * 2 * 8 * bn_channels
                                                    if (synced and peer_comm(create=False) is None) else 0)) if world > 1 else 0),
-        "peer_exchanges_per_step": (peer_comm(create=False).exchanges // max(1, steps + warmup)
-                                    if (world > 1 and peer_comm(create=False) is not None) else 0),
+        "peer_exchanges_per_step": (exchanges() - ex0) // max(1, steps + warmup),
         "buckets_reduced_inside_backward": (reducer.launched_early // max(1, steps + warmup) if reducer is not None else 0),
         "library_launches_per_step": (_cabi.launch_count() - n0) // steps,
         "loss": float(total), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
@@ -196,6 +201,11 @@ def main():
             print(json.dumps(res))
     finally:
         if world > 1:
+            try:
+                from densematchingbenchmark_b200.utils.dist_utils import close_peer_comms
+                close_peer_comms()
+            except Exception:
+                pass
             dist.destroy_process_group()
 
 
