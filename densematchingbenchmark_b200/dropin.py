@@ -45,4 +45,13 @@ def install_into_dmb(dmb_module_name="dmb"):
         replaced["losses"] = ["StereoFocalLoss"]
     except Exception:
         pass
+    # confidence measurement network: GeneralizedStereoModel.__init__ calls the module-level name `build_cmn`
+    # (dmb/modeling/stereo/models/general_stereo_model.py:8,36-38)
+    try:
+        ref_gsm = importlib.import_module(dmb_module_name + ".modeling.stereo.models.general_stereo_model")
+        from .modeling.stereo.cmn import build_cmn
+        ref_gsm.build_cmn = build_cmn
+        replaced["cmn"] = ["build_cmn"]
+    except Exception:
+        pass
     return replaced

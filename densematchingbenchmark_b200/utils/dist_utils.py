@@ -159,29 +159,37 @@ class PeerComm(object):
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > 8:
             raise RuntimeError("PeerComm covers the GPUs of one box (<= 8 ranks)")
-        lib = C.load()
         self._C, self._ct = C, ctypes
-        own = ctypes.c_void_p()
-        C.call("dmb_b200_peer_alloc", ctypes.byref(own))
-        self._own = own
-        handle = ctypes.create_string_buffer(64)
-        C.call("dmb_b200_peer_export", own, handle)
-        handles = [None] * self.world
-        dist.all_gather_object(handles, (self.rank, bytes(handle.raw), torch.cuda.current_device()), group=group)
+        self._own, self._imported, self.seq, self.exchanges = None, [], 0, 0
         self._bufs = (ctypes.c_void_p * self.world)()
-        self._imported = []
-        for r, raw, _dev in sorted(handles):
-            if r == self.rank:
-                self._bufs[r] = own
-            else:
-                ptr = ctypes.c_void_p()
-                C.call("dmb_b200_peer_import", ctypes.create_string_buffer(raw, 64), ctypes.byref(ptr))
-                self._bufs[r] = ptr
-                self._imported.append(ptr)
-        self.seq = 0
-        dist.barrier(group=group)                   # every buffer is zeroed and mapped before the first exchange
-        self.exchanges = 0
-        _ = lib
+        # phase 1 (local, then one collective every rank reaches): allocate, export, gather the handles
+        handle = ctypes.create_string_buffer(64)
+        err = None
+        try:
+            own = ctypes.c_void_p()
+            C.call("dmb_b200_peer_alloc", ctypes.byref(own))
+            self._own = own
+            C.call("dmb_b200_peer_export", own, handle)
+        except Exception as e:                        # noqa: BLE001
+            err = e
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (self.rank, bytes(handle.raw) if err is None else None), group=group)
+        # phase 2 (local): map the peers' buffers; the caller (peer_comm) agrees on success across ranks before anybody
+        # launches an exchange -- a rank that failed here must not leave the others spinning on its flags
+        try:
+            if err is not None or any(h[1] is None for h in handles):
+                raise RuntimeError("a rank could not allocate / export its receive buffer: %s" % (err,))
+            for r, raw in sorted(handles):
+                if r == self.rank:
+                    self._bufs[r] = self._own
+                else:
+                    ptr = ctypes.c_void_p()
+                    C.call("dmb_b200_peer_import", ctypes.create_string_buffer(raw, 64), ctypes.byref(ptr))
+                    self._bufs[r] = ptr
+                    self._imported.append(ptr)
+            self.error = None
+        except Exception as e:                        # noqa: BLE001
+            self.error = e
 
     def exchange(self, src, mode):
         """mode 'gather' -> [world, n]; 'sum' -> same shape as src (float64 or float32).  src: contiguous CUDA tensor
@@ -206,10 +214,11 @@ class PeerComm(object):
                C.stream(src.device))
         return dst
 
-    def close(self):
+    def close(self, collective=True):
         C = self._C
         torch.cuda.synchronize()
-        dist.barrier(group=self.group)
+        if collective:
+            dist.barrier(group=self.group)
         for ptr in self._imported:
             C.call("dmb_b200_peer_close", ptr)
         self._imported = []
@@ -231,27 +240,22 @@ def peer_comm(group=None, create=True):
     if not create or os.environ.get("DMB_B200_PEER_COMM", "1") == "0" or not dist.is_initialized():
         return None
     g = None if group in (None, True) else group
-    if not torch.cuda.is_available() or dist.get_world_size(g) <= 1 or dist.get_backend(g) != "nccl":
+    if not torch.cuda.is_available() or not (1 < dist.get_world_size(g) <= 8) or dist.get_backend(g) != "nccl":
         _PEER_COMMS[key] = None                       # (gloo / single rank: nothing to set up, the same on every rank)
         return None
-    comm = None
-    ok = torch.tensor([1], device="cuda")
-    try:
-        if True:
-            comm = PeerComm(g)
-            probe = comm.exchange(torch.full((4,), float(comm.rank + 1), device="cuda", dtype=torch.float64), "sum")
-            want = sum(range(1, comm.world + 1))
-            if not bool((probe == want).all()):
-                raise RuntimeError("peer exchange self-test failed")
-    except Exception as e:                            # noqa: BLE001 -- fall back to NCCL, loudly
+    comm = PeerComm(g)                                # collective inside: every rank gets here
+    ok = torch.tensor([0 if comm.error is not None else 1], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=g)      # all ranks must agree: one rank falling back alone would
+    if int(ok.item()) == 0:                                 # leave the others spinning on its flags
         import warnings
-        warnings.warn("dmb_b200: peer-memory exchange unavailable (%s); SyncBN statistics go through NCCL" % (e,))
+        warnings.warn("dmb_b200: peer-memory exchange unavailable (%s); SyncBN statistics go through NCCL" % (comm.error,))
+        comm.close(collective=False)
         comm = None
-        ok.zero_()
-    # all ranks must agree (one rank falling back alone would deadlock the others)
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=g)
-    if int(ok.item()) == 0:
-        comm = None
+    else:
+        dist.barrier(group=g)                         # every buffer is zeroed and mapped before the first exchange
+        probe = comm.exchange(torch.full((4,), float(comm.rank + 1), device="cuda", dtype=torch.float64), "sum")
+        if not bool((probe == sum(range(1, comm.world + 1))).all()):
+            raise RuntimeError("dmb_b200: peer-memory exchange self-test failed")
     _PEER_COMMS[key] = comm
     return comm
 
