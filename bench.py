@@ -556,8 +556,9 @@ def run_ours(args, rank, world, local_rank):
     achieved_tflops = 2.0 * macs / (agg_ms * 1e-3) / 1e12
     cat_elem = 4 if (passes == 3 or not on_tc) else 2      # fp32 volume, (hi,lo) pair or a single 16-bit plane
     cat_bytes = B * (2 * 32 * H4 * W4 * 4 + 64 * D4 * H4 * W4 * cat_elem)
-    roofline = {"bound": "tensor", "kernel": "conv3d_tc_kernel: the PSMAggregator trunk = 68 launches of it (+3 head_gather) per step, timed as one span "
-                                                   "(CUDA events around the aggregator segment of the captured graph)",
+    roofline = {"bound": "tensor", "kernel": "conv3d_tc_kernel: the PSMAggregator trunk = 77 launches of it (kinds 3 / 4 / 6-8 and the fused heads) + 3 "
+                                                   "head_gather per step, timed as one span (CUDA events around the aggregator segment "
+                                                   "of the captured graph)",
                 "achieved": achieved_tflops, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved_tflops / pk["tflops_sustained"], "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "algorithmic_flops_per_step": 2.0 * macs, "mma_passes": passes,

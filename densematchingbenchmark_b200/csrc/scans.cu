@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dmb {
 
@@ -991,6 +992,92 @@ __global__ void __launch_bounds__(256, 2) lga_r2_rot_kernel(const float* __restr
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// The same kernel with the NP-plane tile (+ halo) of every stage fetched by ONE 4-D TMA box load issued by one thread
+// (zero fill outside the image and beyond the last depth plane comes from the tensor map): the cp.async staging above
+// costs ~175 integer / address instructions per thread and stage -- 40 % of all instructions executed
+// (profiles/r2_ncu_full_ops.txt) -- in a kernel that is issue bound.
+__device__ __forceinline__ void tma_load_4d_f32(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+template <int NP>
+__global__ void __launch_bounds__(256, 2) lga_r2_tma_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ guid,
+                                                            float* __restrict__ out, int D, int H, int W) {
+    constexpr int TX = 32, TY = 8, PW = TX + 4, PH = TY + 4, NE = PH * PW;   // 432 tile elements per plane
+    __shared__ __align__(128) float tile[2][NP * NE];
+    __shared__ uint64_t full[2];
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int px = x0 + tx, py = y0 + ty;
+    const int b = blockIdx.z;
+    const bool inside = px < W && py < H;
+    const size_t plane = (size_t)H * W;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int nst = (D + 1 + NP - 1) / NP;         // planes 0 .. D (plane D is all zeros: it completes out(D-1))
+    auto issue = [&](int st) {
+        if (tid == 0 && st < nst) {
+            mbar_expect_tx(&full[st & 1], NP * NE * 4);
+            tma_load_4d_f32(tile[st & 1], &xmap, &full[st & 1], x0 - 2, y0 - 2, st * NP, b);
+        }
+    };
+    issue(0);
+    issue(1);
+    float w[75];
+    {
+        const float* gb = guid + (size_t)b * 75 * plane + (size_t)(inside ? py : 0) * W + (inside ? px : 0);
+        float nrm = 0.f;
+#pragma unroll
+        for (int i = 0; i < 75; ++i) {
+            w[i] = __ldg(gb + (size_t)i * plane);
+            nrm += fabsf(w[i]);
+        }
+        nrm = fmaxf(nrm, 1e-12f);
+#pragma unroll
+        for (int i = 0; i < 75; ++i) w[i] = w[i] / nrm;
+    }
+    float* ob = out + (size_t)b * D * plane + (size_t)py * W + px;
+    float pa = 0.f, pb = 0.f, ca = 0.f, cb = 0.f, na = 0.f, nb = 0.f;   // sums for out(d-1), out(d), out(d+1)
+    for (int st = 0; st < nst; ++st) {
+        mbar_wait(&full[st & 1], (st >> 1) & 1);
+        const float* tb0 = &tile[st & 1][ty * PW + tx];
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+            const float* tb = tb0 + pl * NE;
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int i = ky * 5 + kx;
+                    const float v = tb[ky * PW + kx];
+                    if (i & 1) {
+                        cb = fmaf(w[i], v, cb);
+                        nb = fmaf(w[25 + i], v, nb);
+                        pb = fmaf(w[50 + i], v, pb);
+                    } else {
+                        ca = fmaf(w[i], v, ca);
+                        na = fmaf(w[25 + i], v, na);
+                        pa = fmaf(w[50 + i], v, pa);
+                    }
+                }
+            const int d = st * NP + pl;            // the plane just consumed: out(d-1) is complete
+            if (inside && d >= 1 && d <= D) st_cs_f(ob + (size_t)(d - 1) * plane, pa + pb);
+            pa = ca; pb = cb; ca = na; cb = nb; na = 0.f; nb = 0.f;
+        }
+        __syncthreads();                           // everybody is done with buffer st & 1
+        issue(st + 2);
+    }
+}
+
 // any radius: weights re-read per use (slow path, kept for generality)
 __global__ void __launch_bounds__(256) lga_generic_kernel(const float* __restrict__ x, const float* __restrict__ guid,
                                                           float* __restrict__ out, int D, int H, int W, int radius) {
@@ -1236,9 +1323,24 @@ extern "C" int dmb_b200_lga(const float* x, const float* guidance, float* out, i
         static int rot_mode = -1;                  // DMB_B200_LGA_ROT=0: the register-plane kernel (A/B)
         if (rot_mode < 0) {
             const char* e = getenv("DMB_B200_LGA_ROT");
-            rot_mode = (e && e[0] == '0') ? 0 : 1;
+            rot_mode = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);      // 2: the cp.async-staged variant
         }
         if (rot_mode) {
+            // TMA-staged variant when the tensor map can be built (16-byte aligned base and row pitch, sm_100 driver)
+            if (rot_mode != 2 && W % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && tc::device_ok()) {
+                CUtensorMap xmap;
+                const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
+                const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)D * H * W * 4};
+                const cuuint32_t box[4] = {36, 12, 4, 1};
+                const cuuint32_t estr[4] = {1, 1, 1, 1};
+                const CUresult r = tc::encode_fn()(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box,
+                                                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r == CUDA_SUCCESS) {
+                    lga_r2_tma_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(xmap, guidance, out, D, H, W);
+                    return check_launch("lga_r2_tma_kernel");
+                }
+            }
             lga_r2_rot_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(x, guidance, out, D, H, W);
             return check_launch("lga_r2_rot_kernel");
         }
