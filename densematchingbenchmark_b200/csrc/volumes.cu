@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) gwc_rows_kernel(const float* __restrict__
 // ALIGNED (d0 % 4 == 0): the right-row window is fetched as three aligned 16-byte loads starting one column earlier
 // -- the 11 scalar loads at a 16-byte lane stride were 4-way bank conflicted (44 + 4 shared-memory wavefronts per 32
 // FMAs: the kernel sat at the shared-memory bandwidth, 0.45 of the HBM peak; now 12 + 4).
-template <int CPG, bool ALIGNED>   // channels per group (0 = runtime)
+template <int CPG, bool ALIGNED, bool CORR = false>   // channels per group (0 = runtime); CORR: correlation1d_cost epilogue
 __global__ void __launch_bounds__(256) gwc_rows_unit_kernel(const float* __restrict__ left, const float* __restrict__ right,
                                                             float* __restrict__ out, int C, int G, int H, int W, int D,
                                                             int d0, int PAD, float scale, float slope, int reverse) {
@@ -311,9 +311,11 @@ __global__ void __launch_bounds__(256) gwc_rows_unit_kernel(const float* __restr
             const int k = kg * 8 + kk;
             if (k < D) {
                 float4 o = make_float4(acc[kk][0] * inv, acc[kk][1] * inv, acc[kk][2] * inv, acc[kk][3] * inv);
-                o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
-                o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
-                st_cs_f4(out_row0 + (size_t)(reverse ? D - 1 - k : k) * plane + x, o);
+                if (CORR) {                      // (compile-time: the GwcNet volume pays nothing for it)
+                    o.x = o.x > 0.f ? o.x : o.x * slope; o.y = o.y > 0.f ? o.y : o.y * slope;
+                    o.z = o.z > 0.f ? o.z : o.z * slope; o.w = o.w > 0.f ? o.w : o.w * slope;
+                }
+                st_cs_f4(out_row0 + (size_t)((CORR && reverse) ? D - 1 - k : k) * plane + x, o);
             }
         }
     }
@@ -698,13 +700,13 @@ extern "C" int dmb_b200_corr1d_volume(const float* left, const float* right, flo
     const int PAD = ((D - 1 + 8 + 8) + 3) & ~3;
     const size_t smem_u = (size_t)C * (W + W + 2 * PAD) * 4;
     DMB_REQUIRE(smem_u <= 200 * 1024, "corr1d_volume: %d feature rows of width %d do not fit shared memory", C, W);
-    DMB_CUDA(cudaFuncSetAttribute(gwc_rows_unit_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
+    DMB_CUDA(cudaFuncSetAttribute(gwc_rows_unit_kernel<0, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_u));
     const int units = (W / 4) * ((D + 7) / 8), sweeps = (units + 255) / 256;
     int uthreads = (((units + sweeps - 1) / sweeps + 31) / 32) * 32;
     if (uthreads > 256) uthreads = 256;
     dim3 grid(H, 1, B);
-    gwc_rows_unit_kernel<0, true><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, 1, H, W, D, 0, PAD, 1.0f,
-                                                                                  negative_slope, 1);
+    gwc_rows_unit_kernel<0, true, true><<<grid, uthreads, smem_u, as_stream(stream)>>>(left, right, out, C, 1, H, W, D, 0, PAD,
+                                                                                        1.0f, negative_slope, 1);
     return check_launch("gwc_rows_unit_kernel<corr1d>");
 }
 
