@@ -1007,7 +1007,10 @@ __device__ __forceinline__ void tma_load_4d_f32(void* smem_dst, const CUtensorMa
 template <int NP>
 __global__ void __launch_bounds__(256, 2) lga_r2_tma_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ guid,
                                                             float* __restrict__ out, int D, int H, int W) {
-    constexpr int TX = 32, TY = 8, PW = TX + 4, PH = TY + 4, NE = PH * PW;   // 432 tile elements per plane
+    // The TMA unit traps (illegal instruction) on a box whose innermost start coordinate is not a multiple of 16 bytes
+    // (measured: tools/tma_f32_probe.cu, fp32 c0 = -2 / 30 / 62 fault, 0 / -4 do not), so the halo tile starts at
+    // x0 - 4 and is 40 floats wide; the 5 x 5 window of column tx begins at tile column tx + 2.
+    constexpr int TX = 32, TY = 8, PW = TX + 8, PH = TY + 4, NE = PH * PW;   // 480 tile elements per plane
     __shared__ __align__(128) float tile[2][NP * NE];
     __shared__ uint64_t full[2];
     const int tid = threadIdx.x;
@@ -1024,10 +1027,11 @@ __global__ void __launch_bounds__(256, 2) lga_r2_tma_kernel(const __grid_constan
     }
     __syncthreads();
     const int nst = (D + 1 + NP - 1) / NP;         // planes 0 .. D (plane D is all zeros: it completes out(D-1))
-    auto issue = [&](int st) {
+    const CUtensorMap* const mp = &xmap;
+    auto issue = [&, mp](int st) {
         if (tid == 0 && st < nst) {
             mbar_expect_tx(&full[st & 1], NP * NE * 4);
-            tma_load_4d_f32(tile[st & 1], &xmap, &full[st & 1], x0 - 2, y0 - 2, st * NP, b);
+            tma_load_4d_f32(tile[st & 1], mp, &full[st & 1], x0 - 4, y0 - 2, st * NP, b);
         }
     };
     issue(0);
@@ -1049,7 +1053,7 @@ __global__ void __launch_bounds__(256, 2) lga_r2_tma_kernel(const __grid_constan
     float pa = 0.f, pb = 0.f, ca = 0.f, cb = 0.f, na = 0.f, nb = 0.f;   // sums for out(d-1), out(d), out(d+1)
     for (int st = 0; st < nst; ++st) {
         mbar_wait(&full[st & 1], (st >> 1) & 1);
-        const float* tb0 = &tile[st & 1][ty * PW + tx];
+        const float* tb0 = &tile[st & 1][ty * PW + tx + 2];
 #pragma unroll
         for (int pl = 0; pl < NP; ++pl) {
             const float* tb = tb0 + pl * NE;
@@ -1331,7 +1335,7 @@ extern "C" int dmb_b200_lga(const float* x, const float* guidance, float* out, i
                 CUtensorMap xmap;
                 const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)B};
                 const cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)D * H * W * 4};
-                const cuuint32_t box[4] = {36, 12, 4, 1};
+                const cuuint32_t box[4] = {40, 12, 4, 1};        // x0 - 4 .. x0 + 35: 16-byte aligned start
                 const cuuint32_t estr[4] = {1, 1, 1, 1};
                 const CUresult r = tc::encode_fn()(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box,
                                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -390,7 +390,9 @@ def test_sga_vs_oracle(P, shape, bidir):
     torch.testing.assert_close(got, O.sga(x, gd), atol=1e-5, rtol=1e-4)
 
 
-@pytest.mark.parametrize("shape", [(1, 6, 5, 7, 2), (2, 12, 9, 33, 2), (1, 5, 6, 8, 1)])
+@pytest.mark.parametrize("shape", [(1, 6, 5, 7, 2), (2, 12, 9, 33, 2), (1, 5, 6, 8, 1),
+                                   # W % 4 == 0: the TMA-staged radius-2 kernel (ragged tiles, D not a multiple of the 4-plane stage)
+                                   (1, 9, 12, 40, 2), (2, 7, 9, 36, 2), (1, 4, 20, 64, 2)])
 def test_lga_vs_oracle(P, shape):
     from densematchingbenchmark_b200.ops import LGA
     B, D, H, W, radius = shape
