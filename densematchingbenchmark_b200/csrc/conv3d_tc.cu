@@ -225,8 +225,15 @@ struct Smem {
     static constexpr int NST = nstage_of(KIND);
     static constexpr int PLANES_OFF = W_BYTES;
     static constexpr int BAR_OFF = PLANES_OFF + NST * STAGE_BYTES;
-    static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [27][32] fp32 head weights (KIND 3 head variant)
-    static constexpr int TOTAL = HEAD_OFF + (KIND == 3 ? TAPS * NB * 4 : 0);
+    static constexpr int TOTAL = BAR_OFF + 256;
+    // fused classifier head (KIND 3 head variant): the 32 -> 1 convolution's 27 taps as the N rows of a second B operand
+    // ([hi rows | lo rows] x 32 channels, K-major core matrices) and the activated tile as a second A operand
+    // (128 voxels x 32 channels, hi plane then lo plane), both written by the CTA's own threads
+    static constexpr int HEAD_B_OFF = TOTAL;
+    static constexpr int HEAD_B_BYTES = 4 * NB * 16;               // one 16-bit plane of [32 taps][32 channels]: 2048
+    static constexpr int HEAD_A_OFF = HEAD_B_OFF + 2 * HEAD_B_BYTES;
+    static constexpr int HEAD_A_BYTES = 4 * 128 * 16;              // one 16-bit plane of [128 voxels][32 channels]: 8192
+    static constexpr int TOTAL_HEAD = HEAD_A_OFF + (SPLIT ? 2 : 1) * HEAD_A_BYTES;
     static constexpr uint32_t LBO_B = ROWS * 16;
     static constexpr uint32_t SBO_B = 128;
     // The tensor core adds each K=16 partial product into the fp32 accumulator with truncation
@@ -240,8 +247,11 @@ struct Smem {
     static constexpr int ACC_COLS =
         is_t64(KIND) ? 2 * CLS_COLS
                      : ((KIND == 2 || KIND == 5) ? 4 * CLS_COLS : ((KIND == 3 || KIND == 4) ? ROWS : (SPLIT ? 3 * 64 + 32 : 3 * 32)));
+    static constexpr int HEAD_P_COL = 2 * ACC_COLS;                // TMEM columns of the head's 27 (32) tap projections
     static_assert(2 * ACC_COLS <= TMEM_COLS, "accumulators exceed TMEM");
+    static_assert(KIND != 3 || HEAD_P_COL + NB <= TMEM_COLS, "no TMEM columns left for the head projections");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget exceeded");
+    static_assert(KIND != 3 || TOTAL_HEAD <= 227 * 1024, "shared memory budget exceeded (head variant)");
 };
 
 struct Item {
@@ -319,6 +329,12 @@ __device__ __forceinline__ void store_voxel(const Params& p, float (&v)[NB], con
 
 // fused classifier head.  The 32 -> 1 3x3x3 convolution that follows the 32 -> 32 layer is
 //     out(d, h, w) = sum_{kd,kh,kw} P[kd][kh][kw](d + kd - 1, h + kh - 1, w + kw - 1),   P[tap](voxel) = <a(voxel), head_w[tap]>.
+// P is itself a small GEMM -- [128 voxels] x [32 channels] x [27 taps] per tile and plane -- and runs on the tensor core:
+// the epilogue writes the activated tile (bias, ReLU, 16-bit split) to shared memory as a second A operand, the MMA
+// warp multiplies it with the head weights (six N = 32 MMAs into 32 more TMEM columns) in the middle of issuing the
+// NEXT plane, and the epilogue reads the 27 projections back.  (Round 1-2 computed P with 864 FMAs per voxel in the
+// epilogue, every weight a shared-memory load: the LSU pipe, not the tensor core, bounded the kernel -- 281 us per
+// head against 51 us for the same layer without the head.)
 // The epilogue thread of a tile position marches along depth, so the kd sum is local to it:
 //     Q[kh][kw](d) = P[0][kh][kw](d - 1) + P[1][kh][kw](d) + P[2][kh][kw](d + 1)
 // is accumulated in registers across consecutive planes and NINE planes are stored instead of 27 tap planes (the
@@ -330,38 +346,18 @@ __device__ __forceinline__ size_t head_batch_stride(const Params& p) {
     return ((size_t)9 * p.Do + (size_t)18 * p.nseg) * p.Ho * p.Wo;
 }
 template <int K0, int K1>
-__device__ __forceinline__ void head_step(const Params& p, float (&v)[NB], const float (&bias)[NB],
-                                          const float4* __restrict__ hw, const Item& it, int d, int h, int w,
-                                          float (&qprev)[5], float (&qcur)[5]) {
+__device__ __forceinline__ void head_step(const Params& p, const uint32_t (&pr)[NB], float inv_scale, const Item& it, int d,
+                                          int h, int w, float (&qprev)[5], float (&qcur)[5]) {
     const size_t hw_sz = (size_t)p.Ho * p.Wo;
     float* base = p.head_t + (size_t)it.b * head_batch_stride(p) + (size_t)h * p.Wo + w;
     const bool first = d == it.d0;
     float* spill_lo = base + ((size_t)9 * p.Do + (size_t)(it.d0 / p.seg_len) * 18) * hw_sz;
 #pragma unroll
-    for (int c = 0; c < NB; ++c) {
-        v[c] += bias[c];
-        if (p.relu) v[c] = fmaxf(v[c], 0.f);
-    }
-#pragma unroll
     for (int khw = K0; khw < K1; ++khw) {
-        // three taps (kd = 0, 1, 2) x four partial sums = 12 independent FMA chains
-        float acc[3][4];
-#pragma unroll
-        for (int kd = 0; kd < 3; ++kd) acc[kd][0] = acc[kd][1] = acc[kd][2] = acc[kd][3] = 0.f;
-#pragma unroll
-        for (int c4 = 0; c4 < NB / 4; ++c4) {
-#pragma unroll
-            for (int kd = 0; kd < 3; ++kd) {
-                const float4 wv = hw[(kd * 9 + khw) * (NB / 4) + c4];
-                acc[kd][0] = fmaf(v[4 * c4 + 0], wv.x, acc[kd][0]);
-                acc[kd][1] = fmaf(v[4 * c4 + 1], wv.y, acc[kd][1]);
-                acc[kd][2] = fmaf(v[4 * c4 + 2], wv.z, acc[kd][2]);
-                acc[kd][3] = fmaf(v[4 * c4 + 3], wv.w, acc[kd][3]);
-            }
-        }
-        const float p0 = (acc[0][0] + acc[0][1]) + (acc[0][2] + acc[0][3]);
-        const float p1 = (acc[1][0] + acc[1][1]) + (acc[1][2] + acc[1][3]);
-        const float p2 = (acc[2][0] + acc[2][1]) + (acc[2][2] + acc[2][3]);
+        // P[kd][khw] of this voxel: columns kd * 9 + khw of the head MMA's accumulator
+        const float p0 = __uint_as_float(pr[khw]) * inv_scale;
+        const float p1 = __uint_as_float(pr[9 + khw]) * inv_scale;
+        const float p2 = __uint_as_float(pr[18 + khw]) * inv_scale;
         const int k = khw - K0;
         if (first) {
             spill_lo[(size_t)khw * hw_sz] = p2;                                  // contribution to Q(d0 - 1)
@@ -454,9 +450,49 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    uint64_t* a2full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF + 112);   // head: activated tile written (8 warps)
+    uint64_t* pfull = a2full + 1;                                               // head: projections complete (commit)
+    float head_inv_scale = 1.f;
     if (HEAD) {
-        float* hw = reinterpret_cast<float*>(smem + S::HEAD_OFF);
-        for (int i = threadIdx.x; i < TAPS * NB; i += blockDim.x) hw[i] = __ldg(p.head_w + i);
+        // head weights -> second B operand.  fp16 planes: a power-of-two scale keeps the lo parts normal numbers.
+        float* red = reinterpret_cast<float*>(smem + S::BAR_OFF + 192);
+        float mx = 0.f;
+        for (int i = threadIdx.x; i < TAPS * NB; i += blockDim.x) mx = fmaxf(mx, fabsf(__ldg(p.head_w + i)));
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+        int e = 0;                                 // scale = 2^e with max|w| * 2^e in [2^9, 2^10)
+        if (FP16 && mx > 0.f && mx < 3.0e38f) {
+            int ex;
+            frexpf(mx, &ex);                       // mx = f * 2^ex, f in [0.5, 1)
+            e = max(-40, min(40, 10 - ex));
+        }
+        const float scale = exp2f((float)e);
+        head_inv_scale = exp2f((float)-e);
+        unsigned char* b2 = smem + S::HEAD_B_OFF;
+        for (int i = threadIdx.x; i < NB * NB; i += blockDim.x) {
+            const int n = i >> 5, k = i & 31;      // n: tap (27 real rows, 5 zero rows), k: channel
+            const float wv = n < TAPS ? __ldg(p.head_w + n * NB + k) * scale : 0.f;
+            const int off = (k >> 3) * (NB * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+            uint16_t hi16, lo16;
+            if (FP16) {
+                const __half hi = __float2half_rn(wv);
+                const __half lo = __float2half_rn(wv - __half2float(hi));
+                hi16 = __half_as_ushort(hi);
+                lo16 = __half_as_ushort(lo);
+            } else {
+                __nv_bfloat16 hi, lo;
+                split_bf16(wv, hi, lo);
+                hi16 = __bfloat16_as_ushort(hi);
+                lo16 = __bfloat16_as_ushort(lo);
+            }
+            *reinterpret_cast<uint16_t*>(b2 + off) = hi16;
+            *reinterpret_cast<uint16_t*>(b2 + S::HEAD_B_BYTES + off) = lo16;
+        }
+        fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core's operand reads
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSTAGE; ++i) {
@@ -468,6 +504,10 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             mbar_init(&tempty[i], EPI_WARPS);
         }
         mbar_init(wbar, 1);
+        if (HEAD) {
+            mbar_init(a2full, EPI_WARPS);
+            mbar_init(pfull, 1);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {   // TMEM allocation (whole warp, .sync.aligned)
@@ -572,6 +612,43 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             };
             uint32_t n_base = 0, t_base = 0;
             uint32_t ntrace = 0;
+            // fused head: the projection MMAs of plane t are issued (by the elected lane) in the middle of plane t + 1's
+            // issue stream -- by then the epilogue has written plane t's activated tile -- and after the last plane
+            uint32_t head_planes = 0;              // planes issued so far (warp-uniform)
+            auto issue_head = [&](uint32_t t_head) {
+                constexpr uint32_t idesc_head = make_idesc(NB, FP16 ? 0u : 1u);
+                constexpr uint32_t LBO_A2 = 128 * 16, LBO_B2 = NB * 16;
+                constexpr uint32_t hiw = desc_hi(128);
+                const uint32_t a2 = desc_lo(smem_u32(smem + S::HEAD_A_OFF), LBO_A2);
+                const uint32_t b2 = desc_lo(smem_u32(smem + S::HEAD_B_OFF), LBO_B2);
+                const uint32_t pacc = tmem_base + S::HEAD_P_COL;
+                mbar_wait(a2full, t_head & 1);
+                tcgen05_fence_after();
+                if (SPLIT) {                       // small terms first: lo * Whi, hi * Wlo, then hi * Whi
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint32_t ao = (2 * kk * LBO_A2) >> 4, bo = (2 * kk * LBO_B2) >> 4;
+                        if (kk == 0)
+                            mma_f16_ss<false>(pacc, a2 + (S::HEAD_A_BYTES >> 4) + ao, hiw, b2 + bo, hiw, idesc_head);
+                        else
+                            mma_f16_ss<true>(pacc, a2 + (S::HEAD_A_BYTES >> 4) + ao, hiw, b2 + bo, hiw, idesc_head);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const uint32_t ao = (2 * kk * LBO_A2) >> 4, bo = (2 * kk * LBO_B2) >> 4;
+                        mma_f16_ss<true>(pacc, a2 + ao, hiw, b2 + (S::HEAD_B_BYTES >> 4) + bo, hiw, idesc_head);
+                    }
+                }
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const uint32_t ao = (2 * kk * LBO_A2) >> 4, bo = (2 * kk * LBO_B2) >> 4;
+                    if (!SPLIT && kk == 0)
+                        mma_f16_ss<false>(pacc, a2 + ao, hiw, b2 + bo, hiw, idesc_head);
+                    else
+                        mma_f16_ss<true>(pacc, a2 + ao, hiw, b2 + bo, hiw, idesc_head);
+                }
+                commit_one(pfull);
+            };
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const Item it = decode_item<th_of(KIND), twstep_of(KIND)>(p, item);
                 const int nout = it.d1 - it.d0;
@@ -696,6 +773,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                                 tcgen05_fence_after();
                             }
                             trace_stamp(p, 0, ntrace);                         // [2] next plane's barriers passed
+                            if (HEAD && head_planes > 0) issue_head(head_planes - 1);
                             if (!p.flat) issue_kd(2);
                             commit_one(&tfull[buf]);
                             commit_one(&empty[slot]);
@@ -711,6 +789,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                             ++waited;
                         }
                         if (++slot == NSTAGE) { slot = 0; phase ^= 1; }
+                        ++head_planes;
                     }
                     n_base += nout + 2;
                     t_base += nout;
@@ -977,6 +1056,10 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     t_base += 2 * nout;
                 }
             }
+            if (HEAD && head_planes > 0) {         // the last plane's projections
+                if (elect_one()) issue_head(head_planes - 1);
+                __syncwarp();
+            }
         }
         __syncwarp();
     } else {
@@ -986,8 +1069,9 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         // row / column of this thread's accumulator row inside the M tile
         const int hl = KIND == 3 ? (m >> 5) : (KIND == 4 ? (m >> 4) : (m >> 3));
         const int wl = KIND == 3 ? (m & 31) : (KIND == 4 ? (m & 15) : (m & 7));
-        // KIND 3/4 (not the fused-head variant): two warps per TMEM lane quarter, each owns 16 of the 32 channels
-        constexpr bool HALVES = (KIND == 3 || KIND == 4) && !HEAD;
+        // KIND 3/4: two warps per TMEM lane quarter, each owns 16 of the 32 channels (fused head: of the activated tile;
+        // the nine (kh, kw) Q sums are then split 5 / 4 between the two)
+        constexpr bool HALVES = (KIND == 3 || KIND == 4);
         const int half = HALVES ? ((warp - 2) >> 2) : 0;
         float bias[NB];
 #pragma unroll
@@ -1028,23 +1112,7 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * S::ACC_COLS;
                     float v[NB];
                     // out(w) = D'[w-1][kw=0] + D'[w][kw=1] + D'[w+1][kw=2]; lanes of one tile row are adjacent
-                    if constexpr (HEAD) {
-                        uint32_t r0[32], r1[32];
-#pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            tmem_ld32(taddr + kw * NB, r0);
-                            if (SPLIT) tmem_ld32(taddr + 3 * NB + kw * NB, r1);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int c = 0; c < NB; ++c) {
-                                float sv = __uint_as_float(r0[c]);
-                                if (SPLIT) sv += __uint_as_float(r1[c]);
-                                if (kw == 0) v[c] = __shfl_up_sync(0xffffffffu, sv, 1);
-                                else if (kw == 1) v[c] += sv;
-                                else v[c] = (v[c] + __shfl_down_sync(0xffffffffu, sv, 1)) * p.acc_scale;
-                            }
-                        }
-                    } else {
+                    {
                         uint32_t r0[16], r1[16];
 #pragma unroll
                         for (int c = 16; c < NB; ++c) v[c] = 0.f;
@@ -1068,14 +1136,47 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                     if (tracer) trace_stamp(p, 1, ntrace);                     // [2] TMEM drained, buffer released
                     ++t;
-                    if (valid) {
-                        if constexpr (HEAD) {
-                            // two warps per TMEM lane quarter: warps 2..5 project taps 0..13, warps 6..9 taps 14..26
+                    if constexpr (HEAD) {
+                        // activated tile (this warp's 16 channels of its 32 voxels) -> second A operand: K-major core
+                        // matrices, row m of channel block cb at cb * 2048 + m * 16; hi plane, then lo plane
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            v[c] += bias[c];
+                            if (p.relu) v[c] = fmaxf(v[c], 0.f);
+                        }
+                        unsigned char* a2 = smem + S::HEAD_A_OFF + (half * 2) * (128 * 16) + m * 16;
+#pragma unroll
+                        for (int cb = 0; cb < 2; ++cb) {
+                            float hi[8], lo[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const float x = v[cb * 8 + e];
+                                hi[e] = round16<FP16>(x);
+                                lo[e] = x - hi[e];
+                            }
+                            *reinterpret_cast<uint4*>(a2 + cb * (128 * 16)) =
+                                make_uint4(pack2<FP16>(hi[0], hi[1]), pack2<FP16>(hi[2], hi[3]), pack2<FP16>(hi[4], hi[5]), pack2<FP16>(hi[6], hi[7]));
+                            if (SPLIT)
+                                *reinterpret_cast<uint4*>(a2 + S::HEAD_A_BYTES + cb * (128 * 16)) =
+                                    make_uint4(pack2<FP16>(lo[0], lo[1]), pack2<FP16>(lo[2], lo[3]), pack2<FP16>(lo[4], lo[5]), pack2<FP16>(lo[6], lo[7]));
+                        }
+                        fence_proxy_async();                   // generic-proxy stores -> the tensor core's operand reads
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(a2full);
+                        // the 27 projections of this thread's voxel, once the MMA warp has run the head MMAs of the plane
+                        mbar_wait(pfull, (t - 1) & 1);
+                        tcgen05_fence_after();
+                        uint32_t pr[NB];
+                        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + S::HEAD_P_COL, pr);
+                        tmem_ld_wait();
+                        tcgen05_fence_before();                // ordered before the next plane's a2full arrival
+                        if (valid) {
                             // two warps per TMEM lane quarter: warps 2..5 own (kh, kw) 0..4, warps 6..9 own 5..8
-                            const float4* hw4 = reinterpret_cast<const float4*>(smem + S::HEAD_OFF);
-                            if (warp < 6) head_step<0, 5>(p, v, bias, hw4, it, d, h, w, hq_prev, hq_cur);
-                            else head_step<5, 9>(p, v, bias, hw4, it, d, h, w, hq_prev, hq_cur);
-                        } else if (!(p.y_f32 && half)) {       // single-channel output: the first half's warp writes it
+                            if (warp < 6) head_step<0, 5>(p, pr, head_inv_scale, it, d, h, w, hq_prev, hq_cur);
+                            else head_step<5, 9>(p, pr, head_inv_scale, it, d, h, w, hq_prev, hq_cur);
+                        }
+                    } else if (valid) {
+                        if (!(p.y_f32 && half)) {              // single-channel output: the first half's warp writes it
                             store_voxel<FP16, 2>(p, v, bias, it.b, d, h, w, half * 2);
                         }
                     }
@@ -1308,7 +1409,7 @@ static int launch_pass(const Maps& maps, const Params& p, int grid, void* stream
 
 template <bool SPLIT, bool FP16>
 static int launch_head(const Maps& maps, const Params& p, int grid, void* stream) {
-    const size_t smem = Smem<3, SPLIT>::TOTAL;
+    const size_t smem = Smem<3, SPLIT>::TOTAL_HEAD;
     DMB_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<3, SPLIT, FP16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conv3d_tc_kernel<3, SPLIT, FP16, true><<<grid, nthreads_of(3, true), smem, as_stream(stream)>>>(maps, p);
     return check_launch("conv3d_tc_kernel<head>");
