@@ -528,10 +528,10 @@ def run_ours(args, rank, world, local_rank):
             # the same step with the torch backbone's BatchNorm left per-rank (the hot path's own BatchNorm layers stay
             # synchronised): separates the cost of the ~220 backbone exchanges, whose lock-step with a launch-bound
             # torch section is the residual limiter of the fully synchronised step
-            alt = run_train_bench("AcfNet", 4, 256, 512, MAX_DISP, steps=tsteps, warmup=2, sync_bn=True, backbone=True,
+            alt_train = run_train_bench("AcfNet", 4, 256, 512, MAX_DISP, steps=tsteps, warmup=2, sync_bn=True, backbone=True,
                                   bucket_mb=4.0, loss="config", rank=rank, world=world, device=device,
                                   sync_backbone_bn=False)
-            extra["train"]["variant_backbone_bn_per_rank"] = {k: alt[k] for k in ("ms_per_step", "pairs_per_s", "segments_ms",
+            extra["train"]["variant_backbone_bn_per_rank"] = {k: alt_train[k] for k in ("ms_per_step", "pairs_per_s", "segments_ms",
                                                                                   "peer_exchanges_per_step")}
             torch.cuda.empty_cache()
     if rank != 0:

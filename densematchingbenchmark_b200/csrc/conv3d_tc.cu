@@ -388,20 +388,20 @@ __device__ __forceinline__ void head_finish(const Params& p, const Item& it, int
 __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restrict__ T, const float* __restrict__ res,
                                                           float* __restrict__ y, int B, int D, int H, int W, int seg_len,
                                                           int nseg) {
-    const size_t hw_sz = (size_t)H * W, vol = (size_t)D * hw_sz;
-    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i >= (size_t)B * vol) return;
-    const int b = (int)(i / vol);
-    size_t r = i - (size_t)b * vol;
-    const int d = (int)(r / hw_sz);
-    r -= (size_t)d * hw_sz;
-    const int h = (int)(r / W), w = (int)(r - (size_t)h * W);
+    // grid: (plane positions / 256, D, B) -- no 64-bit index divisions (round 2's flat index cost three per thread)
+    const int hw = H * W;
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= hw) return;
+    const int d = blockIdx.y, b = blockIdx.z;
+    const int h = r / W, w = r - h * W;
+    const size_t hw_sz = (size_t)hw;
     const float* tb = T + (size_t)b * ((size_t)9 * D + (size_t)18 * nseg) * hw_sz;
     const int seg = d / seg_len;
     const int seg_end = min(D, (seg + 1) * seg_len);
     // spill planes to add: previous segment's "hi" at the first plane, next segment's "lo" at the last plane
     const float* sp_a = (d == seg * seg_len && seg > 0) ? tb + ((size_t)9 * D + (size_t)(seg - 1) * 18 + 9) * hw_sz : nullptr;
     const float* sp_b = (d == seg_end - 1 && seg + 1 < nseg) ? tb + ((size_t)9 * D + (size_t)(seg + 1) * 18) * hw_sz : nullptr;
+    const float* qd = tb + (size_t)d * hw_sz + r;          // Q[0][d] at this position; plane khw is khw * D planes further
     float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
@@ -412,14 +412,15 @@ __global__ void __launch_bounds__(256) head_gather_kernel(const float* __restric
             const int ww = w + kw - 1;
             if (ww < 0 || ww >= W) continue;
             const int khw = kh * 3 + kw;
-            const size_t o = (size_t)hh * W + ww;
-            float q = __ldg(tb + ((size_t)khw * D + d) * hw_sz + o);
-            if (sp_a) q += __ldg(sp_a + (size_t)khw * hw_sz + o);
-            if (sp_b) q += __ldg(sp_b + (size_t)khw * hw_sz + o);
+            const int o = (kh - 1) * W + (kw - 1);
+            float q = __ldg(qd + (size_t)khw * D * hw_sz + o);
+            if (sp_a) q += __ldg(sp_a + (size_t)khw * hw_sz + r + o);
+            if (sp_b) q += __ldg(sp_b + (size_t)khw * hw_sz + r + o);
             acc[kh] += q;
         }
     }
     float o = (acc[0] + acc[1]) + acc[2];
+    const size_t i = ((size_t)b * D + d) * hw_sz + r;
     if (res) o += __ldg(res + i);
     y[i] = o;
 }
@@ -1696,7 +1697,8 @@ extern "C" int dmb_b200_head_gather(const float* head_t, const float* res, float
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "head_gather: non-positive dimension");
     Params p;                                      // the same static schedule the head launch used
     plan_schedule(p, 3, B, D, H, W);
-    const int64_t n = (int64_t)B * D * H * W;
-    head_gather_kernel<<<(unsigned)cdiv(n, 256), 256, 0, as_stream(stream)>>>(head_t, res, y, B, D, H, W, p.seg_len, p.nseg);
+    DMB_REQUIRE(D <= 65535 && B <= 65535 && (int64_t)H * W < (int64_t)1 << 30, "head_gather: dimension too large");
+    const dim3 grid((unsigned)cdiv((int64_t)H * W, 256), (unsigned)D, (unsigned)B);
+    head_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(head_t, res, y, B, D, H, W, p.seg_len, p.nseg);
     return check_launch("head_gather_kernel");
 }

@@ -25,7 +25,8 @@ constexpr int MAXR = 8;                    // ranks of one box
 constexpr int NSLOT = 8;
 constexpr int SLOT_BYTES = 8192;           // per (slot, source rank): 2048 floats / 1024 doubles
 constexpr size_t FLAG_OFF = (size_t)NSLOT * MAXR * SLOT_BYTES;
-constexpr size_t BUF_BYTES = FLAG_OFF + (size_t)NSLOT * MAXR * 8;
+constexpr size_t SEQ_OFF = FLAG_OFF + (size_t)NSLOT * MAXR * 8;   // this rank's own exchange counter (seq == 0 mode)
+constexpr size_t BUF_BYTES = SEQ_OFF + 64;
 
 struct Ptrs {
     unsigned char* p[MAXR];
@@ -41,9 +42,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 }
 
 // mode 0: gather (dst = [world][nwords] 32-bit words), 1: sum of float64 (nwords / 2 values), 2: sum of float32
-__global__ void __launch_bounds__(256) peer_exchange_kernel(Ptrs pp, int rank, int world, unsigned long long seq,
+// seq_arg == 0: the sequence number is the rank's own device-side counter (+1 per exchange, kept in its buffer), so that
+// the launch carries no per-call host state and can be captured in a CUDA graph and replayed; every rank issues the
+// same exchanges in the same order, so the counters agree.
+__global__ void __launch_bounds__(256) peer_exchange_kernel(Ptrs pp, int rank, int world, unsigned long long seq_arg,
                                                             const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
                                                             int nwords, int mode) {
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(pp.p[rank] + SEQ_OFF);
+    const unsigned long long seq = seq_arg ? seq_arg : *counter + 1;       // (launches of one stream are serialised)
     const int slot = (int)(seq % NSLOT);
     const size_t region = ((size_t)slot * MAXR + rank) * SLOT_BYTES;
     // 1. my vector into every rank's receive region (my own included): peer stores over NVLink
@@ -64,6 +70,7 @@ __global__ void __launch_bounds__(256) peer_exchange_kernel(Ptrs pp, int rank, i
         }
     }
     __syncthreads();
+    if (threadIdx.x == 0 && !seq_arg) *counter = seq;          // every thread has read the counter before the barriers above
     // 4. combine out of my own buffer, rank order fixed -> identical bits on every rank
     const unsigned char* base = pp.p[rank] + (size_t)slot * MAXR * SLOT_BYTES;
     if (mode == 0) {
@@ -126,13 +133,14 @@ extern "C" int dmb_b200_peer_close(void* ptr) {
 }
 
 // One exchange.  bufs: HOST array of `world` device pointers (entry `rank` = this rank's own buffer, the others the
-// imported peer mappings); seq: 1, 2, 3, ... identical on every rank; src: nbytes (multiple of 4, <= 8192) on this device;
+// imported peer mappings); seq: 0 = the device-side counter of the buffer (graph-capturable; do not mix with explicit
+// numbers on one set of buffers), or 1, 2, 3, ... identical on every rank; src: nbytes (multiple of 4, <= 8192) on this device;
 // dst: world * nbytes (mode 0, gather) or nbytes (mode 1: float64 sum, mode 2: float32 sum).
 extern "C" int dmb_b200_peer_exchange(void* const* bufs, int rank, int world, long long seq, const void* src, void* dst,
                                       int nbytes, int mode, void* stream) {
     DMB_REQUIRE(bufs && src && dst, "peer_exchange: null pointer");
     DMB_REQUIRE(world >= 1 && world <= MAXR && rank >= 0 && rank < world, "peer_exchange: rank %d / world %d out of range (max %d)", rank, world, MAXR);
-    DMB_REQUIRE(seq >= 1, "peer_exchange: sequence numbers start at 1");
+    DMB_REQUIRE(seq >= 0, "peer_exchange: sequence number must be 0 (device-side counter) or 1, 2, 3, ...");
     DMB_REQUIRE(nbytes > 0 && nbytes <= SLOT_BYTES && nbytes % 4 == 0 && (mode != 1 || nbytes % 8 == 0),
                 "peer_exchange: %d bytes not supported (multiple of 4, at most %d)", nbytes, SLOT_BYTES);
     DMB_REQUIRE(mode >= 0 && mode <= 2, "peer_exchange: mode must be 0 (gather), 1 (sum f64) or 2 (sum f32)");
@@ -143,4 +151,13 @@ extern "C" int dmb_b200_peer_exchange(void* const* bufs, int rank, int world, lo
                                                            reinterpret_cast<const uint32_t*>(src), reinterpret_cast<uint32_t*>(dst),
                                                            nbytes / 4, mode);
     return check_launch("peer_exchange_kernel");
+}
+
+extern "C" int dmb_b200_peer_count(const void* own_buf, long long* count) {
+    DMB_REQUIRE(own_buf && count, "peer_count: null pointer");
+    unsigned long long c = 0;
+    DMB_CUDA(cudaDeviceSynchronize());
+    DMB_CUDA(cudaMemcpy(&c, reinterpret_cast<const unsigned char*>(own_buf) + SEQ_OFF, 8, cudaMemcpyDeviceToHost));
+    *count = (long long)c;
+    return DMB_OK;
 }

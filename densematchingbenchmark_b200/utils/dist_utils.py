@@ -208,11 +208,18 @@ class PeerComm(object):
             dst, m = torch.empty_like(src), 2
         else:
             raise TypeError("PeerComm.exchange('sum') takes float32 / float64")
-        self.seq += 1
-        self.exchanges += 1
-        C.call("dmb_b200_peer_exchange", self._bufs, self.rank, self.world, self.seq, C.ptr(src), C.ptr(dst), nbytes, m,
+        self.exchanges += 1                       # (launches issued from Python: a replayed CUDA graph is not counted)
+        # sequence number 0: the buffer's own device-side counter, so the launch can sit inside a captured graph
+        C.call("dmb_b200_peer_exchange", self._bufs, self.rank, self.world, 0, C.ptr(src), C.ptr(dst), nbytes, m,
                C.stream(src.device))
         return dst
+
+    def device_exchanges(self):
+        """Exchanges this rank has completed, read from the device-side counter (counts the launches replayed by
+        CUDA graphs too; synchronises the device)."""
+        out = self._ct.c_longlong(0)
+        self._C.call("dmb_b200_peer_count", self._own, self._ct.byref(out))
+        return int(out.value)
 
     def close(self, collective=True):
         C = self._C
@@ -366,6 +373,33 @@ def convert_sync_batchnorm(module, group=None):
         if new is not child:
             out.add_module(name, new)
     return out
+
+
+class _BackboneView(torch.nn.Module):
+    """One per-view pass of a backbone (`backbone._forward`) as a module of its own: the unit `graph_backbone_views`
+    captures.  The views share the backbone's parameters and buffers."""
+
+    def __init__(self, backbone):
+        super(_BackboneView, self).__init__()
+        self.backbone = backbone
+
+    def forward(self, x):
+        return self.backbone._forward(x)
+
+
+def graph_backbone_views(backbone, sample, views=2, warmup=3):
+    """CUDA graphs of the per-view training passes of a torch backbone (forward and backward of each view one graph
+    launch each, torch.cuda.make_graphed_callables).  The ~120 BatchNorm layers of the PSMNet backbone make its eager
+    training pass launch bound; synchronised over ranks (PeerSyncBatchNorm) every layer is in addition a rendezvous,
+    so host-side launch jitter of ANY rank stalls all of them ~240 times per step.  Captured, the exchanges (device-
+    side sequence counter, csrc/peer_comm.cu) follow each other at GPU speed.  Every rank must call this at the same
+    point (the warm-up passes exchange statistics).  Returns `views` callables image -> features, to be called in
+    order within a step; BatchNorm running statistics are updated by the replays as in eager mode."""
+    if not sample.is_cuda:
+        raise ValueError("graph_backbone_views: CUDA tensors only")
+    mods = tuple(_BackboneView(backbone) for _ in range(views))
+    args = tuple((sample.detach().clone(memory_format=torch.preserve_format),) for _ in range(views))
+    return torch.cuda.make_graphed_callables(mods, args, num_warmup_iters=warmup)
 
 
 def enable_sync_batchnorm(module, group=True):

@@ -334,7 +334,9 @@ int dmb_b200_dif_volume_backward(const float* dvol, float* dleft, float* dright,
  * One kernel per exchange on the caller's stream: peer stores into every rank's receive buffer, a system-scope
  * release / acquire flag per (slot, rank), a local fixed-order reduction.  One process per GPU; buffers are shared
  * through CUDA IPC handles that the host exchanges once (utils/dist_utils.py:PeerComm).  All ranks must issue the same
- * sequence of exchanges (seq = 1, 2, 3, ...) on one stream each.
+ * sequence of exchanges on one stream each.  seq = 0 numbers the exchanges with a counter kept in the rank's own buffer
+ * (no per-launch host state: the launch can be captured in a CUDA graph and replayed); seq = 1, 2, 3, ... passes the
+ * number explicitly (do not mix the two on one set of buffers).
  * ------------------------------------------------------------------------------------------ */
 int64_t dmb_b200_peer_buffer_bytes(void);
 int dmb_b200_peer_alloc(void** ptr);                             /* this rank's zeroed receive buffer (cudaMalloc) */
@@ -346,6 +348,8 @@ int dmb_b200_peer_close(void* ptr);
  * mode 0: gather -> dst [world][nbytes]; mode 1: float64 sum -> dst [nbytes]; mode 2: float32 sum -> dst [nbytes] */
 int dmb_b200_peer_exchange(void* const* bufs, int rank, int world, long long seq, const void* src, void* dst, int nbytes,
                            int mode, void* stream);
+/* exchanges completed so far on this rank's buffer in seq = 0 mode (synchronises the device) */
+int dmb_b200_peer_count(const void* own_buf, long long* count);
 
 #ifdef __cplusplus
 }

@@ -477,6 +477,52 @@ def test_data_parallel_train_step_two_gpus(P, kind):
 
 
 # ---------------------------------------------------------------------------- peer-memory statistics exchange (2 GPUs)
+class _TinyBackbone(torch.nn.Module):
+    """conv-BN-ReLU-conv-BN with the backbone's `_forward` entry point (what graph_backbone_views captures)."""
+
+    def __init__(self):
+        super(_TinyBackbone, self).__init__()
+        self.c1, self.b1 = torch.nn.Conv2d(3, 8, 3, padding=1, bias=False), torch.nn.BatchNorm2d(8)
+        self.c2, self.b2 = torch.nn.Conv2d(8, 8, 3, padding=1, bias=False), torch.nn.BatchNorm2d(8)
+
+    def _forward(self, x):
+        return self.b2(self.c2(torch.relu(self.b1(self.c1(x)))))
+
+
+def test_backbone_views_replayed_from_cuda_graphs_match_eager(P):
+    """graph_backbone_views on one GPU (plain BatchNorm in train mode): features, parameter gradients and running
+    statistics of two per-view passes equal the eager ones, replay after replay."""
+    from densematchingbenchmark_b200.utils import dist_utils as DU
+    from densematchingbenchmark_b200.modeling.stereo.backbones.PSMNet import PSMNetBackbone
+    torch.manual_seed(0)
+    bb = PSMNetBackbone(3).cuda().train().to(memory_format=torch.channels_last)
+    state = {k: v.clone() for k, v in bb.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.rand(2, 3, 256, 256, generator=g).cuda().contiguous(memory_format=torch.channels_last) for _ in range(2)]
+    ws = [torch.randn(2, 32, 64, 64, generator=g).cuda() for _ in range(2)]
+
+    def two_views(fns):
+        for prm in bb.parameters():
+            prm.grad = None
+        ys = [fns[v](xs[v]) for v in range(2)]
+        sum((y * w).sum() for y, w in zip(ys, ws)).backward()
+        return ([y.detach().clone() for y in ys], {n: prm.grad.detach().clone() for n, prm in bb.named_parameters()},
+                {k: v.clone() for k, v in bb.state_dict().items() if "running" in k or "num_batches" in k})
+
+    e_out, e_grad, e_stat = two_views([bb._forward, bb._forward])
+    views = DU.graph_backbone_views(bb, xs[0], views=2)
+    for rep in range(2):
+        bb.load_state_dict(state)
+        g_out, g_grad, g_stat = two_views(views)
+        for a, b in zip(e_out, g_out):
+            assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(a.abs().max()))
+        for n in e_grad:
+            sc = max(1e-6, float(e_grad[n].abs().max()))
+            assert float((e_grad[n] - g_grad[n]).abs().max()) <= 2e-3 * sc, (n, rep)
+        for k in e_stat:
+            torch.testing.assert_close(g_stat[k].float(), e_stat[k].float(), rtol=1e-4, atol=1e-6)
+
+
 def _peer_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
@@ -519,7 +565,32 @@ def _peer_worker(rank, world, port, q):
         ok = ok and torch.allclose(x.grad.cpu(), xall.grad[sl], atol=1e-5, rtol=1e-4)
         ok = ok and torch.allclose(bn.running_mean.cpu(), bn_ref.running_mean, atol=1e-6, rtol=1e-5)
         ok = ok and torch.allclose(bn.running_var.cpu(), bn_ref.running_var, atol=1e-6, rtol=1e-5)
-        q.put((rank, bool(ok), comm.exchanges))
+        # the same layers replayed from CUDA graphs (graph_backbone_views: device-side sequence counter) == eager
+        torch.manual_seed(1)
+        tiny = DU.convert_sync_batchnorm(_TinyBackbone()).to(dev).train()
+        state = {k: v.clone() for k, v in tiny.state_dict().items()}
+        xv = [torch.randn(2, 3, 12, 16, generator=torch.Generator().manual_seed(30 + 2 * rank + v)).to(dev) for v in range(2)]
+        wv = [torch.randn(2, 8, 12, 16, generator=torch.Generator().manual_seed(40 + 2 * rank + v)).to(dev) for v in range(2)]
+
+        def two_views(fns):
+            for prm in tiny.parameters():
+                prm.grad = None
+            ys = [fns[v](xv[v]) for v in range(2)]
+            sum((y * w).sum() for y, w in zip(ys, wv)).backward()
+            return ([y.detach().clone() for y in ys], [prm.grad.detach().clone() for prm in tiny.parameters()],
+                    {k: v.clone() for k, v in tiny.state_dict().items() if "running" in k or "num_batches" in k})
+
+        e_out, e_grad, e_stat = two_views([tiny._forward, tiny._forward])
+        n_before = comm.device_exchanges()
+        views = DU.graph_backbone_views(tiny, xv[0], views=2)
+        for rep in range(2):                                  # two replays from the same initial state
+            tiny.load_state_dict(state)
+            g_out, g_grad, g_stat = two_views(views)
+            ok = ok and all(torch.allclose(a, b, atol=1e-5, rtol=1e-5) for a, b in zip(e_out, g_out))
+            ok = ok and all(torch.allclose(a, b, atol=1e-4, rtol=1e-4) for a, b in zip(e_grad, g_grad))
+            ok = ok and all(torch.allclose(e_stat[k].float(), g_stat[k].float(), atol=1e-6, rtol=1e-5) for k in e_stat)
+        ok = ok and comm.device_exchanges() > n_before       # the replays exchanged statistics (device-side counter)
+        q.put((rank, bool(ok), comm.device_exchanges()))
         DU.close_peer_comms()
     finally:
         dist.destroy_process_group()

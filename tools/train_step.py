@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 
 def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192, steps=3, warmup=2, sync_bn=True,
                     backbone=True, bucket_mb=4.0, loss="config", rank=0, world=1, device=None, sync_backbone_bn=True,
-                    channels_last_backbone=True):
+                    channels_last_backbone=True, graph_backbone=True):
     """Times `steps` training steps after `warmup`.  The process group (NCCL) must already be initialised when
     world > 1.  Returns the result dict on every rank (times are the max over ranks)."""
     import torch.distributed as dist
@@ -44,9 +44,8 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
 
     def exchanges():
         c = peer_comm(create=False)
-        return c.exchanges if c is not None else 0
+        return c.device_exchanges() if c is not None else 0
 
-    ex0 = exchanges()
     cfg = P.ConfigDict(model=dict(
         batch_norm=True,
         cost_processor=dict(type="Concatenation",
@@ -90,6 +89,15 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
     gt = (torch.rand(B, 1, H, W, generator=g) * 149 + 1).to(device)
     weights = (1.0, 0.7, 0.5)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    views = None
+    if bb is not None and graph_backbone:
+        # the torch backbone's two per-view passes as CUDA graphs (forward and backward one launch each): its ~120
+        # BatchNorm layers make the eager pass launch bound, and with synchronised statistics every layer is a rendezvous
+        from densematchingbenchmark_b200.utils.dist_utils import graph_backbone_views
+        if synced and sync_backbone_bn:
+            peer_comm()                                              # set up (collectively) before the capture
+        if not (synced and sync_backbone_bn) or peer_comm(create=False) is not None:   # (NCCL fall-back: eager)
+            views = graph_backbone_views(bb, left, views=2)
 
     def step(marks=None):
         def mark():
@@ -97,7 +105,10 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
                 marks.append(ev()); marks[-1].record()
         opt.zero_grad(set_to_none=True)
         mark()
-        lf, rf = bb(left, right) if bb is not None else (left, right)
+        if views is not None:
+            lf, rf = views[0](left), views[1](right)
+        else:
+            lf, rf = bb(left, right) if bb is not None else (left, right)
         costs = proc(lf, rf)
         disps = [pred(c) for c in costs]
         mask = (gt > 0) & (gt < max_disp)
@@ -115,6 +126,7 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
         mark()
         return total
 
+    ex0 = exchanges()                                                # (after the graph capture's own warm-up passes)
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -151,7 +163,9 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
         "loss_terms": ("stereo focal loss (coefficient 5, variance 1.2) + 0.1 x smooth-L1" if use_focal else "smooth-L1"),
         "sync_bn": synced, "sync_bn_layers": n_bn,
         "backbone_sync_bn": bool(synced and bb is not None and sync_backbone_bn),
-        "backbone": "torch autograd (cuDNN), outside the hot path" if bb is not None else "none (synthetic features)",
+        "backbone": ("torch autograd (cuDNN), outside the hot path"
+                     + ("; its two per-view passes replayed from CUDA graphs" if views is not None else ", eager"))
+                    if bb is not None else "none (synthetic features)",
         "collective": ("NCCL all-reduce (mean) of all gradients, %d buckets of <= %.0f MB issued from inside backward; "
                        "SyncBN statistics (2*C numbers per BatchNorm layer and direction): %s"
                        % (len(reducer.buckets), bucket_mb,
@@ -182,6 +196,7 @@ def main():
     ap.add_argument("--bucket-mb", type=float, default=4.0)
     ap.add_argument("--local-backbone-bn", action="store_true", help="keep the torch backbone's BatchNorm per rank")
     ap.add_argument("--nchw-backbone", action="store_true", help="torch backbone in NCHW (default: channels_last)")
+    ap.add_argument("--eager-backbone", action="store_true", help="do not capture the backbone's passes in CUDA graphs")
     ap.add_argument("--loss", default="config", choices=["config", "l1"],
                     help="config: the losses of the reference configuration; l1: smooth-L1 only")
     args = ap.parse_args()
@@ -196,7 +211,7 @@ def main():
     try:
         res = run_train_bench(args.kind, args.batch, args.height, args.width, args.max_disp, args.steps, args.warmup,
                               args.sync_bn, not args.no_backbone, args.bucket_mb, args.loss, rank, world, device,
-                              not args.local_backbone_bn, not args.nchw_backbone)
+                              not args.local_backbone_bn, not args.nchw_backbone, not args.eager_backbone)
         if rank == 0:
             print(json.dumps(res))
     finally:
