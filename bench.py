@@ -522,7 +522,7 @@ def run_ours(args, rank, world, local_rank):
         tsteps = max(2, min(args.steps, 5))
         extra["train"] = run_train_bench("AcfNet", 4, 256, 512, MAX_DISP, steps=tsteps, warmup=2,
                                          sync_bn=True, backbone=True, bucket_mb=4.0, loss="config", rank=rank, world=world,
-                                         device=device)
+                                         device=device, graph_hot_path=True)
         torch.cuda.empty_cache()
         if world > 1:
             # the same step with the torch backbone's BatchNorm left per-rank (the hot path's own BatchNorm layers stay
@@ -530,7 +530,7 @@ def run_ours(args, rank, world, local_rank):
             # torch section is the residual limiter of the fully synchronised step
             alt_train = run_train_bench("AcfNet", 4, 256, 512, MAX_DISP, steps=tsteps, warmup=2, sync_bn=True, backbone=True,
                                   bucket_mb=4.0, loss="config", rank=rank, world=world, device=device,
-                                  sync_backbone_bn=False)
+                                  sync_backbone_bn=False, graph_hot_path=True)
             extra["train"]["variant_backbone_bn_per_rank"] = {k: alt_train[k] for k in ("ms_per_step", "pairs_per_s", "segments_ms",
                                                                                   "peer_exchanges_per_step")}
             torch.cuda.empty_cache()

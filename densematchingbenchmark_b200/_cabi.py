@@ -70,6 +70,8 @@ SIGNATURES = {
     "dmb_b200_peer_close": [_P],
     "dmb_b200_peer_exchange": [POINTER(c_void_p), _I, _I, _LL, _P, _P, _I, _I, _P],
     "dmb_b200_peer_count": [_P, POINTER(c_longlong)],
+    "dmb_b200_peer_sum2_f32": [POINTER(c_void_p), _I, _I, _P, _I, _P, _I, _P, _P, _P],
+    "dmb_b200_peer_bn_forward": [POINTER(c_void_p), _I, _I, _P, _P, _F, _F, _F, _P, _P, _P, _P, _P, _I, _P],
     "dmb_b200_dif_volume_backward": [_P, _P, _P, _I, _I, _I, _I, _IP, _I, _P],
 }
 # entry points that do not return a status code

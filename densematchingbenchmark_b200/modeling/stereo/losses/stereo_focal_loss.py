@@ -57,6 +57,7 @@ class StereoFocalLoss(object):
         self.weights = weights
         self.focal_coefficient = focal_coefficient
         self.sparse = sparse
+        self._disp_values = {}                     # disparity samples per (configuration, device), uploaded once
         # sparse ground truth (KITTI) -> max pooling, dense -> average pooling (stereo_focal_loss.py:55-61)
         self.scale_func = F.adaptive_max_pool2d if sparse else F.adaptive_avg_pool2d
 
@@ -79,7 +80,12 @@ class StereoFocalLoss(object):
             n = (max_disp + dilation - 1) // dilation
             if n != D:
                 raise ValueError("cost volume has %d disparity samples, the loss configuration implies %d" % (D, n))
-            disp_values = torch.linspace(self.start_disp, inner_end, n).to(estCost.device)
+            # built on the host like the reference's (losses/utils/disp2prob.py), uploaded once per configuration and
+            # device: a per-call host-to-device copy is a stream synchronisation and cannot be captured in a CUDA graph
+            key = (self.start_disp, inner_end, n, estCost.device)
+            disp_values = self._disp_values.get(key)
+            if disp_values is None:
+                disp_values = self._disp_values[key] = torch.linspace(self.start_disp, inner_end, n).to(estCost.device)
         else:
             disp_sample = C.f32(disp_sample.to(estCost.device).detach())
             assert (disp_sample.shape[0], disp_sample.shape[2], disp_sample.shape[3]) == (B, H, W), \

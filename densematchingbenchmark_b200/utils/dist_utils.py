@@ -214,6 +214,32 @@ class PeerComm(object):
                C.stream(src.device))
         return dst
 
+    def sum2(self, a, b):
+        """Float32 sums over the ranks of two vectors in ONE exchange -> (sum_a, sum_b)."""
+        C = self._C
+        a, b = a.contiguous(), b.contiguous()
+        if a.dtype != torch.float32 or b.dtype != torch.float32 or (a.numel() + b.numel()) * 4 > self.MAX_BYTES:
+            raise ValueError("PeerComm.sum2: two float32 vectors of at most %d bytes together" % self.MAX_BYTES)
+        oa, ob = torch.empty_like(a), torch.empty_like(b)
+        self.exchanges += 1
+        C.call("dmb_b200_peer_sum2_f32", self._bufs, self.rank, self.world, C.ptr(a), a.numel(), C.ptr(b), b.numel(),
+               C.ptr(oa), C.ptr(ob), C.stream(a.device))
+        return oa, ob
+
+    def bn_forward(self, mean, invstd, count, eps, momentum, running_mean, running_var):
+        """Per-rank BatchNorm statistics (torch.batch_norm_stats) -> statistics of the joint batch, running statistics
+        updated in place, every rank's element count: exchange and merge in one kernel.  Returns (mean, invstd,
+        counts int32 [world])."""
+        C = self._C
+        mean, invstd = mean.contiguous(), invstd.contiguous()
+        om, oi = torch.empty_like(mean), torch.empty_like(invstd)
+        counts = torch.empty(self.world, dtype=torch.int32, device=mean.device)
+        self.exchanges += 1
+        C.call("dmb_b200_peer_bn_forward", self._bufs, self.rank, self.world, C.ptr(mean), C.ptr(invstd), float(count),
+               float(eps), float(momentum), C.ptr(running_mean), C.ptr(running_var), C.ptr(om), C.ptr(oi), C.ptr(counts),
+               mean.numel(), C.stream(mean.device))
+        return om, oi, counts
+
     def device_exchanges(self):
         """Exchanges this rank has completed, read from the device-side counter (counts the launches replayed by
         CUDA graphs too; synchronises the device)."""
@@ -296,20 +322,27 @@ class _PeerSyncBatchNormFn(torch.autograd.Function):
             x = x.contiguous()
         C_ = x.shape[1]
         mean, invstd = torch.batch_norm_stats(x, eps)
-        count = torch.full((1,), x.numel() // C_, dtype=mean.dtype, device=mean.device)
-        combined = torch.cat([mean, invstd, count], dim=0)                       # [2C + 1]
         comm = peer_comm(group)
-        if comm is not None:
-            allc = comm.exchange(combined, "gather")                             # [world, 2C + 1]
+        fused = (comm is not None and mean.dtype == torch.float32 and (2 * C_ + 1) * 4 <= PeerComm.MAX_BYTES
+                 and all(t is None or (t.dtype == torch.float32 and t.is_contiguous()) for t in (running_mean, running_var)))
+        if fused:
+            # exchange + merge + running-statistics update in one kernel (csrc/peer_comm.cu:peer_bn_forward_kernel)
+            mean, invstd, counts = comm.bn_forward(mean, invstd, x.numel() // C_, eps, momentum, running_mean, running_var)
         else:
-            world = dist.get_world_size(None if group in (None, True) else group)
-            allc = torch.empty(world, combined.numel(), dtype=combined.dtype, device=combined.device)
-            dist.all_gather_into_tensor(allc.view(-1), combined, None if group in (None, True) else group)
-        mean_all, invstd_all, count_all = torch.split(allc, C_, dim=1)
-        counts = count_all.reshape(-1)
-        mean, invstd = torch.batch_norm_gather_stats_with_counts(x, mean_all, invstd_all, running_mean, running_var,
-                                                                 momentum, eps, counts)
-        ctx.save_for_backward(x, weight, mean, invstd, counts.to(torch.int32))
+            count = torch.full((1,), x.numel() // C_, dtype=mean.dtype, device=mean.device)
+            combined = torch.cat([mean, invstd, count], dim=0)                       # [2C + 1]
+            if comm is not None:
+                allc = comm.exchange(combined, "gather")                             # [world, 2C + 1]
+            else:
+                world = dist.get_world_size(None if group in (None, True) else group)
+                allc = torch.empty(world, combined.numel(), dtype=combined.dtype, device=combined.device)
+                dist.all_gather_into_tensor(allc.view(-1), combined, None if group in (None, True) else group)
+            mean_all, invstd_all, count_all = torch.split(allc, C_, dim=1)
+            counts = count_all.reshape(-1)
+            mean, invstd = torch.batch_norm_gather_stats_with_counts(x, mean_all, invstd_all, running_mean, running_var,
+                                                                     momentum, eps, counts)
+            counts = counts.to(torch.int32)
+        ctx.save_for_backward(x, weight, mean, invstd, counts)
         ctx.group = group
         return torch.batch_norm_elemt(x, weight, bias, mean, invstd, eps)
 
@@ -322,9 +355,13 @@ class _PeerSyncBatchNormFn(torch.autograd.Function):
                                                                       ctx.needs_input_grad[1], ctx.needs_input_grad[2])
         gx = None
         if ctx.needs_input_grad[0]:
-            combined = torch.cat([sum_dy, sum_dy_xmu], dim=0)
-            sum_over_ranks_(combined, ctx.group)
-            sum_dy, sum_dy_xmu = torch.split(combined, sum_dy.shape[0])
+            comm = peer_comm(ctx.group)
+            if comm is not None and sum_dy.dtype == torch.float32 and 2 * sum_dy.numel() * 4 <= PeerComm.MAX_BYTES:
+                sum_dy, sum_dy_xmu = comm.sum2(sum_dy, sum_dy_xmu)                # both sums in one exchange, no cat / split
+            else:
+                combined = torch.cat([sum_dy, sum_dy_xmu], dim=0)
+                sum_over_ranks_(combined, ctx.group)
+                sum_dy, sum_dy_xmu = torch.split(combined, sum_dy.shape[0])
             gx = torch.batch_norm_backward_elemt(gy, x, mean, invstd, weight, sum_dy, sum_dy_xmu, counts)
         return gx, (gw if ctx.needs_input_grad[1] else None), (gb if ctx.needs_input_grad[2] else None), None, None, None, None, None
 

@@ -348,6 +348,19 @@ int dmb_b200_peer_close(void* ptr);
  * mode 0: gather -> dst [world][nbytes]; mode 1: float64 sum -> dst [nbytes]; mode 2: float32 sum -> dst [nbytes] */
 int dmb_b200_peer_exchange(void* const* bufs, int rank, int world, long long seq, const void* src, void* dst, int nbytes,
                            int mode, void* stream);
+/* float32 sums over the ranks of TWO vectors in one exchange: dst0[n0], dst1[n1] ((n0 + n1) * 4 <= 8192).  The backward
+ * statistics of synchronised BatchNorm (sum(dy), sum(dy * (x - mean)): torch.batch_norm_backward_reduce -> all_reduce ->
+ * batch_norm_backward_elemt in torch.nn.SyncBatchNorm / apex.parallel.SyncBatchNorm) */
+int dmb_b200_peer_sum2_f32(void* const* bufs, int rank, int world, const float* src0, int n0, const float* src1, int n1,
+                           float* dst0, float* dst1, void* stream);
+/* forward statistics of synchronised BatchNorm, exchange FUSED with the merge: this rank's mean[C], invstd[C] (1 / sqrt(var
+ * + eps), biased variance) and element count -> the joint batch's out_mean[C] / out_invstd[C], every rank's count
+ * (out_counts[world] int32, may be NULL) and the running-statistics update (momentum; unbiased variance; pointers may be
+ * NULL).  Replaces all_gather + batch_norm_gather_stats_with_counts of torch.nn.SyncBatchNorm (apex: welford_parallel).
+ * (2 * C + 1) * 4 <= 8192 */
+int dmb_b200_peer_bn_forward(void* const* bufs, int rank, int world, const float* mean, const float* invstd, float count,
+                             float eps, float momentum, float* running_mean, float* running_var, float* out_mean,
+                             float* out_invstd, int* out_counts, int C, void* stream);
 /* exchanges completed so far on this rank's buffer in seq = 0 mode (synchronises the device) */
 int dmb_b200_peer_count(const void* own_buf, long long* count);
 

@@ -489,11 +489,13 @@ class _TinyBackbone(torch.nn.Module):
         return self.b2(self.c2(torch.relu(self.b1(self.c1(x)))))
 
 
-def test_backbone_views_replayed_from_cuda_graphs_match_eager(P):
+def test_backbone_views_replayed_from_cuda_graphs_match_eager(P, monkeypatch):
     """graph_backbone_views on one GPU (plain BatchNorm in train mode): features, parameter gradients and running
     statistics of two per-view passes equal the eager ones, replay after replay."""
     from densematchingbenchmark_b200.utils import dist_utils as DU
     from densematchingbenchmark_b200.modeling.stereo.backbones.PSMNet import PSMNetBackbone
+    # cuDNN picks its algorithms per call site; with TF32 allowed two algorithms differ at the 1e-3 level
+    monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     torch.manual_seed(0)
     bb = PSMNetBackbone(3).cuda().train().to(memory_format=torch.channels_last)
     state = {k: v.clone() for k, v in bb.state_dict().items()}
@@ -516,9 +518,10 @@ def test_backbone_views_replayed_from_cuda_graphs_match_eager(P):
         g_out, g_grad, g_stat = two_views(views)
         for a, b in zip(e_out, g_out):
             assert float((a - b).abs().max()) <= 1e-4 * max(1.0, float(a.abs().max()))
-        for n in e_grad:
-            sc = max(1e-6, float(e_grad[n].abs().max()))
-            assert float((e_grad[n] - g_grad[n]).abs().max()) <= 2e-3 * sc, (n, rep)
+        gmax = max(float(v.abs().max()) for v in e_grad.values())
+        for n in e_grad:                                      # (conv biases in front of a BatchNorm have a zero gradient:
+            sc = float(e_grad[n].abs().max())                 #  rounding noise only, hence the absolute floor)
+            assert float((e_grad[n] - g_grad[n]).abs().max()) <= 2e-3 * sc + 5e-5 * gmax, (n, rep)
         for k in e_stat:
             torch.testing.assert_close(g_stat[k].float(), e_stat[k].float(), rtol=1e-4, atol=1e-6)
 

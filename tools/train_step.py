@@ -28,7 +28,7 @@ if ROOT not in sys.path:
 
 def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192, steps=3, warmup=2, sync_bn=True,
                     backbone=True, bucket_mb=4.0, loss="config", rank=0, world=1, device=None, sync_backbone_bn=True,
-                    channels_last_backbone=True, graph_backbone=True):
+                    channels_last_backbone=True, graph_backbone=True, graph_hot_path=False):
     """Times `steps` training steps after `warmup`.  The process group (NCCL) must already be initialised when
     world > 1.  Returns the result dict on every rank (times are the max over ranks)."""
     import torch.distributed as dist
@@ -89,7 +89,31 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
     gt = (torch.rand(B, 1, H, W, generator=g) * 149 + 1).to(device)
     weights = (1.0, 0.7, 0.5)
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    views = None
+    def losses(lf, rf):
+        costs = proc(lf, rf)
+        disps = [pred(c) for c in costs]
+        # mean over the valid pixels without boolean indexing (d[mask] sizes its result on the host: a
+        # synchronisation per level, and not capturable): the same sum divided by the same count
+        mask = ((gt > 0) & (gt < max_disp)).to(gt.dtype)
+        n_valid = mask.sum().clamp_min(1.0)
+        total = l1_weight * sum(w * (torch.nn.functional.smooth_l1_loss(d, gt, reduction="none") * mask).sum() / n_valid
+                                for w, d in zip(weights, disps))
+        if focal is not None:
+            total = total + sum(focal(list(costs), gt, variance=1.2).values())
+        return total
+
+    class _HotPath(torch.nn.Module):
+        """cat volume + aggregator + soft-argmin + the configuration's losses as one module: with `graph_hot_path` its
+        forward and backward are one CUDA-graph launch each (torch.cuda.make_graphed_callables)."""
+
+        def __init__(self):
+            super(_HotPath, self).__init__()
+            self.proc, self.pred = proc, pred
+
+        def forward(self, lf, rf):
+            return losses(lf, rf)
+
+    views = hot = None
     if bb is not None and graph_backbone:
         # the torch backbone's two per-view passes as CUDA graphs (forward and backward one launch each): its ~120
         # BatchNorm layers make the eager pass launch bound, and with synchronised statistics every layer is a rendezvous
@@ -98,6 +122,11 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
             peer_comm()                                              # set up (collectively) before the capture
         if not (synced and sync_backbone_bn) or peer_comm(create=False) is not None:   # (NCCL fall-back: eager)
             views = graph_backbone_views(bb, left, views=2)
+    if graph_hot_path and (not synced or peer_comm() is not None):
+        with torch.no_grad():
+            f0 = (bb._forward(left) if bb is not None else left).detach()
+        sample = (f0.clone().requires_grad_(True), f0.clone().requires_grad_(True))
+        hot = torch.cuda.make_graphed_callables(_HotPath(), sample, num_warmup_iters=2, allow_unused_input=True)
 
     def step(marks=None):
         def mark():
@@ -109,12 +138,7 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
             lf, rf = views[0](left), views[1](right)
         else:
             lf, rf = bb(left, right) if bb is not None else (left, right)
-        costs = proc(lf, rf)
-        disps = [pred(c) for c in costs]
-        mask = (gt > 0) & (gt < max_disp)
-        total = l1_weight * sum(w * torch.nn.functional.smooth_l1_loss(d[mask], gt[mask]) for w, d in zip(weights, disps))
-        if focal is not None:
-            total = total + sum(focal(list(costs), gt, variance=1.2).values())
+        total = hot(lf, rf) if hot is not None else losses(lf, rf)
         mark()
         total.backward()
         mark()
@@ -161,6 +185,7 @@ def run_train_bench(kind="AcfNet", batch=4, height=256, width=512, max_disp=192,
         "segments_ms": {"forward+loss": seg[0], "backward (all-reduce overlapped)": seg[1],
                         "reducer tail + grad clip": seg[2], "optimizer": seg[3]},
         "loss_terms": ("stereo focal loss (coefficient 5, variance 1.2) + 0.1 x smooth-L1" if use_focal else "smooth-L1"),
+        "hot_path_launch": "CUDA graphs (forward + losses / backward one launch each)" if hot is not None else "eager",
         "sync_bn": synced, "sync_bn_layers": n_bn,
         "backbone_sync_bn": bool(synced and bb is not None and sync_backbone_bn),
         "backbone": ("torch autograd (cuDNN), outside the hot path"
@@ -197,6 +222,7 @@ def main():
     ap.add_argument("--local-backbone-bn", action="store_true", help="keep the torch backbone's BatchNorm per rank")
     ap.add_argument("--nchw-backbone", action="store_true", help="torch backbone in NCHW (default: channels_last)")
     ap.add_argument("--eager-backbone", action="store_true", help="do not capture the backbone's passes in CUDA graphs")
+    ap.add_argument("--graph-hot-path", action="store_true", help="capture the hot path's forward + losses / backward in CUDA graphs too")
     ap.add_argument("--loss", default="config", choices=["config", "l1"],
                     help="config: the losses of the reference configuration; l1: smooth-L1 only")
     args = ap.parse_args()
@@ -211,7 +237,8 @@ def main():
     try:
         res = run_train_bench(args.kind, args.batch, args.height, args.width, args.max_disp, args.steps, args.warmup,
                               args.sync_bn, not args.no_backbone, args.bucket_mb, args.loss, rank, world, device,
-                              not args.local_backbone_bn, not args.nchw_backbone, not args.eager_backbone)
+                              not args.local_backbone_bn, not args.nchw_backbone, not args.eager_backbone,
+                              args.graph_hot_path)
         if rank == 0:
             print(json.dumps(res))
     finally:
