@@ -1082,6 +1082,101 @@ __global__ void __launch_bounds__(256, 2) lga_r2_tma_kernel(const __grid_constan
     }
 }
 
+// Two vertically adjacent pixels per thread: the 6 x 5 tile window of the pair is read once and feeds both pixels'
+// sums (15 shared loads per output value instead of 25 -- the shared-memory pipe, 128 B per clock and SM, ran level with
+// the FMA pipe in the one-pixel kernel: 100 B against 75 FMAs per output).  150 weights + 6 running sums per thread,
+// 128 threads per CTA (same 32 x 8 tile, same TMA box), two CTAs per SM.
+// MEASURED SLOWER (config 4: 0.504 ms against 0.456 ms for one pixel per thread; with the registers capped at 170 for
+// three CTAs per SM: 0.70 ms): 189 registers leave 8 warps per SM, too few to cover the shared-load latency.  Kept
+// as an A/B (DMB_B200_LGA_ROT=3); the one-pixel kernel is the default.
+template <int NP>
+__global__ void __launch_bounds__(128, 2) lga_r2_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ guid,
+                                                             float* __restrict__ out, int D, int H, int W) {
+    constexpr int TX = 32, TY = 8, PW = TX + 8, PH = TY + 4, NE = PH * PW;   // tile starts at x0 - 4 (16-byte aligned box)
+    __shared__ __align__(128) float tile[2][NP * NE];
+    __shared__ uint64_t full[2];
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = (tid >> 5) * 2;                            // rows ty, ty + 1 of the tile
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
+    const int px = x0 + tx, py = y0 + ty;
+    const int b = blockIdx.z;
+    const bool in_a = px < W && py < H, in_b = px < W && py + 1 < H;
+    const size_t plane = (size_t)H * W;
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int nst = (D + 1 + NP - 1) / NP;         // planes 0 .. D (plane D is all zeros: it completes out(D-1))
+    const CUtensorMap* const mp = &xmap;
+    auto issue = [&, mp](int st) {
+        if (tid == 0 && st < nst) {
+            mbar_expect_tx(&full[st & 1], NP * NE * 4);
+            tma_load_4d_f32(tile[st & 1], mp, &full[st & 1], x0 - 4, y0 - 2, st * NP, b);
+        }
+    };
+    issue(0);
+    issue(1);
+    float wa[75], wb[75];
+    {
+        const float* ga = guid + (size_t)b * 75 * plane + (size_t)(in_a ? py : 0) * W + (in_a ? px : 0);
+        const float* gb = guid + (size_t)b * 75 * plane + (size_t)(in_b ? py + 1 : 0) * W + (in_b ? px : 0);
+        float na = 0.f, nb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 75; ++i) {
+            wa[i] = __ldg(ga + (size_t)i * plane);
+            wb[i] = __ldg(gb + (size_t)i * plane);
+            na += fabsf(wa[i]);
+            nb += fabsf(wb[i]);
+        }
+        na = fmaxf(na, 1e-12f);
+        nb = fmaxf(nb, 1e-12f);
+#pragma unroll
+        for (int i = 0; i < 75; ++i) {
+            wa[i] = wa[i] / na;
+            wb[i] = wb[i] / nb;
+        }
+    }
+    float* oa = out + (size_t)b * D * plane + (size_t)py * W + px;
+    float pa = 0.f, ca = 0.f, na = 0.f, pb = 0.f, cb = 0.f, nb = 0.f;      // sums for out(d-1), out(d), out(d+1) of A, B
+    for (int st = 0; st < nst; ++st) {
+        mbar_wait(&full[st & 1], (st >> 1) & 1);
+        const float* tb0 = &tile[st & 1][ty * PW + tx + 2];
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) {
+            const float* tb = tb0 + pl * NE;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const float v = tb[r * PW + kx];
+                    if (r < 5) {                   // pixel A: window row ky = r
+                        const int i = r * 5 + kx;
+                        ca = fmaf(wa[i], v, ca);
+                        na = fmaf(wa[25 + i], v, na);
+                        pa = fmaf(wa[50 + i], v, pa);
+                    }
+                    if (r > 0) {                   // pixel B (one row lower): window row ky = r - 1
+                        const int i = (r - 1) * 5 + kx;
+                        cb = fmaf(wb[i], v, cb);
+                        nb = fmaf(wb[25 + i], v, nb);
+                        pb = fmaf(wb[50 + i], v, pb);
+                    }
+                }
+            const int d = st * NP + pl;            // the plane just consumed: out(d-1) is complete
+            if (d >= 1 && d <= D) {
+                if (in_a) st_cs_f(oa + (size_t)(d - 1) * plane, pa);
+                if (in_b) st_cs_f(oa + (size_t)(d - 1) * plane + W, pb);
+            }
+            pa = ca; ca = na; na = 0.f;
+            pb = cb; cb = nb; nb = 0.f;
+        }
+        __syncthreads();                           // everybody is done with buffer st & 1
+        issue(st + 2);
+    }
+}
+
 // any radius: weights re-read per use (slow path, kept for generality)
 __global__ void __launch_bounds__(256) lga_generic_kernel(const float* __restrict__ x, const float* __restrict__ guid,
                                                           float* __restrict__ out, int D, int H, int W, int radius) {
@@ -1327,7 +1422,8 @@ extern "C" int dmb_b200_lga(const float* x, const float* guidance, float* out, i
         static int rot_mode = -1;                  // DMB_B200_LGA_ROT=0: the register-plane kernel (A/B)
         if (rot_mode < 0) {
             const char* e = getenv("DMB_B200_LGA_ROT");
-            rot_mode = (e && e[0] == '0') ? 0 : ((e && e[0] == '2') ? 2 : 1);      // 2: the cp.async-staged variant
+            // 0: register-plane kernel, 2: cp.async-staged, 3: TMA-staged with two pixels per thread, default 1: TMA-staged
+            rot_mode = (e && e[0] >= '0' && e[0] <= '3' && e[0] != '1') ? e[0] - '0' : 1;
         }
         if (rot_mode) {
             // TMA-staged variant when the tensor map can be built (16-byte aligned base and row pitch, sm_100 driver)
@@ -1341,6 +1437,10 @@ extern "C" int dmb_b200_lga(const float* x, const float* guidance, float* out, i
                                                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r == CUDA_SUCCESS) {
+                    if (rot_mode == 3) {           // two pixels per thread (A/B: measured slower)
+                        lga_r2_tma2_kernel<4><<<grid, 128, 0, as_stream(stream)>>>(xmap, guidance, out, D, H, W);
+                        return check_launch("lga_r2_tma2_kernel");
+                    }
                     lga_r2_tma_kernel<4><<<grid, 256, 0, as_stream(stream)>>>(xmap, guidance, out, D, H, W);
                     return check_launch("lga_r2_tma_kernel");
                 }
