@@ -30,6 +30,7 @@
 // Warp roles (192 threads): warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (warp 1 also
 // owns the TMEM allocation), warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
 #include <cuda.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <cuda_fp16.h>
 
@@ -168,6 +169,8 @@ struct Params {
     int y_cb0, y_cbs;          // first block / total blocks of y
     int res_cb0, res_cbs;      // same for the residual tensor
     int tiles_h, tiles_w, nseg, seg_len, n_items;
+    int balanced, planes_total; // balanced = 1: CTA k of G works planes [k T / G, (k + 1) T / G) of the T = columns x Dm
+                                // (tile column, depth plane) sequence, cut into items at column ends (see ItemIter)
     int relu;
     int n_valid_out;           // output channels that exist (1 in y_f32 mode, else 32)
     float acc_scale;           // 2^-k undoing the power-of-two weight pre-scaling (exact)
@@ -271,6 +274,58 @@ __device__ __forceinline__ Item decode_item(const Params& p, int item) {
     it.h0 = th * THSTEP;
     it.w0 = tw * TWSTEP;
     return it;
+}
+
+// Work items of one CTA.  Static schedule (balanced = 0): items blockIdx.x, blockIdx.x + G, ... of the uniform
+// (tile column x depth segment) grid.  Balanced schedule: the CTA's contiguous share of the linearised (tile column,
+// depth plane) sequence, cut at column ends -- every CTA gets the same number of planes (+-1) in at most a few items,
+// where the static schedule's slowest CTA ran ceil(items / G) whole segments (measured on the hourglass' 1/8-resolution
+// layers: SMs active 66 % of the kernel, profiles/r2_ncu_full_conv3d_tc_k7.txt).  A share boundary that would leave
+// a one-plane item at a column end is moved to the column end.
+struct ItemIter {
+    int L, L1;
+};
+__device__ __forceinline__ int snap_boundary(const Params& p, long long k) {
+    int L = (int)(k * p.planes_total / gridDim.x);
+    const int r = L % p.Dm;
+    if (p.Dm >= 4) {
+        if (r == 1) L -= 1;
+        else if (r == p.Dm - 1) L += 1;
+    }
+    return L;
+}
+__device__ __forceinline__ ItemIter items_begin(const Params& p) {
+    ItemIter s;
+    if (p.balanced) {
+        s.L = snap_boundary(p, blockIdx.x);
+        s.L1 = blockIdx.x + 1 == gridDim.x ? p.planes_total : snap_boundary(p, (long long)blockIdx.x + 1);
+    } else {
+        s.L = blockIdx.x;
+        s.L1 = p.n_items;
+    }
+    return s;
+}
+template <int THSTEP, int TWSTEP>
+__device__ __forceinline__ bool items_next(const Params& p, ItemIter& s, Item& it) {
+    if (s.L >= s.L1) return false;
+    if (p.balanced) {
+        const int col = s.L / p.Dm;                // (b, tile row, tile column)
+        const int d0 = s.L - col * p.Dm;
+        const int d1 = min(p.Dm, d0 + (s.L1 - s.L));
+        const int per_b = p.tiles_w * p.tiles_h;
+        it.b = col / per_b;
+        const int r = col - it.b * per_b;
+        const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
+        it.d0 = d0;
+        it.d1 = d1;
+        it.h0 = th * THSTEP;
+        it.w0 = tw * TWSTEP;
+        s.L += d1 - d0;
+    } else {
+        it = decode_item<THSTEP, TWSTEP>(p, s.L);
+        s.L += gridDim.x;
+    }
+    return true;
 }
 
 // bias + residual + ReLU + 16-bit (hi[,lo]) split + store of one output voxel's 32 channels
@@ -541,8 +596,9 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
             uint32_t n = 0;
             uint32_t ntrace_p = 0;
             const int in_cb0_k4 = p.in_cb0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<th_of(KIND), twstep_of(KIND)>(p, item);
+            ItemIter iter = items_begin(p);
+            Item it;
+            while (items_next<th_of(KIND), twstep_of(KIND)>(p, iter, it)) {
                 const int nout = it.d1 - it.d0;
                 const int nplanes = (KIND == 0 || KIND == 3) ? nout + 2 : ((KIND == 1 || KIND == 4) ? 2 * nout + 1 : nout + 1);   // KIND 2/5: nout + 1
                 const int pl0 = (KIND == 0 || KIND == 3) ? it.d0 - 1 : ((KIND == 1 || KIND == 4) ? 2 * it.d0 - 1 : it.d0);
@@ -650,8 +706,9 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
                 }
                 commit_one(pfull);
             };
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const Item it = decode_item<th_of(KIND), twstep_of(KIND)>(p, item);
+            ItemIter iter = items_begin(p);
+            Item it;
+            while (items_next<th_of(KIND), twstep_of(KIND)>(p, iter, it)) {
                 const int nout = it.d1 - it.d0;
                 if (KIND == 0) {
                     constexpr uint32_t LBO_A = 18 * 10 * 16, SBO_A = 10 * 16;
@@ -1083,8 +1140,9 @@ conv3d_tc_kernel(const __grid_constant__ Maps maps, const Params p) {
         uint32_t t = 0;
         uint32_t ntrace = 0;
         const bool tracer = (warp == 2 && lane == 0);
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const Item it = decode_item<th_of(KIND), twstep_of(KIND)>(p, item);
+        ItemIter iter = items_begin(p);
+        Item it;
+        while (items_next<th_of(KIND), twstep_of(KIND)>(p, iter, it)) {
             const int h = it.h0 + hl;
             // KIND 3/4: tile columns are input columns w0-1 .. w0+14; KIND 4 keeps the even centres (ow = w/2)
             const int win = it.w0 - 1 + wl;
@@ -1472,7 +1530,7 @@ extern "C" int dmb_b200_conv3d_tc_pack_weights(const float* w_packed, void* w_bl
 // Geometry and static schedule of one launch: M-space / output extents, tile counts, depth segmentation.
 // Returns the grid size (persistent CTAs).  Pure host arithmetic (dmb_b200_conv3d_tc_schedule exposes it to the
 // CPU tests).
-static int plan_schedule(Params& p, int kind, int B, int D, int H, int W) {
+static int plan_schedule(Params& p, int kind, int B, int D, int H, int W, bool head = false) {
     p.B = (kind == 1) ? 1 : B;
     const bool s2 = (kind == 1 || kind == 4);
     // KIND 4 tiles W in INPUT columns (every column is computed, even centres are kept)
@@ -1511,6 +1569,23 @@ static int plan_schedule(Params& p, int kind, int B, int D, int H, int W) {
     p.seg_len = (int)cdiv(p.Dm, nseg);
     p.nseg = (int)cdiv(p.Dm, p.seg_len);
     p.n_items = cols * p.nseg;
+    p.balanced = 0;
+    p.planes_total = cols * p.Dm;
+    // DMB_B200_TC_BALANCED=1 selects the balanced plane schedule (ItemIter).  OFF by default: measured on the PSMNet
+    // trunk it is 2 % SLOWER (aggregator 6.98-7.05 ms against 6.89 ms on one box) although the static schedule leaves the
+    // SMs of the small hourglass layers idle a third of the time -- the trunk is power bound, the idle SMs' share of the
+    // power budget clocks the busy ones higher, and the static schedule's wave-like order shares halo planes in L2.
+    static int balanced_on = -1;
+    if (balanced_on < 0) {
+        const char* e = getenv("DMB_B200_TC_BALANCED");
+        balanced_on = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (balanced_on && !head && (int64_t)cols * p.Dm < ((int64_t)1 << 30)) {
+        // (the fused head's spill planes are indexed by the uniform segments: it stays on the static schedule)
+        p.balanced = 1;
+        const int g = (int)std::min<int64_t>(sm_count(), std::max<int64_t>(1, p.planes_total / 2));
+        return g;
+    }
     return p.n_items < sm_count() ? p.n_items : sm_count();
 }
 
@@ -1558,7 +1633,7 @@ static int conv3d_tc_impl(const void* x_hi, const void* x_lo, int Cin, const voi
     p.flat = flat;
     p.head_w = head_w;
     p.head_t = head_t;
-    const int grid = plan_schedule(p, kind, B, D, H, W);
+    const int grid = plan_schedule(p, kind, B, D, H, W, head_t != nullptr);
     p.n_valid_out = scalar_out ? 1 : nbo;
     p.acc_scale = 1.0f / w_scale;
     const size_t blob = (size_t)TAPS * cbk * (split ? 2 * nbo : nbo) * 16;
@@ -1687,7 +1762,7 @@ extern "C" int64_t dmb_b200_conv3d_tc_head_floats(int B, int D, int H, int W) {
     // per batch element 9 Q planes per depth + 2 x 9 spill planes per depth segment of the launch's schedule
     if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
     Params p;
-    plan_schedule(p, 3, B, D, H, W);
+    plan_schedule(p, 3, B, D, H, W, true);
     return (int64_t)B * ((int64_t)9 * D + (int64_t)18 * p.nseg) * H * W;
 }
 
@@ -1696,7 +1771,7 @@ extern "C" int dmb_b200_head_gather(const float* head_t, const float* res, float
     DMB_REQUIRE(head_t && y, "head_gather: null pointer");
     DMB_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "head_gather: non-positive dimension");
     Params p;                                      // the same static schedule the head launch used
-    plan_schedule(p, 3, B, D, H, W);
+    plan_schedule(p, 3, B, D, H, W, true);
     DMB_REQUIRE(D <= 65535 && B <= 65535 && (int64_t)H * W < (int64_t)1 << 30, "head_gather: dimension too large");
     const dim3 grid((unsigned)cdiv((int64_t)H * W, 256), (unsigned)D, (unsigned)B);
     head_gather_kernel<<<grid, 256, 0, as_stream(stream)>>>(head_t, res, y, B, D, H, W, p.seg_len, p.nseg);
