@@ -674,8 +674,9 @@ def main():
         # NCCL_DEBUG (whatever the launcher set: INFO shows the communicator / NVLS lines) stays as it is; its log
         # goes to stderr so that stdout carries the ONE JSON line only
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        if "NCCL_DEBUG" not in os.environ:
-            # no choice made by the launcher: show the communicator set-up (ranks, transports, NVLS) on stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            # unset, or a quieter level (this image exports VERSION): raise it so that the communicator set-up (ranks,
+            # transports, NVLS) is on record -- on stderr, initialisation subsystem only
             os.environ["NCCL_DEBUG"] = "INFO"
             os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
